@@ -1,0 +1,13 @@
+"""Import shim: `import endo_b200` loads the package that lives in the (non-identifier)
+directory `endoscopydepthestimation-pytorch_b200/` next to this file."""
+import importlib.util
+import os
+import sys
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_pkg_dir = os.path.join(_here, "endoscopydepthestimation-pytorch_b200")
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_pkg_dir, "__init__.py"), submodule_search_locations=[_pkg_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

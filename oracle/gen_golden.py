@@ -1,0 +1,184 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (TEST INFRASTRUCTURE ONLY).
+
+Run in the build container, where /root/reference exists:   python -m oracle.gen_golden
+Imports /root/reference/models.py and /root/reference/losses.py read-only with the two shims
+of SURVEY.md section 8(c):
+  * torch.Tensor.cuda -> identity          (the layers hard-code .cuda(); no GPU here)
+  * torch.solve(B, A) -> (linalg.solve(A, B), None)   (models.py:392,493; removed in torch>=1.13)
+and records, for seeded synthetic inputs, the reference's outputs and gradients.  The
+fixtures are small (KBs): network parameters are regenerated from the seed by
+`oracle.net.init_state`, inputs by `endo_b200.synthetic.make_batch`.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.solve = lambda B, A: (torch.linalg.solve(A, B), None)
+    sys.path.insert(0, REF)
+    import models as ref_models  # noqa
+    import losses as ref_losses  # noqa
+    sys.path.pop(0)
+    return ref_models, ref_losses
+
+
+def np32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def main():
+    import endo_b200
+    from oracle import net as onet
+    ref_models, ref_losses = load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+
+    # ---------------------------------------------------------------- geometric layers + losses
+    for tag, (b, h, w, seed, ones) in {"geo_a": (2, 64, 96, 101, False), "geo_b": (3, 32, 64, 202, True)}.items():
+        batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, all_ones_boundary=ones, sparse_prob=0.02)
+        d1, d2 = endo_b200.synthetic.jitter_depths(batch, seed=seed + 1)
+        d1 = d1.clone().requires_grad_(True)
+        d2 = d2.clone().requires_grad_(True)
+        out = {}
+        scale = ref_models.DepthScalingLayer(epsilon=1e-8)
+        s1, std1 = scale([d1, batch["sparse_depths_1"], batch["sparse_depth_masks_1"]])
+        g = torch.Generator().manual_seed(seed + 7)
+        gs = torch.randn(s1.shape, generator=g)
+        (gd_scale,) = torch.autograd.grad((s1 * gs).sum(), d1, retain_graph=True)
+        out.update(scale_out=np32(s1), scale_std=np32(std1), scale_gout=np32(gs), scale_gd=np32(gd_scale))
+
+        flow_layer = ref_models.FlowfromDepthLayer()
+        f1 = flow_layer([d1, batch["boundaries"], batch["translations_1_wrt_2"], batch["rotations_1_wrt_2"],
+                         batch["intrinsics"]])
+        gf = torch.randn(f1.shape, generator=g)
+        (gd_flow,) = torch.autograd.grad((f1 * gf * batch["boundaries"]).sum(), d1, retain_graph=True)
+        out.update(flow_out=np32(f1), flow_gout=np32(gf * batch["boundaries"]), flow_gd=np32(gd_flow))
+
+        warp = ref_models.DepthWarpingLayer(epsilon=1e-8)
+        wd, inter = warp([d1, d2, batch["boundaries"], batch["translations_1_wrt_2"], batch["rotations_1_wrt_2"],
+                          batch["intrinsics"]])
+        gw = torch.randn(wd.shape, generator=g)
+        gd1_w, gd2_w = torch.autograd.grad((wd * gw).sum(), [d1, d2], retain_graph=True)
+        out.update(warp_out=np32(wd), warp_inter=np32(inter), warp_gout=np32(gw), warp_gd1=np32(gd1_w),
+                   warp_gd2=np32(gd2_w))
+
+        l1 = ref_losses.SparseMaskedL1Loss()
+        fm = batch["sparse_flow_masks_1"] * batch["boundaries"]
+        f1_leaf = f1.detach().clone().requires_grad_(True)
+        lv = l1([batch["sparse_flows_1"] * batch["boundaries"], f1_leaf * batch["boundaries"], fm])
+        (gf_l1,) = torch.autograd.grad(lv, f1_leaf, retain_graph=True)
+        out.update(l1_out=np32(lv), l1_gflow=np32(gf_l1))
+
+        ndl = ref_losses.NormalizedDistanceLoss(height=h, width=w)
+        wd_leaf = wd.detach().clone().requires_grad_(True)      # partial derivatives of the loss layer alone
+        nv = ndl([d1, wd_leaf, inter, batch["intrinsics"]])
+        gd_n, gw_n = torch.autograd.grad(nv, [d1, wd_leaf], retain_graph=True)
+        out.update(ndl_out=np32(nv), ndl_gd=np32(gd_n), ndl_gw=np32(gw_n))
+
+        sil = ref_losses.ScaleInvariantLoss(epsilon=1e-8)
+        sv = sil([d1, d2, batch["boundaries"]])
+        gp_s, gg_s = torch.autograd.grad(sv, [d1, d2])
+        out.update(sil_out=np32(sv), sil_gp=np32(gp_s), sil_gg=np32(gg_s))
+        np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), meta=np.array([b, h, w, seed, int(ones)]), **out)
+        print(tag, {k: v.shape for k, v in out.items()})
+
+    # ---------------------------------------------------------------- network fwd / bwd
+    b, h, w, seed = 2, 64, 96, 303
+    cfg = onet.FCDENSENET57
+    state = onet.init_state(cfg, seed=seed, perturb=True)
+    model = ref_models.FCDenseNet57(n_classes=1)
+    missing = model.load_state_dict(state, strict=True)
+    model.train()
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed)
+    x = (batch["boundaries"] * batch["colors_1"]).clone()
+    y = model(x)
+    g = torch.Generator().manual_seed(seed + 7)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    out = dict(y=np32(y), gy=np32(gy))
+    sd = model.state_dict()
+    names = [k for k in onet.param_shapes(cfg) if not onet.is_buffer(k)]
+    params = dict(model.named_parameters())
+    out["grad_l2"] = np.array([params[k].grad.double().norm().item() for k in names], dtype=np.float64)
+    out["grad_sum"] = np.array([params[k].grad.double().sum().item() for k in names], dtype=np.float64)
+    for k in ("firstconv.weight", "firstconv.bias", "finalConv.weight", "denseBlocksDown.0.layers.3.conv.weight",
+              "denseBlocksDown.0.layers.0.norm.weight", "denseBlocksDown.0.layers.0.norm.bias",
+              "transDownBlocks.2.conv.weight", "transDownBlocks.2.norm.weight",
+              "bottleneck.bottleneck.layers.1.conv.weight", "transUpBlocks.0.convTrans.1.weight",
+              "transUpBlocks.4.convTrans.1.bias", "denseBlocksUp.4.layers.3.conv.weight",
+              "denseBlocksUp.2.layers.0.norm.bias"):
+        out["grad::" + k] = np32(params[k].grad)
+    for k in ("denseBlocksDown.0.layers.0.norm.running_mean", "denseBlocksDown.0.layers.0.norm.running_var",
+              "transDownBlocks.4.norm.running_var", "denseBlocksUp.4.layers.3.norm.running_mean",
+              "bottleneck.bottleneck.layers.3.norm.running_var"):
+        out["buf::" + k] = np32(sd[k])
+    out["num_batches_tracked"] = np.array(int(sd["denseBlocksDown.0.layers.0.norm.num_batches_tracked"]))
+    # eval-mode forward (evaluate.py path)
+    model.eval()
+    with torch.no_grad():
+        out["y_eval"] = np32(model(x))
+    np.savez_compressed(os.path.join(OUT, "net_a.npz"), meta=np.array([b, h, w, seed]), **out)
+    print("net_a", y.shape, float(y.mean()))
+
+    # ---------------------------------------------------------------- one full train step (train.py:272-328)
+    b, h, w, seed = 2, 64, 64, 404
+    state = onet.init_state(cfg, seed=seed, perturb=False)          # reference init: kaiming / zero bias / gamma 1
+    model = ref_models.FCDenseNet57(n_classes=1)
+    model.load_state_dict(state, strict=True)
+    model.train()
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, sparse_prob=0.02)
+    opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
+    scale = ref_models.DepthScalingLayer(epsilon=1e-8)
+    warp = ref_models.DepthWarpingLayer(epsilon=1e-8)
+    flow_layer = ref_models.FlowfromDepthLayer()
+    l1 = ref_losses.SparseMaskedL1Loss()
+    ndl = ref_losses.NormalizedDistanceLoss(height=h, width=w)
+    rec = {"loss": [], "dcl": [], "sfl": [], "gnorm": []}
+    for it in range(2):
+        B = batch
+        c1 = B["boundaries"] * B["colors_1"]
+        c2 = B["boundaries"] * B["colors_2"]
+        p1 = model(c1)
+        p2 = model(c2)
+        s1, _ = scale([p1, B["sparse_depths_1"], B["sparse_depth_masks_1"]])
+        s2, _ = scale([p2, B["sparse_depths_2"], B["sparse_depth_masks_2"]])
+        f1 = flow_layer([s1, B["boundaries"], B["translations_1_wrt_2"], B["rotations_1_wrt_2"], B["intrinsics"]])
+        f2 = flow_layer([s2, B["boundaries"], B["translations_2_wrt_1"], B["rotations_2_wrt_1"], B["intrinsics"]])
+        m1 = B["sparse_flow_masks_1"] * B["boundaries"]
+        m2 = B["sparse_flow_masks_2"] * B["boundaries"]
+        sfl = 20.0 * 0.5 * (l1([B["sparse_flows_1"] * B["boundaries"], f1 * B["boundaries"], m1]) +
+                            l1([B["sparse_flows_2"] * B["boundaries"], f2 * B["boundaries"], m2]))
+        w21, i1 = warp([s1, s2, B["boundaries"], B["translations_1_wrt_2"], B["rotations_1_wrt_2"], B["intrinsics"]])
+        w12, i2 = warp([s2, s1, B["boundaries"], B["translations_2_wrt_1"], B["rotations_2_wrt_1"], B["intrinsics"]])
+        dcl = 5.0 * 0.5 * (ndl([s1, w21, i1, B["intrinsics"]]) + ndl([s2, w12, i2, B["intrinsics"]]))
+        loss = dcl + sfl
+        opt.zero_grad()
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        rec["loss"].append(loss.item()); rec["dcl"].append(dcl.item()); rec["sfl"].append(sfl.item())
+        rec["gnorm"].append(float(gn))
+        if it == 0:
+            first = dict(p1=np32(p1), s1=np32(s1), w21=np32(w21), i1=np32(i1), f1=np32(f1))
+    out = {k: np.array(v, dtype=np.float64) for k, v in rec.items()}
+    out.update(first)
+    params = dict(model.named_parameters())
+    out["w_l2_after"] = np.array([params[k].double().norm().item() for k in names], dtype=np.float64)
+    for k in ("firstconv.weight", "finalConv.weight", "denseBlocksUp.4.layers.3.conv.weight",
+              "denseBlocksDown.2.layers.1.norm.weight"):
+        out["after::" + k] = np32(params[k])
+    np.savez_compressed(os.path.join(OUT, "step_a.npz"), meta=np.array([b, h, w, seed]), **out)
+    print("step_a", rec)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,243 @@
+"""Oracle restatement of the FC-DenseNet depth network (TEST INFRASTRUCTURE ONLY).
+
+Restates /root/reference/models.py:19-208 as a pure function over a flat {name: tensor}
+state dict that uses the reference's own parameter / buffer names, so a reference checkpoint
+(`utils.py:674-682`) feeds it directly.  torch CPU tensors, any float dtype; gradients come
+from autograd.  BatchNorm is written out explicitly (batch mean, biased variance for the
+normalisation, unbiased variance + momentum 0.1 for the running buffers) instead of calling
+`F.batch_norm`, so that the semantics the CUDA path must match are visible here.
+"""
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+@dataclass(frozen=True)
+class NetConfig:
+    """Constructor arguments of `FCDenseNet.__init__` (models.py:101-103)."""
+    in_channels: int = 3
+    down_blocks: Tuple[int, ...] = (4, 4, 4, 4, 4)
+    up_blocks: Tuple[int, ...] = (4, 4, 4, 4, 4)
+    bottleneck_layers: int = 4
+    growth_rate: int = 12
+    out_chans_first_conv: int = 48
+    n_classes: int = 1
+
+
+FCDENSENET57 = NetConfig()                                              # models.py:190-194
+FCDENSENET67 = NetConfig(down_blocks=(5,) * 5, up_blocks=(5,) * 5,      # models.py:197-201
+                         bottleneck_layers=5, growth_rate=16)
+FCDENSENET103 = NetConfig(down_blocks=(4, 5, 7, 10, 12), up_blocks=(12, 10, 7, 5, 4),
+                          bottleneck_layers=15, growth_rate=16)         # models.py:204-208
+
+BN_EPS = 1e-5        # nn.BatchNorm2d default, models.py:22,59
+BN_MOMENTUM = 0.1
+
+
+def param_shapes(cfg: NetConfig = FCDENSENET57) -> "OrderedDict[str, Tuple[int, ...]]":
+    """Names and shapes of every parameter and buffer in `FCDenseNet.state_dict()` order.
+
+    Follows the registration order of models.py:111-169 (module tree: firstconv,
+    denseBlocksDown, transDownBlocks, bottleneck, transUpBlocks, denseBlocksUp, finalConv).
+    """
+    out: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+
+    def bn(prefix, c):
+        out[prefix + ".weight"] = (c,)
+        out[prefix + ".bias"] = (c,)
+        out[prefix + ".running_mean"] = (c,)
+        out[prefix + ".running_var"] = (c,)
+        out[prefix + ".num_batches_tracked"] = ()
+
+    def conv(prefix, cin, cout, k):
+        out[prefix + ".weight"] = (cout, cin, k, k)
+        out[prefix + ".bias"] = (cout,)
+
+    def dense_block(prefix, cin, n_layers):
+        for j in range(n_layers):                                        # models.py:35-37
+            bn(f"{prefix}.layers.{j}.norm", cin + j * cfg.growth_rate)
+            conv(f"{prefix}.layers.{j}.conv", cin + j * cfg.growth_rate, cfg.growth_rate, 3)
+
+    g = cfg.growth_rate
+    conv("firstconv", cfg.in_channels, cfg.out_chans_first_conv, 3)      # models.py:111-113
+    cur = cfg.out_chans_first_conv
+    skips: List[int] = []
+    down_specs = []
+    for i, n in enumerate(cfg.down_blocks):                              # models.py:122-127
+        down_specs.append((i, cur, n))
+        cur += g * n
+        skips.insert(0, cur)
+    for i, c, n in down_specs:
+        dense_block(f"denseBlocksDown.{i}", c, n)
+    c = cfg.out_chans_first_conv
+    for i, n in enumerate(cfg.down_blocks):
+        c += g * n
+        bn(f"transDownBlocks.{i}.norm", c)
+        conv(f"transDownBlocks.{i}.conv", c, c, 1)
+    dense_block("bottleneck.bottleneck", cur, cfg.bottleneck_layers)     # models.py:133-136
+    prev = g * cfg.bottleneck_layers
+    up_specs = []
+    for i, n in enumerate(cfg.up_blocks):                                # models.py:144-163
+        up_specs.append((i, prev, prev + skips[i], n))
+        prev = g * n
+    for i, p, c, n in up_specs:
+        conv(f"transUpBlocks.{i}.convTrans.1", p, p, 3)
+    for i, p, c, n in up_specs:
+        dense_block(f"denseBlocksUp.{i}", c, n)
+    last = up_specs[-1][2] + g * cfg.up_blocks[-1]
+    conv("finalConv", last, cfg.n_classes, 1)                            # models.py:167-169
+    return out
+
+
+def is_buffer(name: str) -> bool:
+    return name.endswith(("running_mean", "running_var", "num_batches_tracked"))
+
+
+def init_state(cfg: NetConfig = FCDENSENET57, seed: int = 0, dtype=torch.float32,
+               perturb: bool = False) -> Dict[str, torch.Tensor]:
+    """Kaiming-normal fan-in/relu conv weights, zero biases, BN gamma 1 (utils.py:655-671).
+
+    Uses numpy's RandomState (stable across library versions) rather than torch's RNG so the
+    golden fixtures can be regenerated from the seed alone.  `perturb=True` additionally
+    randomises biases, BN affine parameters and running buffers so that parity tests
+    exercise every term (the reference's init leaves them at 0 / 1).
+    """
+    rs = np.random.RandomState(seed)
+    state: Dict[str, torch.Tensor] = OrderedDict()
+    for name, shape in param_shapes(cfg).items():
+        if name.endswith("num_batches_tracked"):
+            state[name] = torch.zeros((), dtype=torch.long)
+        elif name.endswith("running_mean"):
+            v = rs.standard_normal(shape) * 0.1 if perturb else np.zeros(shape)
+            state[name] = torch.tensor(v, dtype=dtype)
+        elif name.endswith("running_var"):
+            v = 1.0 + 0.2 * rs.uniform(-1, 1, shape) if perturb else np.ones(shape)
+            state[name] = torch.tensor(v, dtype=dtype)
+        elif ".norm." in name and name.endswith(".weight"):
+            v = 1.0 + 0.2 * rs.uniform(-1, 1, shape) if perturb else np.ones(shape)
+            state[name] = torch.tensor(v, dtype=dtype)
+        elif name.endswith(".bias"):
+            v = 0.1 * rs.standard_normal(shape) if perturb else np.zeros(shape)
+            state[name] = torch.tensor(v, dtype=dtype)
+        else:  # conv weight: std = sqrt(2 / fan_in)
+            fan_in = shape[1] * shape[2] * shape[3]
+            v = rs.standard_normal(shape) * np.sqrt(2.0 / fan_in)
+            state[name] = torch.tensor(v, dtype=dtype)
+    return state
+
+
+def _batch_norm_train(x, prefix, state, new_buffers):
+    """nn.BatchNorm2d in training mode (models.py:22,59): normalise with the batch statistics
+    (biased variance) and record the running-buffer update (unbiased variance, momentum 0.1)."""
+    n = x.shape[0] * x.shape[2] * x.shape[3]
+    mean = x.mean(dim=(0, 2, 3))
+    var = ((x - mean[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
+    if new_buffers is not None:
+        with torch.no_grad():
+            rm = state[prefix + ".running_mean"] if prefix + ".running_mean" not in new_buffers \
+                else new_buffers[prefix + ".running_mean"]
+            rv = state[prefix + ".running_var"] if prefix + ".running_var" not in new_buffers \
+                else new_buffers[prefix + ".running_var"]
+            nb = state[prefix + ".num_batches_tracked"] if prefix + ".num_batches_tracked" not in new_buffers \
+                else new_buffers[prefix + ".num_batches_tracked"]
+            unbiased = var * (n / max(n - 1, 1))
+            new_buffers[prefix + ".running_mean"] = (1 - BN_MOMENTUM) * rm + BN_MOMENTUM * mean.detach()
+            new_buffers[prefix + ".running_var"] = (1 - BN_MOMENTUM) * rv + BN_MOMENTUM * unbiased.detach()
+            new_buffers[prefix + ".num_batches_tracked"] = nb + 1
+    xhat = (x - mean[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + BN_EPS)
+    return xhat * state[prefix + ".weight"][None, :, None, None] + state[prefix + ".bias"][None, :, None, None]
+
+
+def _batch_norm_eval(x, prefix, state):
+    rm, rv = state[prefix + ".running_mean"], state[prefix + ".running_var"]
+    xhat = (x - rm[None, :, None, None]) / torch.sqrt(rv[None, :, None, None] + BN_EPS)
+    return xhat * state[prefix + ".weight"][None, :, None, None] + state[prefix + ".bias"][None, :, None, None]
+
+
+def _bn(x, prefix, state, training, new_buffers):
+    if training:
+        return _batch_norm_train(x, prefix, state, new_buffers)
+    return _batch_norm_eval(x, prefix, state)
+
+
+def _dense_layer(x, prefix, state, training, new_buffers):
+    """BN -> ReLU -> conv3x3 pad 1 (models.py:19-28)."""
+    a = F.relu(_bn(x, prefix + ".norm", state, training, new_buffers))
+    return F.conv2d(a, state[prefix + ".conv.weight"], state[prefix + ".conv.bias"], padding=1)
+
+
+def _dense_block(x, prefix, n_layers, upsample, state, training, new_buffers):
+    """models.py:39-53: concat-grow; `upsample=True` returns only the new features."""
+    new = []
+    for j in range(n_layers):
+        out = _dense_layer(x, f"{prefix}.layers.{j}", state, training, new_buffers)
+        x = torch.cat([x, out], 1)
+        new.append(out)
+    return torch.cat(new, 1) if upsample else x
+
+
+def _transition_down(x, prefix, state, training, new_buffers):
+    """BN -> ReLU -> conv1x1 -> MaxPool2d(2) (models.py:56-67)."""
+    a = F.relu(_bn(x, prefix + ".norm", state, training, new_buffers))
+    y = F.conv2d(a, state[prefix + ".conv.weight"], state[prefix + ".conv.bias"])
+    return F.max_pool2d(y, 2)
+
+
+def _transition_up(x, skip, prefix, state):
+    """nearest x2 -> conv3x3 -> centre crop -> cat([up, skip]) (models.py:70-80, 93-97)."""
+    up = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)          # nn.Upsample nearest x2
+    out = F.conv2d(up, state[prefix + ".convTrans.1.weight"], state[prefix + ".convTrans.1.bias"], padding=1)
+    h, w = skip.shape[2], skip.shape[3]
+    x1 = (out.shape[3] - w) // 2
+    y1 = (out.shape[2] - h) // 2
+    out = out[:, :, y1:y1 + h, x1:x1 + w]
+    return torch.cat([out, skip], 1)
+
+
+def forward(state: Dict[str, torch.Tensor], x: torch.Tensor, cfg: NetConfig = FCDENSENET57,
+            training: bool = True, new_buffers: Dict[str, torch.Tensor] = None) -> torch.Tensor:
+    """`FCDenseNet.forward` (models.py:171-187).  `new_buffers`, if given, receives the updated
+    BN running buffers (chained, so calling twice with the same dict applies two updates,
+    like the two `net(...)` calls of train.py:276-277)."""
+    out = F.conv2d(x, state["firstconv.weight"], state["firstconv.bias"], padding=1)
+    skips = []
+    for i, n in enumerate(cfg.down_blocks):
+        out = _dense_block(out, f"denseBlocksDown.{i}", n, False, state, training, new_buffers)
+        skips.append(out)
+        out = _transition_down(out, f"transDownBlocks.{i}", state, training, new_buffers)
+    out = _dense_block(out, "bottleneck.bottleneck", cfg.bottleneck_layers, True, state, training, new_buffers)
+    for i, n in enumerate(cfg.up_blocks):
+        skip = skips.pop()
+        out = _transition_up(out, skip, f"transUpBlocks.{i}", state)
+        out = _dense_block(out, f"denseBlocksUp.{i}", n, i != len(cfg.up_blocks) - 1, state, training, new_buffers)
+    out = F.conv2d(out, state["finalConv.weight"], state["finalConv.bias"])
+    return torch.abs(out)                                                 # models.py:186
+
+
+def conv_flops_per_image(cfg: NetConfig, h: int, w: int) -> float:
+    """2*Cin*Cout*k*k*Hout*Wout summed over every conv."""
+    shapes = param_shapes(cfg)
+    total = 0.0
+    n_down = len(cfg.down_blocks)
+
+    def res(level):
+        return (h >> level) * (w >> level)
+
+    for name, s in shapes.items():
+        if not name.endswith(".weight") or len(s) != 4:
+            continue
+        co, ci, k, _ = s
+        if name.startswith("firstconv") or name.startswith("finalConv"):
+            lvl = 0
+        elif name.startswith("denseBlocksDown") or name.startswith("transDownBlocks"):
+            lvl = int(name.split(".")[1])
+        elif name.startswith("bottleneck"):
+            lvl = n_down
+        else:  # transUpBlocks.i / denseBlocksUp.i run at level n_down-1-i
+            lvl = n_down - 1 - int(name.split(".")[1])
+        total += 2.0 * ci * co * k * k * res(lvl)
+    return total
