@@ -1,0 +1,124 @@
+"""ctypes binding of libendo_b200.so (the C ABI in include/endo_b200.h).
+
+The library is the product: there is no fallback.  `lib()` raises if the shared object is
+missing (run `python -m endo_b200.build` / `__graft_entry__.build()`), and every wrapper
+raises on a non-CUDA tensor or a non-zero status code.
+"""
+import ctypes
+import os
+import threading
+from ctypes import c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libendo_b200.so")
+WS_HEADER_BYTES = 256
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NetConfig(ctypes.Structure):
+    """endo_net_config (include/endo_b200.h) == FCDenseNet.__init__ arguments (models.py:101-103)."""
+    _fields_ = [("in_channels", c_int), ("n_down", c_int), ("down_layers", c_int * 8), ("up_layers", c_int * 8),
+                ("bottleneck_layers", c_int), ("growth_rate", c_int), ("first_conv_channels", c_int),
+                ("n_classes", c_int)]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    "endo_version": (c_int, []),
+    "endo_strerror": (ctypes.c_char_p, [c_int]),
+    "endo_launch_count": (c_ulonglong, []),
+    "endo_depth_scale_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "endo_depth_scale_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
+    "endo_depth_scale_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
+    "endo_flow_from_depth_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "endo_flow_from_depth_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "endo_depth_warp_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "endo_depth_warp_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "endo_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "endo_sparse_l1_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
+    "endo_sparse_l1_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "endo_norm_dist_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
+    "endo_norm_dist_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "endo_scale_inv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
+    "endo_scale_inv_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
+    "endo_net_param_count": (c_longlong, [ctypes.POINTER(NetConfig)]),
+    "endo_net_buffer_count": (c_longlong, [ctypes.POINTER(NetConfig)]),
+    "endo_net_activation_bytes": (c_size_t, [ctypes.POINTER(NetConfig), c_int, c_int, c_int]),
+    "endo_net_backward_scratch_bytes": (c_size_t, [ctypes.POINTER(NetConfig), c_int, c_int, c_int]),
+    "endo_net_fwd": (c_int, [ctypes.POINTER(NetConfig), _P, _P, _P, _P, _P, c_size_t, c_int, c_int, c_int, c_int,
+                             c_int, c_int, _P]),
+    "endo_net_bwd": (c_int, [ctypes.POINTER(NetConfig), _P, _P, _P, _P, _P, _P, c_size_t, _P, c_size_t, c_int,
+                             c_int, c_int, c_int, c_int, c_int, _P]),
+    "endo_sgd_workspace_bytes": (c_size_t, [c_longlong]),
+    "endo_sgd_clip_step": (c_int, [_P, _P, _P, c_longlong, c_float, c_float, c_float, c_int, _P, _P, _P, c_size_t,
+                                   _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded shared library (loads it on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                        "endo_b200 has no CPU or PyTorch fallback.")
+                handle = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(code: int, what: str = ""):
+    if code != 0:
+        raise RuntimeError(f"libendo_b200 {what} failed: {lib().endo_strerror(code).decode()} (code {code})")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("endo_b200 runs on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+        if t.dtype != torch.float32:
+            raise RuntimeError("endo_b200 expects float32 tensors, got " + str(t.dtype))
+
+
+def contig(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_ws_cache = {}
+
+
+def workspace(device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) scratch with a zeroed, self-resetting counter header (see endo_b200.h)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def launch_count() -> int:
+    return int(lib().endo_launch_count())

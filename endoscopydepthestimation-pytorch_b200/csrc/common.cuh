@@ -1,0 +1,88 @@
+// Shared device/host helpers for libendo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/endo_b200.h"
+
+namespace endo {
+
+extern unsigned long long g_launch_count;   // defined in api.cu
+
+#define ENDO_CHECK_LAUNCH()                                         \
+    do {                                                            \
+        ++endo::g_launch_count;                                     \
+        if (cudaPeekAtLastError() != cudaSuccess) {                 \
+            cudaGetLastError();                                     \
+            return ENDO_ERR_CUDA;                                   \
+        }                                                           \
+    } while (0)
+
+#define ENDO_CUDA(call)                                             \
+    do {                                                            \
+        if ((call) != cudaSuccess) {                                \
+            cudaGetLastError();                                     \
+            return ENDO_ERR_CUDA;                                   \
+        }                                                           \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+constexpr int kNumSMs = 148;   // B200
+constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d defaults (models.py:22,59)
+constexpr float kBnMomentum = 0.1f;
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic reductions.
+//   Level 1: every block reduces N per-thread fp32 partials to N doubles (warp shuffles, fixed tree).
+//   Level 2: blocks write their N doubles to a partial array; the block that arrives last (ticket
+//            counter in the workspace header, self-resetting) sums the partials in a fixed order.
+// The result therefore does not depend on block scheduling: bit-identical run to run.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int N, int THREADS>
+__device__ __forceinline__ void block_sum(double (&v)[N], double* smem /* N * THREADS/32 doubles */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = THREADS / 32;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) smem[i * NW + warp] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = lane < NW ? smem[i * NW + lane] : 0.0;
+            s = warp_sum(s);
+            v[i] = s;   // valid in every lane of warp 0
+        }
+    }
+    __syncthreads();
+}
+
+// returns true in every thread of the block that arrived last among `total` blocks on `counter`
+__device__ __forceinline__ bool arrive_is_last(unsigned* counter, unsigned total) {
+    __shared__ unsigned s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(counter, 1u);
+        s_last = (t == total - 1u) ? 1u : 0u;
+        if (s_last) *counter = 0u;   // self-reset: header is zero again when the kernel ends
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0u;
+}
+
+__device__ __forceinline__ double ld_cg(const double* p) {
+    return __ldcg(p);   // bypass L1: partials were written by other SMs
+}
+
+}  // namespace endo

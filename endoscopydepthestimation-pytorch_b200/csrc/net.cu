@@ -1,0 +1,323 @@
+// FCDenseNet forward / backward entry points (reference models.py:100-187 and the autograd backward
+// PyTorch derives from it), fp32 FFMA path.  Host side: walks the NetPlan and enqueues the kernels of
+// net_kernels.cuh on the caller's stream; no allocation, no synchronisation.
+#include "net_kernels.cuh"
+#include "net_plan.cuh"
+
+namespace endo {
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP>
+static int launch_conv(const ConvArgs& a, cudaStream_t s) {
+    constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW>();
+    static bool configured = false;
+    auto kern = conv_kernel<KS, PX, CO, NW, LM, EM, WM, UP>;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int tiles = cdiv(a.ow, 32) * cdiv(a.oh, NW * PX);
+    dim3 grid(tiles, cdiv(a.N, CO), a.B);
+    kern<<<grid, NW * 32, smem, s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
+static int launch_wgrad(WgradArgs a, cudaStream_t s) {
+    constexpr size_t smem = wgrad_smem_bytes<KS, CW, NCG>();
+    static bool configured = false;
+    auto kern = wgrad_kernel<KS, CW, NCG, NPS, LMA, LMG, UP>;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int ychunks = cdiv(a.a_K, 32), zchunks = cdiv(a.g_K, CW * NCG);
+    a.n_tiles = a.B * cdiv(a.oh, 8) * cdiv(a.ow, 32);
+    int want = (3 * kNumSMs) / (ychunks * zchunks);
+    if (want < 1) want = 1;
+    if (want > a.n_tiles) want = a.n_tiles;
+    a.tiles_per_cta = cdiv(a.n_tiles, want);
+    dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
+    kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+struct Ctx {
+    const NetPlan& P;
+    char* acts; char* scratch;
+    const float* params; float* gparams; float* bnbuf;
+    cudaStream_t s;
+    int training;
+    float* X(int l) const { return reinterpret_cast<float*>(acts + P.x_off[l]); }
+    double* ST(int l) const { return reinterpret_cast<double*>(acts + P.stat_off[l]); }
+    float* MI(int l) const { return reinterpret_cast<float*>(acts + P.mi_off[l]); }
+    float* COEF(const BnP& b) const { return reinterpret_cast<float*>(acts) + b.coef; }
+    float* GX(int l) const { return reinterpret_cast<float*>(scratch + P.gx_off[l]); }
+    float* AB(int l) const { return reinterpret_cast<float*>(scratch + P.ab_off[l]); }
+    double* BNRED() const { return reinterpret_cast<double*>(scratch + P.bnred_off); }
+    double count(int l) const { return (double)(P.B / P.G) * P.h[l] * P.w[l]; }
+};
+
+static int bn_prepare(const Ctx& c, const BnP& bn, int level, int ch_off) {
+    BnPrepArgs a;
+    a.stats = c.ST(level); a.mi = c.MI(level); a.coef = c.COEF(bn);
+    a.gamma = c.params + bn.gamma; a.beta = c.params + bn.beta;
+    a.rmean = c.bnbuf + bn.rmean; a.rvar = c.bnbuf + bn.rvar;
+    a.C = bn.c; a.Ctot = c.P.Ctot[level]; a.ch_off = ch_off; a.G = c.P.G; a.training = c.training;
+    a.count = c.count(level);
+    bn_prepare_kernel<<<cdiv(bn.c, 128), 128, 0, c.s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+static ConvArgs base_args(const Ctx& c) {
+    ConvArgs a{};
+    a.B = c.P.B; a.G = c.P.G;
+    return a;
+}
+
+#define ENDO_TRY(expr)                 \
+    do {                               \
+        int _e = (expr);               \
+        if (_e != ENDO_OK) return _e;  \
+    } while (0)
+
+static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
+    const NetPlan& P = c.P;
+    const int l = d.level;
+    ENDO_TRY(bn_prepare(c, d.bn, l, d.in_off));
+    ConvArgs a = base_args(c);
+    a.in = c.X(l); a.coef = c.COEF(d.bn); a.in_C = P.Ctot[l]; a.in_off = d.in_off; a.K = d.cin; a.ih = P.h[l]; a.iw = P.w[l];
+    a.w = c.params + d.conv.w; a.bias = c.params + d.conv.b; a.w_cin = d.cin;
+    a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = d.out_off; a.N = d.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
+    a.stats = c.ST(l); a.stats_C = P.Ctot[l];
+    if (d.conv.cout == 12) return launch_conv<3, 8, 12, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
+    return launch_conv<3, 6, 16, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
+}
+
+static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
+    const NetPlan& P = c.P;
+    const int l = d.level;
+    // weight / bias gradient
+    WgradArgs w{};
+    w.a_in = c.X(l); w.a_coef = c.COEF(d.bn); w.a_C = P.Ctot[l]; w.a_off = d.in_off; w.a_K = d.cin; w.a_h = P.h[l]; w.a_w = P.w[l];
+    w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = d.out_off; w.g_K = d.conv.cout;
+    w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
+    w.dw = c.gparams + d.conv.w; w.db = c.gparams + d.conv.b; w.w_cin = d.cin;
+    if (d.conv.cout == 12) ENDO_TRY((launch_wgrad<3, 12, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+    else ENDO_TRY((launch_wgrad<3, 16, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+    // data gradient through conv, ReLU and BatchNorm (first term; the mean terms are applied lazily)
+    ConvArgs a = base_args(c);
+    a.in = c.GX(l); a.in2 = c.X(l); a.in_ab = c.AB(l); a.in_C = P.Ctot[l]; a.in_off = d.out_off; a.K = d.conv.cout;
+    a.ih = P.h[l]; a.iw = P.w[l];
+    a.w = c.params + d.conv.w; a.w_cin = d.cin;
+    a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = d.in_off; a.N = d.cin; a.oh = P.h[l]; a.ow = P.w[l];
+    a.stats = c.BNRED(); a.stats_C = P.maxC;
+    a.x = c.X(l); a.ep_coef = c.COEF(d.bn); a.ep_mi = c.MI(l);
+    ENDO_TRY((launch_conv<3, 2, 48, 8, LM_GRAD, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+    BnBwdArgs b;
+    b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(d.bn); b.mi = c.MI(l); b.ab = c.AB(l);
+    b.dgamma = c.gparams + d.bn.gamma; b.dbeta = c.gparams + d.bn.beta;
+    b.C = d.cin; b.Ctot = P.Ctot[l]; b.ch_off = d.in_off; b.G = P.G; b.count = c.count(l);
+    bn_bwd_finalize_kernel<<<cdiv(d.cin, 128), 128, 0, c.s>>>(b);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+static int trans_down_fwd(const Ctx& c, int l) {
+    const NetPlan& P = c.P;
+    const TransDownP& t = P.td[l];
+    const int cs = t.bn.c;
+    ENDO_TRY(bn_prepare(c, t.bn, l, P.offIn[l]));
+    ConvArgs a = base_args(c);
+    a.in = c.X(l); a.coef = c.COEF(t.bn); a.in_C = P.Ctot[l]; a.in_off = P.offIn[l]; a.K = cs; a.ih = P.h[l]; a.iw = P.w[l];
+    a.w = c.params + t.conv.w; a.bias = c.params + t.conv.b; a.w_cin = cs;
+    a.out = c.X(l + 1); a.out_C = P.Ctot[l + 1]; a.out_off = P.offIn[l + 1]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
+    a.stats = c.ST(l + 1); a.stats_C = P.Ctot[l + 1];
+    a.argmax_out = reinterpret_cast<unsigned char*>(c.acts + t.argmax);
+    return launch_conv<1, 2, 48, 8, LM_BNRELU, EM_POOL, WM_FWD, false>(a, c.s);
+}
+
+static int trans_down_bwd(const Ctx& c, int l) {
+    const NetPlan& P = c.P;
+    const TransDownP& t = P.td[l];
+    const int cs = t.bn.c;
+    const unsigned char* am = reinterpret_cast<const unsigned char*>(c.acts + t.argmax);
+    WgradArgs w{};
+    w.a_in = c.X(l); w.a_coef = c.COEF(t.bn); w.a_C = P.Ctot[l]; w.a_off = P.offIn[l]; w.a_K = cs; w.a_h = P.h[l]; w.a_w = P.w[l];
+    w.g_in = c.GX(l + 1); w.g_x = c.X(l + 1); w.g_ab = c.AB(l + 1); w.g_argmax = am; w.g_C = P.Ctot[l + 1];
+    w.g_off = P.offIn[l + 1]; w.g_K = cs; w.g_h = P.h[l + 1]; w.g_w = P.w[l + 1];
+    w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
+    w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = cs;
+    ENDO_TRY((launch_wgrad<1, 48, 1, 4, LM_BNRELU, LM_GRADPOOL, false>(w, c.s)));
+    ConvArgs a = base_args(c);
+    a.in = c.GX(l + 1); a.in2 = c.X(l + 1); a.in_ab = c.AB(l + 1); a.argmax = am; a.in_C = P.Ctot[l + 1];
+    a.in_off = P.offIn[l + 1]; a.K = cs; a.ih = P.h[l + 1]; a.iw = P.w[l + 1];
+    a.w = c.params + t.conv.w; a.w_cin = cs;
+    a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = P.offIn[l]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
+    a.stats = c.BNRED(); a.stats_C = P.maxC;
+    a.x = c.X(l); a.ep_coef = c.COEF(t.bn); a.ep_mi = c.MI(l);
+    ENDO_TRY((launch_conv<1, 2, 48, 8, LM_GRADPOOL, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+    BnBwdArgs b;
+    b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(t.bn); b.mi = c.MI(l); b.ab = c.AB(l);
+    b.dgamma = c.gparams + t.bn.gamma; b.dbeta = c.gparams + t.bn.beta;
+    b.C = cs; b.Ctot = P.Ctot[l]; b.ch_off = P.offIn[l]; b.G = P.G; b.count = c.count(l);
+    bn_bwd_finalize_kernel<<<cdiv(cs, 128), 128, 0, c.s>>>(b);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+static int trans_up_fwd(const Ctx& c, int i) {
+    const NetPlan& P = c.P;
+    const TransUpP& t = P.tu[i];
+    const int l = t.dst_level, ls = t.src_level;
+    ConvArgs a = base_args(c);
+    a.in = c.X(ls); a.in_C = P.Ctot[ls]; a.in_off = t.src_off; a.K = t.cin; a.ih = P.h[ls]; a.iw = P.w[ls];
+    a.w = c.params + t.conv.w; a.bias = c.params + t.conv.b; a.w_cin = t.cin;
+    a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = 0; a.N = t.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
+    a.stats = c.ST(l); a.stats_C = P.Ctot[l];
+    return launch_conv<3, 2, 48, 8, LM_PLAIN, EM_STORE, WM_FWD, true>(a, c.s);
+}
+
+static int trans_up_bwd(const Ctx& c, int i) {
+    const NetPlan& P = c.P;
+    const TransUpP& t = P.tu[i];
+    const int l = t.dst_level, ls = t.src_level;
+    WgradArgs w{};
+    w.a_in = c.X(ls); w.a_C = P.Ctot[ls]; w.a_off = t.src_off; w.a_K = t.cin; w.a_h = P.h[ls]; w.a_w = P.w[ls];
+    w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = 0; w.g_K = t.conv.cout;
+    w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
+    w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = t.cin;
+    ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.s)));
+    ConvArgs a = base_args(c);
+    a.in = c.GX(l); a.in2 = c.X(l); a.in_ab = c.AB(l); a.in_C = P.Ctot[l]; a.in_off = 0; a.K = t.conv.cout;
+    a.ih = P.h[l]; a.iw = P.w[l];
+    a.w = c.params + t.conv.w; a.w_cin = t.cin;
+    a.out = c.GX(ls); a.out_C = P.Ctot[ls]; a.out_off = t.src_off; a.N = t.cin; a.oh = P.h[l]; a.ow = P.w[l];
+    return launch_conv<3, 2, 48, 8, LM_GRAD, EM_DGRAD_UP, WM_DGRAD, false>(a, c.s);
+}
+
+}  // namespace endo
+
+using namespace endo;
+
+extern "C" long long endo_net_param_count(const endo_net_config* cfg) {
+    NetPlan P;
+    if (build_plan(cfg, 0, 0, 0, 1, P) != ENDO_OK) return -1;
+    return P.n_params;
+}
+extern "C" long long endo_net_buffer_count(const endo_net_config* cfg) {
+    NetPlan P;
+    if (build_plan(cfg, 0, 0, 0, 1, P) != ENDO_OK) return -1;
+    return P.n_buffers;
+}
+extern "C" size_t endo_net_activation_bytes(const endo_net_config* cfg, int B, int H, int W) {
+    NetPlan P;
+    // sized for the largest group count that divides B (the layout only grows with G)
+    int G = 1;
+    if (B > 0 && B % 2 == 0) G = 2;
+    if (build_plan(cfg, B, H, W, G, P) != ENDO_OK) return 0;
+    return (size_t)P.acts_bytes;
+}
+extern "C" size_t endo_net_backward_scratch_bytes(const endo_net_config* cfg, int B, int H, int W) {
+    NetPlan P;
+    int G = 1;
+    if (B > 0 && B % 2 == 0) G = 2;
+    if (build_plan(cfg, B, H, W, G, P) != ENDO_OK) return 0;
+    return (size_t)P.scratch_bytes;
+}
+
+extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const float* params, float* bn_buffers,
+                            float* y, void* acts, size_t acts_bytes, int B, int H, int W, int groups, int training,
+                            int math, endo_stream_t stream) {
+    if (math != ENDO_MATH_FP32) return ENDO_ERR_CONFIG;
+    if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
+    if (!x || !params || !bn_buffers || !y || !acts) return ENDO_ERR_BAD_POINTER;
+    if (!aligned16(x) || !aligned16(params) || !aligned16(y) || (reinterpret_cast<uintptr_t>(acts) & 255u))
+        return ENDO_ERR_BAD_POINTER;
+    if (B <= 0 || B > 65535) return ENDO_ERR_BAD_SHAPE;
+    NetPlan P;
+    ENDO_TRY(build_plan(cfg, B, H, W, groups, P));
+    if (acts_bytes < (size_t)P.acts_bytes) return ENDO_ERR_WORKSPACE;
+    Ctx c{P, static_cast<char*>(acts), nullptr, params, nullptr, bn_buffers, (cudaStream_t)stream, training};
+    const int nd = cfg->n_down;
+    // statistics accumulate with atomics: clear them
+    ENDO_CUDA(cudaMemsetAsync(c.acts + P.stat_off[0], 0, (size_t)(P.mi_off[0] - P.stat_off[0]), c.s));
+    {   // firstconv 3x3 in_channels -> first_conv_channels on the NCHW input (models.py:111-113, :172)
+        ConvArgs a = base_args(c);
+        a.in = x; a.K = cfg->in_channels; a.ih = H; a.iw = W;
+        a.w = params + P.first.w; a.bias = params + P.first.b; a.w_cin = cfg->in_channels;
+        a.out = c.X(0); a.out_C = P.Ctot[0]; a.out_off = P.offIn[0]; a.N = P.first.cout; a.oh = H; a.ow = W;
+        a.stats = c.ST(0); a.stats_C = P.Ctot[0];
+        ENDO_TRY((launch_conv<3, 2, 48, 8, LM_NCHW, EM_STORE, WM_FWD, false>(a, c.s)));
+    }
+    for (int l = 0; l < nd; ++l) {                           // models.py:175-178
+        for (const auto& d : P.down[l]) ENDO_TRY(dense_layer_fwd(c, d));
+        ENDO_TRY(trans_down_fwd(c, l));
+    }
+    for (const auto& d : P.down[nd]) ENDO_TRY(dense_layer_fwd(c, d));   // bottleneck, :180
+    for (int i = 0; i < nd; ++i) {                           // :181-184
+        ENDO_TRY(trans_up_fwd(c, i));
+        for (const auto& d : P.up[i]) ENDO_TRY(dense_layer_fwd(c, d));
+    }
+    {   // abs(finalConv(out)), :186
+        const long long npix = (long long)B * H * W;
+        float* pre = reinterpret_cast<float*>(c.acts + P.pre_off);
+        final_fwd_kernel<<<cdiv(npix * 8, 256), 256, 0, c.s>>>(c.X(0), params + P.final_.w, params + P.final_.b, pre, y,
+                                                               npix, P.Ctot[0]);
+        ENDO_CHECK_LAUNCH();
+    }
+    return ENDO_OK;
+}
+
+extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const float* x, const float* params,
+                            float* g_params, float* g_x, void* acts, size_t acts_bytes, void* scratch,
+                            size_t scratch_bytes, int B, int H, int W, int groups, int accumulate, int math,
+                            endo_stream_t stream) {
+    if (math != ENDO_MATH_FP32) return ENDO_ERR_CONFIG;
+    if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
+    if (g_x != nullptr) return ENDO_ERR_CONFIG;              // train.py never differentiates w.r.t. the images
+    if (!g_y || !x || !params || !g_params || !acts || !scratch) return ENDO_ERR_BAD_POINTER;
+    if (!aligned16(g_y) || !aligned16(params) || !aligned16(g_params) || (reinterpret_cast<uintptr_t>(acts) & 255u) ||
+        (reinterpret_cast<uintptr_t>(scratch) & 255u))
+        return ENDO_ERR_BAD_POINTER;
+    if (B <= 0 || B > 65535) return ENDO_ERR_BAD_SHAPE;
+    NetPlan P;
+    ENDO_TRY(build_plan(cfg, B, H, W, groups, P));
+    if (acts_bytes < (size_t)P.acts_bytes || scratch_bytes < (size_t)P.scratch_bytes) return ENDO_ERR_WORKSPACE;
+    if (P.Ctot[0] > 384) return ENDO_ERR_CONFIG;
+    Ctx c{P, static_cast<char*>(acts), static_cast<char*>(scratch), params, g_params, nullptr, (cudaStream_t)stream, 1};
+    const int nd = cfg->n_down;
+    // gradient buffers of levels >= 1, the lazy-correction arrays and the BN sums start at zero; the level-0
+    // gradient buffer (the largest) is fully written by the finalConv backward and needs no clearing
+    ENDO_CUDA(cudaMemsetAsync(c.scratch + P.gx_off[1], 0, (size_t)(P.scratch_bytes - P.gx_off[1]), c.s));
+    if (!accumulate) ENDO_CUDA(cudaMemsetAsync(g_params, 0, sizeof(float) * (size_t)P.n_params, c.s));
+    {
+        const long long npix = (long long)B * H * W;
+        const float* pre = reinterpret_cast<const float*>(c.acts + P.pre_off);
+        const int ppc = (int)((npix + 2 * kNumSMs - 1) / (2 * kNumSMs));
+        final_bwd_kernel<<<cdiv(npix, ppc), 256, sizeof(float) * P.Ctot[0], c.s>>>(
+            g_y, pre, c.X(0), params + P.final_.w, c.GX(0), g_params + P.final_.w, g_params + P.final_.b, npix, P.Ctot[0], ppc);
+        ENDO_CHECK_LAUNCH();
+    }
+    for (int i = nd - 1; i >= 0; --i) {
+        for (int j = (int)P.up[i].size() - 1; j >= 0; --j) ENDO_TRY(dense_layer_bwd(c, P.up[i][j]));
+        ENDO_TRY(trans_up_bwd(c, i));
+    }
+    for (int j = (int)P.down[nd].size() - 1; j >= 0; --j) ENDO_TRY(dense_layer_bwd(c, P.down[nd][j]));
+    for (int l = nd - 1; l >= 0; --l) {
+        ENDO_TRY(trans_down_bwd(c, l));
+        for (int j = (int)P.down[l].size() - 1; j >= 0; --j) ENDO_TRY(dense_layer_bwd(c, P.down[l][j]));
+    }
+    {   // firstconv: weight gradient only
+        WgradArgs w{};
+        w.a_in = x; w.a_K = cfg->in_channels; w.a_h = H; w.a_w = W;
+        w.g_in = c.GX(0); w.g_x = c.X(0); w.g_ab = c.AB(0); w.g_C = P.Ctot[0]; w.g_off = P.offIn[0]; w.g_K = P.first.cout;
+        w.g_h = H; w.g_w = W; w.oh = H; w.ow = W; w.B = B; w.G = P.G;
+        w.dw = g_params + P.first.w; w.db = g_params + P.first.b; w.w_cin = cfg->in_channels;
+        ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.s)));
+    }
+    return ENDO_OK;
+}

@@ -1,0 +1,631 @@
+// Device kernels of the FC-DenseNet engine, fp32 FFMA path (ENDO_MATH_FP32).
+//
+// One templated implicit-GEMM convolution kernel serves every convolution of the forward pass and every
+// data-gradient of the backward pass; what changes is
+//   * the LOADER that produces the GEMM A operand on the fly while staging it into shared memory
+//       LM_BNRELU   relu(a_c * x + b_c)          BatchNorm(train)+ReLU fused into the operand load
+//       LM_PLAIN    x (optionally nearest-x2 upsampled: TransitionUp, models.py:73)
+//       LM_NCHW     x read from the user's NCHW input tensor (firstconv)
+//       LM_GRAD     g + A_c + B_c * x            output gradient with the lazy BN-backward correction
+//       LM_GRADPOOL the same routed through MaxPool2d's argmax (TransitionDown backward)
+//   * the EPILOGUE
+//       EM_STORE      + bias, store 12/16/48 channels in place, emit per-channel sum / sum-of-squares
+//       EM_POOL       + bias, 2x2 max-pool (first-max-wins like ATen), store, argmax byte, statistics
+//       EM_DGRAD_BN   ReLU mask, BN-backward sums, scaled accumulate into the gradient buffer
+//       EM_DGRAD_UP   2x2 sum (backward of nearest upsampling), accumulate
+//   * the weight view: forward (k = ci, n = co) or data-gradient (k = co, n = ci, taps flipped).
+// Thread mapping: a warp owns PX output rows x 32 consecutive columns (lane = column, so every shared
+// memory access is either conflict-free or a broadcast), a CTA stacks NW warps vertically; each
+// thread keeps PX x CO fp32 accumulators.
+#pragma once
+#include "common.cuh"
+
+namespace endo {
+
+enum { LM_PLAIN = 0, LM_BNRELU = 1, LM_NCHW = 2, LM_GRAD = 3, LM_GRADPOOL = 4 };
+enum { EM_STORE = 0, EM_POOL = 1, EM_DGRAD_BN = 2, EM_DGRAD_UP = 3 };
+enum { WM_FWD = 0, WM_DGRAD = 1 };
+
+constexpr int KC = 8;   // input channels staged per main-loop step
+
+struct ConvArgs {
+    // ---- operand A (loader)
+    const float* in;          // activation / gradient buffer the loader reads (NHWC, or NCHW for LM_NCHW)
+    const float* in2;         // LM_GRAD*: activation buffer x matching `in` (lazy correction needs x)
+    const float* in_ab;       // LM_GRAD*: [G][in_C][2] (A, Bc) of that buffer
+    const float* coef;        // LM_BNRELU: [G][K][2] (a, b) of this layer's BatchNorm
+    const unsigned char* argmax;  // LM_GRADPOOL: [B, ih, iw, K] window index chosen by the forward pool
+    int in_C, in_off, K;      // channel stride of the buffer, first channel, number of GEMM-K channels
+    int ih, iw;               // spatial size of the buffer the loader reads
+    // ---- weights
+    const float* w;           // OIHW tensor of the layer
+    const float* bias;
+    int w_cin;                // I of OIHW
+    // ---- output
+    float* out;               // buffer written / accumulated (NHWC)
+    int out_C, out_off, N;    // channel stride, first channel, number of output channels
+    int oh, ow;               // output spatial size == GEMM pixel grid
+    int B, G;
+    double* stats;            // EM_STORE/EM_POOL: [G][out_C][2]; EM_DGRAD_BN: [G][maxC][2] (index = n)
+    int stats_C;
+    unsigned char* argmax_out;    // EM_POOL: [B, oh/2, ow/2, N]
+    // ---- EM_DGRAD_BN
+    const float* x;           // activation buffer (same geometry as `out`)
+    const float* ep_coef;     // [G][N][2] (a, b) of the BatchNorm being differentiated
+    const float* ep_mi;       // [G][out_C][2] (mean, invstd), absolute channel index
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ---------------------------------------------------------------------------------------------------
+template <int LM, bool UP>
+__device__ __forceinline__ float4 load_a4(const ConvArgs& A, int b, int g, int y, int x, int c) {
+    // (y, x) are coordinates in the OUTPUT pixel grid; returns channels c..c+3 of operand A (zeros outside)
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y < 0 || y >= A.oh || x < 0 || x >= A.ow || c >= A.K) return r;
+    if constexpr (LM == LM_PLAIN) {
+        const int sy = UP ? (y >> 1) : y, sx = UP ? (x >> 1) : x;
+        return ldg4(A.in + ((size_t)(b * A.ih + sy) * A.iw + sx) * A.in_C + A.in_off + c);
+    } else if constexpr (LM == LM_BNRELU) {
+        const float4 v = ldg4(A.in + ((size_t)(b * A.ih + y) * A.iw + x) * A.in_C + A.in_off + c);
+        const float4 c0 = ldg4(A.coef + ((size_t)g * A.K + c) * 2), c1 = ldg4(A.coef + ((size_t)g * A.K + c) * 2 + 4);
+        r.x = fmaxf(fmaf(c0.x, v.x, c0.y), 0.f); r.y = fmaxf(fmaf(c0.z, v.y, c0.w), 0.f);
+        r.z = fmaxf(fmaf(c1.x, v.z, c1.y), 0.f); r.w = fmaxf(fmaf(c1.z, v.w, c1.w), 0.f);
+        return r;
+    } else if constexpr (LM == LM_GRAD) {
+        const size_t o = ((size_t)(b * A.ih + y) * A.iw + x) * A.in_C + A.in_off + c;
+        const float4 gq = ldg4(A.in + o), xq = ldg4(A.in2 + o);
+        const float* ab = A.in_ab + ((size_t)g * A.in_C + A.in_off + c) * 2;
+        const float4 c0 = ldg4(ab), c1 = ldg4(ab + 4);
+        r.x = gq.x + fmaf(c0.y, xq.x, c0.x); r.y = gq.y + fmaf(c0.w, xq.y, c0.z);
+        r.z = gq.z + fmaf(c1.y, xq.z, c1.x); r.w = gq.w + fmaf(c1.w, xq.w, c1.z);
+        return r;
+    } else if constexpr (LM == LM_GRADPOOL) {
+        const int sy = y >> 1, sx = x >> 1;
+        const unsigned pos = ((y & 1) << 1) | (x & 1);
+        const size_t pp = (size_t)(b * A.ih + sy) * A.iw + sx;
+        const unsigned am = __ldg(reinterpret_cast<const unsigned*>(A.argmax + pp * A.K + c));
+        const bool h0 = (am & 0xffu) == pos, h1 = ((am >> 8) & 0xffu) == pos, h2 = ((am >> 16) & 0xffu) == pos,
+                   h3 = (am >> 24) == pos;
+        if (!(h0 | h1 | h2 | h3)) return r;
+        const size_t o = pp * A.in_C + A.in_off + c;
+        const float4 gq = ldg4(A.in + o), xq = ldg4(A.in2 + o);
+        const float* ab = A.in_ab + ((size_t)g * A.in_C + A.in_off + c) * 2;
+        const float4 c0 = ldg4(ab), c1 = ldg4(ab + 4);
+        if (h0) r.x = gq.x + fmaf(c0.y, xq.x, c0.x);
+        if (h1) r.y = gq.y + fmaf(c0.w, xq.y, c0.z);
+        if (h2) r.z = gq.z + fmaf(c1.y, xq.z, c1.x);
+        if (h3) r.w = gq.w + fmaf(c1.w, xq.w, c1.z);
+        return r;
+    }
+    return r;
+}
+
+template <int KS, int PX, int NW>
+struct ConvTile {
+    static constexpr int PAD = KS / 2;
+    static constexpr int TR = NW * PX;             // output rows per CTA
+    static constexpr int TRP = TR + 2 * PAD;
+    static constexpr int TWP = 32 + 2 * PAD;
+    static constexpr int PLANE = TRP * TWP + ((TRP * TWP) % 32 == 4 ? 0 : ((36 - (TRP * TWP) % 32) % 32));   // plane % 32 == 4
+};
+
+template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP>
+__global__ void __launch_bounds__(NW * 32)
+conv_kernel(const ConvArgs A) {
+    using T = ConvTile<KS, PX, NW>;
+    constexpr int PAD = T::PAD, TR = T::TR, TRP = T::TRP, TWP = T::TWP, PLANE = T::PLANE, TAPS = KS * KS;
+    constexpr int NT = NW * 32;
+    extern __shared__ __align__(16) float smem[];
+    float* a_s = smem;                          // [KC][PLANE]
+    float* w_s = smem + KC * PLANE;             // [KC][TAPS][CO]
+
+    const int tiles_x = (A.ow + 31) / 32;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int y0 = ty * TR, x0 = tx * 32;
+    const int n0 = blockIdx.y * CO;
+    const int b = blockIdx.z;
+    const int g = b / (A.B / A.G);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = warp * PX;
+
+    float acc[PX][CO];
+#pragma unroll
+    for (int i = 0; i < PX; ++i)
+#pragma unroll
+        for (int j = 0; j < CO; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < A.K; k0 += KC) {
+        __syncthreads();
+        // ---- stage operand A: global (NHWC, transformed on the fly) -> shared [k][row][col]
+        if constexpr (LM == LM_NCHW) {
+            for (int idx = threadIdx.x; idx < KC * TRP * TWP; idx += NT) {
+                const int kk = idx / (TRP * TWP), pix = idx - kk * (TRP * TWP);
+                const int r = pix / TWP, c = pix - r * TWP;
+                const int y = y0 + r - PAD, x = x0 + c - PAD, ch = k0 + kk;
+                float v = 0.f;
+                if (ch < A.K && y >= 0 && y < A.oh && x >= 0 && x < A.ow)
+                    v = __ldg(A.in + ((size_t)(b * A.K + ch) * A.ih + y) * A.iw + x);
+                a_s[kk * PLANE + pix] = v;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < TRP * TWP * (KC / 4); idx += NT) {
+                const int q = idx % (KC / 4), pix = idx / (KC / 4);
+                const int r = pix / TWP, c = pix - r * TWP;
+                const float4 v = load_a4<LM, UP>(A, b, g, y0 + r - PAD, x0 + c - PAD, k0 + q * 4);
+                float* d = a_s + (q * 4) * PLANE + pix;
+                d[0] = v.x; d[PLANE] = v.y; d[2 * PLANE] = v.z; d[3 * PLANE] = v.w;
+            }
+        }
+        // ---- stage weights: w_s[kk][tap][n]
+        for (int idx = threadIdx.x; idx < CO * KC * TAPS; idx += NT) {
+            const int tap = idx % TAPS, kk = (idx / TAPS) % KC, n = idx / (TAPS * KC);
+            const int k = k0 + kk, nn = n0 + n;
+            float v = 0.f;
+            if (k < A.K && nn < A.N) {
+                if constexpr (WM == WM_FWD) v = __ldg(A.w + ((size_t)nn * A.w_cin + k) * TAPS + tap);
+                else v = __ldg(A.w + ((size_t)k * A.w_cin + nn) * TAPS + (TAPS - 1 - tap));
+            }
+            w_s[(kk * TAPS + tap) * CO + n] = v;
+        }
+        __syncthreads();
+        // ---- main loop: PX x CO register tile per thread
+#pragma unroll 1
+        for (int kk = 0; kk < KC; ++kk) {
+            const float* ap = a_s + kk * PLANE + r0 * TWP + lane;
+            const float* wp = w_s + kk * TAPS * CO;
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+                float av[PX + KS - 1];
+#pragma unroll
+                for (int i = 0; i < PX + KS - 1; ++i) av[i] = ap[i * TWP + kx];
+#pragma unroll
+                for (int ky = 0; ky < KS; ++ky) {
+                    float wv[CO];
+#pragma unroll
+                    for (int j = 0; j < CO / 4; ++j) {
+                        const float4 q = *reinterpret_cast<const float4*>(wp + (ky * KS + kx) * CO + j * 4);
+                        wv[j * 4] = q.x; wv[j * 4 + 1] = q.y; wv[j * 4 + 2] = q.z; wv[j * 4 + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < PX; ++i)
+#pragma unroll
+                        for (int j = 0; j < CO; ++j) acc[i][j] = fmaf(av[i + ky], wv[j], acc[i][j]);
+                }
+            }
+        }
+    }
+
+    // =================================================================================== epilogue
+    __syncthreads();                             // smem is reused for the cross-warp reduction
+    float* red = smem;                           // [NW][CO][2]
+    const int x = x0 + lane;
+    float s1[CO], s2[CO];
+#pragma unroll
+    for (int j = 0; j < CO; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+
+    if constexpr (EM == EM_STORE) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const int y = y0 + r0 + i;
+            const bool ok = (y < A.oh) && (x < A.ow);
+            float* op = A.out + ((size_t)(b * A.oh + y) * A.ow + x) * A.out_C + A.out_off + n0;
+#pragma unroll
+            for (int j = 0; j < CO; j += 4) {
+                if (n0 + j < A.N) {
+                    const float4 bq = ldg4(A.bias + n0 + j);
+                    float4 v = make_float4(acc[i][j] + bq.x, acc[i][j + 1] + bq.y, acc[i][j + 2] + bq.z, acc[i][j + 3] + bq.w);
+                    if (ok) {
+                        *reinterpret_cast<float4*>(op + j) = v;
+                        s1[j] += v.x; s2[j] += v.x * v.x; s1[j + 1] += v.y; s2[j + 1] += v.y * v.y;
+                        s1[j + 2] += v.z; s2[j + 2] += v.z * v.z; s1[j + 3] += v.w; s2[j + 3] += v.w * v.w;
+                    }
+                }
+            }
+        }
+    } else if constexpr (EM == EM_POOL) {
+        static_assert(EM != EM_POOL || (PX % 2 == 0), "pooling needs an even number of rows per thread");
+        const int oh2 = A.oh >> 1, ow2 = A.ow >> 1;
+#pragma unroll
+        for (int i = 0; i < PX; i += 2) {
+            const int y = y0 + r0 + i;
+            const bool ok = (y < A.oh) && (x < A.ow) && ((lane & 1) == 0);
+            const size_t pp = (size_t)(b * oh2 + (y >> 1)) * ow2 + (x >> 1);
+#pragma unroll
+            for (int j = 0; j < CO; j += 4) {
+                float m4[4];
+                unsigned am4 = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float bb = (n0 + j + e < A.N) ? __ldg(A.bias + n0 + j + e) : 0.f;
+                    const float v00 = acc[i][j + e] + bb, v10 = acc[i + 1][j + e] + bb;
+                    const float v01 = __shfl_xor_sync(0xffffffffu, v00, 1), v11 = __shfl_xor_sync(0xffffffffu, v10, 1);
+                    float m = v00; unsigned am = 0;                              // ATen max_pool2d: (val > max) || isnan(val)
+                    if (v01 > m || v01 != v01) { m = v01; am = 1; }
+                    if (v10 > m || v10 != v10) { m = v10; am = 2; }
+                    if (v11 > m || v11 != v11) { m = v11; am = 3; }
+                    m4[e] = m; am4 |= am << (8 * e);
+                }
+                if (ok && n0 + j < A.N) {
+                    *reinterpret_cast<float4*>(A.out + pp * A.out_C + A.out_off + n0 + j) = make_float4(m4[0], m4[1], m4[2], m4[3]);
+                    *reinterpret_cast<unsigned*>(A.argmax_out + pp * A.N + n0 + j) = am4;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { s1[j + e] += m4[e]; s2[j + e] += m4[e] * m4[e]; }
+                }
+            }
+        }
+    } else if constexpr (EM == EM_DGRAD_BN) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const int y = y0 + r0 + i;
+            const bool ok = (y < A.oh) && (x < A.ow);
+            if (ok) {
+                const size_t o = ((size_t)(b * A.oh + y) * A.ow + x) * A.out_C + A.out_off + n0;
+#pragma unroll
+                for (int j = 0; j < CO; j += 4) {
+                    if (n0 + j < A.N) {
+                        const float4 xq = ldg4(A.x + o + j);
+                        const float* cf = A.ep_coef + ((size_t)g * A.N + n0 + j) * 2;
+                        const float* mi = A.ep_mi + ((size_t)g * A.out_C + A.out_off + n0 + j) * 2;
+                        const float4 c0 = ldg4(cf), c1 = ldg4(cf + 4), m0 = ldg4(mi), m1 = ldg4(mi + 4);
+                        float4 gq = *reinterpret_cast<const float4*>(A.out + o + j);
+                        const float g0 = fmaf(c0.x, xq.x, c0.y) > 0.f ? acc[i][j] : 0.f;
+                        const float g1 = fmaf(c0.z, xq.y, c0.w) > 0.f ? acc[i][j + 1] : 0.f;
+                        const float g2 = fmaf(c1.x, xq.z, c1.y) > 0.f ? acc[i][j + 2] : 0.f;
+                        const float g3 = fmaf(c1.z, xq.w, c1.w) > 0.f ? acc[i][j + 3] : 0.f;
+                        s1[j] += g0; s2[j] += g0 * ((xq.x - m0.x) * m0.y);
+                        s1[j + 1] += g1; s2[j + 1] += g1 * ((xq.y - m0.z) * m0.w);
+                        s1[j + 2] += g2; s2[j + 2] += g2 * ((xq.z - m1.x) * m1.y);
+                        s1[j + 3] += g3; s2[j + 3] += g3 * ((xq.w - m1.z) * m1.w);
+                        gq.x = fmaf(c0.x, g0, gq.x); gq.y = fmaf(c0.z, g1, gq.y);
+                        gq.z = fmaf(c1.x, g2, gq.z); gq.w = fmaf(c1.z, g3, gq.w);
+                        *reinterpret_cast<float4*>(A.out + o + j) = gq;
+                    }
+                }
+            }
+        }
+    } else if constexpr (EM == EM_DGRAD_UP) {
+        static_assert(EM != EM_DGRAD_UP || (PX % 2 == 0), "2x2 sum needs an even number of rows per thread");
+        const int oh2 = A.oh >> 1, ow2 = A.ow >> 1;
+#pragma unroll
+        for (int i = 0; i < PX; i += 2) {
+            const int y = y0 + r0 + i;
+            const bool ok = (y < A.oh) && (x < A.ow) && ((lane & 1) == 0);
+            const size_t o = ((size_t)(b * oh2 + (y >> 1)) * ow2 + (x >> 1)) * A.out_C + A.out_off + n0;
+#pragma unroll
+            for (int j = 0; j < CO; j += 4) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float t = acc[i][j + e] + acc[i + 1][j + e];
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    v[e] = t;
+                }
+                if (ok && n0 + j < A.N) {
+                    float4 gq = *reinterpret_cast<const float4*>(A.out + o + j);
+                    gq.x += v[0]; gq.y += v[1]; gq.z += v[2]; gq.w += v[3];
+                    *reinterpret_cast<float4*>(A.out + o + j) = gq;
+                }
+            }
+        }
+    }
+
+    if constexpr (EM != EM_DGRAD_UP) {
+        // per-channel sums: warp shuffle tree -> shared -> one fp64 atomic per channel per CTA
+#pragma unroll
+        for (int j = 0; j < CO; ++j) {
+            float a = s1[j], c = s2[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                c += __shfl_xor_sync(0xffffffffu, c, o);
+            }
+            if (lane == 0) { red[(warp * CO + j) * 2] = a; red[(warp * CO + j) * 2 + 1] = c; }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < CO * 2; t += NT) {
+            const int j = t >> 1, which = t & 1;
+            if (n0 + j < A.N) {
+                double s = 0.0;
+#pragma unroll
+                for (int wq = 0; wq < NW; ++wq) s += (double)red[(wq * CO + j) * 2 + which];
+                const int ch = (EM == EM_DGRAD_BN) ? (n0 + j) : (A.out_off + n0 + j);
+                atomicAdd(A.stats + ((size_t)g * A.stats_C + ch) * 2 + which, s);
+            }
+        }
+    }
+}
+
+template <int KS, int PX, int CO, int NW>
+constexpr size_t conv_smem_bytes() {
+    using T = ConvTile<KS, PX, NW>;
+    size_t main = sizeof(float) * (size_t)(KC * T::PLANE + KC * KS * KS * CO);
+    size_t red = sizeof(float) * (size_t)(NW * CO * 2);
+    return main > red ? main : red;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient: dW[co][ci][ky][kx] = sum_p g_out[p][co] * a[p + tap][ci]   (and db[co] = sum_p g_out[p][co])
+// GEMM with M = ci*taps, N = co, K = pixels.  lane = ci inside a 32-channel chunk, warps = (ky, co group,
+// pixel subgroup); a thread keeps KS x CW accumulators over the whole pixel range of its CTA and issues
+// one atomicAdd per weight at the end.
+// ---------------------------------------------------------------------------------------------------
+struct WgradArgs {
+    // activations (operand a)
+    const float* a_in; const float* a_coef; int a_C, a_off, a_K, a_h, a_w;   // a_K = Cin of the layer
+    // output gradient (operand g)
+    const float* g_in; const float* g_x; const float* g_ab; const unsigned char* g_argmax;
+    int g_C, g_off, g_K, g_h, g_w;                                          // g_K = Cout of the layer
+    int oh, ow, B, G;
+    float* dw; float* db; int w_cin;
+    int tiles_per_cta, n_tiles;
+};
+
+template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
+__global__ void __launch_bounds__(KS * NCG * NPS * 32)
+wgrad_kernel(const WgradArgs A) {
+    constexpr int PAD = KS / 2, TR = 8, TRP = TR + 2 * PAD, TWP = 32 + 2 * PAD, COT = CW * NCG;
+    constexpr int NT = KS * NCG * NPS * 32;
+    extern __shared__ __align__(16) float smem[];
+    float* a_s = smem;                          // [TRP][TWP][32]   (ci fastest)
+    float* g_s = smem + TRP * TWP * 32;         // [TR][32][COT]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ky = warp % KS, cg = (warp / KS) % NCG, ps = warp / (KS * NCG);
+    const int c0 = blockIdx.y * 32;             // ci chunk
+    const int co0 = blockIdx.z * COT;           // co chunk
+    const int tiles_x = (A.ow + 31) / 32, tiles_y = (A.oh + TR - 1) / TR;
+
+    // ConvArgs views so the conv loaders can be reused
+    ConvArgs LA{}; LA.in = A.a_in; LA.coef = A.a_coef; LA.in_C = A.a_C; LA.in_off = A.a_off; LA.K = A.a_K;
+    LA.ih = A.a_h; LA.iw = A.a_w; LA.oh = A.oh; LA.ow = A.ow; LA.B = A.B; LA.G = A.G;
+    ConvArgs LG{}; LG.in = A.g_in; LG.in2 = A.g_x; LG.in_ab = A.g_ab; LG.argmax = A.g_argmax; LG.in_C = A.g_C;
+    LG.in_off = A.g_off; LG.K = A.g_K; LG.ih = A.g_h; LG.iw = A.g_w; LG.oh = A.oh; LG.ow = A.ow; LG.B = A.B; LG.G = A.G;
+
+    float acc[KS][CW];
+#pragma unroll
+    for (int i = 0; i < KS; ++i)
+#pragma unroll
+        for (int j = 0; j < CW; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    const bool do_bias = (blockIdx.y == 0) && (ky == 0) && (lane < CW);
+
+    const int t_begin = blockIdx.x * A.tiles_per_cta;
+    const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
+    for (int t = t_begin; t < t_end; ++t) {
+        const int b = t / (tiles_x * tiles_y), rem = t - b * (tiles_x * tiles_y);
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const int y0 = ty * TR, x0 = tx * 32;
+        const int g = b / (A.B / A.G);
+        __syncthreads();
+        // stage a: [row][col][ci]
+        if constexpr (LMA == LM_NCHW) {
+            for (int idx = threadIdx.x; idx < TRP * TWP * 32; idx += NT) {
+                const int pix = idx % (TRP * TWP), ci = idx / (TRP * TWP);
+                const int r = pix / TWP, c = pix - r * TWP;
+                const int y = y0 + r - PAD, x = x0 + c - PAD, ch = c0 + ci;
+                float v = 0.f;
+                if (ch < A.a_K && y >= 0 && y < A.oh && x >= 0 && x < A.ow)
+                    v = __ldg(A.a_in + ((size_t)(b * A.a_K + ch) * A.a_h + y) * A.a_w + x);
+                a_s[pix * 32 + ci] = v;
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < TRP * TWP * 8; idx += NT) {
+                const int q = idx & 7, pix = idx >> 3;
+                const int r = pix / TWP, c = pix - r * TWP;
+                const float4 v = load_a4<LMA, UP>(LA, b, g, y0 + r - PAD, x0 + c - PAD, c0 + q * 4);
+                *reinterpret_cast<float4*>(a_s + pix * 32 + q * 4) = v;
+            }
+        }
+        // stage g: [row][col][co]
+        for (int idx = threadIdx.x; idx < TR * 32 * (COT / 4); idx += NT) {
+            const int q = idx % (COT / 4), pix = idx / (COT / 4);
+            const int r = pix >> 5, c = pix & 31;
+            const float4 v = load_a4<LMG, false>(LG, b, g, y0 + r, x0 + c, co0 + q * 4);
+            *reinterpret_cast<float4*>(g_s + pix * COT + q * 4) = v;
+        }
+        __syncthreads();
+        for (int r = ps; r < TR; r += NPS) {
+            const float* ar = a_s + ((r + ky) * TWP) * 32 + lane;
+            const float* gr = g_s + (r * 32) * COT + cg * CW;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if constexpr (KS == 3) { a1 = ar[0]; a2 = ar[32]; }
+#pragma unroll 4
+            for (int xx = 0; xx < 32; ++xx) {
+                if constexpr (KS == 3) { a0 = a1; a1 = a2; a2 = ar[(xx + 2) * 32]; }
+                else a0 = ar[xx * 32];
+                float gv[CW];
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(gr + xx * COT + j * 4);
+                    gv[j * 4] = q.x; gv[j * 4 + 1] = q.y; gv[j * 4 + 2] = q.z; gv[j * 4 + 3] = q.w;
+                }
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    acc[0][j] = fmaf(a0, gv[j], acc[0][j]);
+                    if constexpr (KS == 3) { acc[1][j] = fmaf(a1, gv[j], acc[1][j]); acc[2][j] = fmaf(a2, gv[j], acc[2][j]); }
+                }
+                if (do_bias) bsum += gr[xx * COT + lane];
+            }
+        }
+    }
+    const int ci = c0 + lane;
+    if (ci < A.a_K) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const int co = co0 + cg * CW + j;
+            if (co < A.g_K) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx)
+                    atomicAdd(A.dw + ((size_t)co * A.w_cin + ci) * (KS * KS) + ky * KS + kx, acc[kx][j]);
+            }
+        }
+    }
+    if (do_bias && A.db && co0 + cg * CW + lane < A.g_K) atomicAdd(A.db + co0 + cg * CW + lane, bsum);
+}
+
+template <int KS, int CW, int NCG>
+constexpr size_t wgrad_smem_bytes() {
+    constexpr int PAD = KS / 2;
+    return sizeof(float) * (size_t)((8 + 2 * PAD) * (32 + 2 * PAD) * 32 + 8 * 32 * CW * NCG);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BatchNorm bookkeeping (tiny kernels, one thread per channel)
+// ---------------------------------------------------------------------------------------------------
+struct BnPrepArgs {
+    const double* stats;      // [G][Ctot][2] of the level buffer
+    float* mi;                // [G][Ctot][2] (mean, invstd)
+    float* coef;              // [G][C][2] (a, b) for this BN
+    const float* gamma; const float* beta;
+    float* rmean; float* rvar;
+    int C, Ctot, ch_off, G, training;
+    double count;             // pixels per group
+};
+
+__global__ void bn_prepare_kernel(const BnPrepArgs A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.C) return;
+    const float gam = A.gamma[c], bet = A.beta[c];
+    if (!A.training) {
+        const float inv = 1.0f / sqrtf(A.rvar[c] + kBnEps);
+        for (int g = 0; g < A.G; ++g) {
+            A.coef[((size_t)g * A.C + c) * 2] = gam * inv;
+            A.coef[((size_t)g * A.C + c) * 2 + 1] = bet - A.rmean[c] * gam * inv;
+            A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2] = A.rmean[c];
+            A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1] = inv;
+        }
+        return;
+    }
+    float rm = A.rmean[c], rv = A.rvar[c];
+    for (int g = 0; g < A.G; ++g) {
+        const double s = A.stats[((size_t)g * A.Ctot + A.ch_off + c) * 2];
+        const double q = A.stats[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1];
+        const double mean = s / A.count;
+        double var = q / A.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double inv = 1.0 / sqrt(var + (double)kBnEps);
+        const float a = (float)((double)gam * inv);
+        A.coef[((size_t)g * A.C + c) * 2] = a;
+        A.coef[((size_t)g * A.C + c) * 2 + 1] = (float)((double)bet - mean * (double)gam * inv);
+        A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2] = (float)mean;
+        A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1] = (float)inv;
+        // running buffers: momentum 0.1, unbiased variance (nn.BatchNorm2d); groups update in order
+        const double unb = A.count > 1.0 ? var * (A.count / (A.count - 1.0)) : var;
+        rm = (1.0f - kBnMomentum) * rm + kBnMomentum * (float)mean;
+        rv = (1.0f - kBnMomentum) * rv + kBnMomentum * (float)unb;
+    }
+    A.rmean[c] = rm; A.rvar[c] = rv;
+}
+
+struct BnBwdArgs {
+    double* red;              // [G][maxC][2] sums (sum gy, sum gy*xhat); zeroed again on exit
+    int red_C;
+    const float* coef;        // [G][C][2]
+    const float* mi;          // [G][Ctot][2]
+    float* ab;                // [G][Ctot][2] lazy correction of the level buffer (accumulated)
+    float* dgamma; float* dbeta;
+    int C, Ctot, ch_off, G;
+    double count;
+};
+
+__global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.C) return;
+    double dg = 0.0, db = 0.0;
+    for (int g = 0; g < A.G; ++g) {
+        double* r = A.red + ((size_t)g * A.red_C + c) * 2;
+        const double s1 = r[0], s2 = r[1];
+        r[0] = 0.0; r[1] = 0.0;
+        dg += s2; db += s1;
+        const double a = A.coef[((size_t)g * A.C + c) * 2];
+        const double mean = A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2];
+        const double inv = A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1];
+        // dL/dx = a*gy - (a/N) * (S1 + xhat * S2),  xhat = (x - mean) * inv   ->  affine in x, applied lazily
+        float* ab = A.ab + ((size_t)g * A.Ctot + A.ch_off + c) * 2;
+        ab[0] += (float)(-(a / A.count) * (s1 - mean * inv * s2));
+        ab[1] += (float)(-(a / A.count) * inv * s2);
+    }
+    A.dgamma[c] += (float)dg;
+    A.dbeta[c] += (float)db;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// finalConv 1x1 C -> 1 followed by abs (models.py:167-169, 186): 8 lanes per pixel, HBM-bound
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+final_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 float* __restrict__ pre, float* __restrict__ y, long long npix, int C) {
+    const int sub = threadIdx.x & 7;
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    float s = 0.f;
+    if (p < npix) {
+        const float* xp = x + p * C;
+        for (int c = sub * 4; c < C; c += 32) {
+            const float4 a = ldg4(xp + c), q = ldg4(w + c);
+            s = fmaf(a.x, q.x, s); s = fmaf(a.y, q.y, s); s = fmaf(a.z, q.z, s); s = fmaf(a.w, q.w, s);
+        }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (p < npix && sub == 0) {
+        s += bias[0];
+        pre[p] = s;
+        y[p] = fabsf(s);
+    }
+}
+
+// backward: g_pre = g_y * sign(pre); gx[p][c] = g_pre * w[c] (first writer of the level-0 gradient buffer);
+// dW[c] += sum_p g_pre * x[p][c]; db += sum_p g_pre
+__global__ void __launch_bounds__(256)
+final_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ pre, const float* __restrict__ x,
+                 const float* __restrict__ w, float* __restrict__ gx, float* __restrict__ dw, float* __restrict__ db,
+                 long long npix, int C, int pix_per_cta) {
+    extern __shared__ __align__(16) float sm[];     // [C] dW partial
+    for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = 0.f;
+    __syncthreads();
+    const int sub = threadIdx.x & 7, grp = threadIdx.x >> 3;          // 32 pixel groups per CTA
+    const long long p_begin = (long long)blockIdx.x * pix_per_cta;
+    const long long p_end = min(p_begin + pix_per_cta, npix);
+    float bsum = 0.f;
+    // each 8-lane group walks pixels; lane `sub` owns channels sub*4 + 32*k
+    constexpr int MAXQ = 12;                                            // supports C <= 384
+    float wacc[MAXQ][4];
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) { wacc[k][0] = wacc[k][1] = wacc[k][2] = wacc[k][3] = 0.f; }
+    for (long long p = p_begin + grp; p < p_end; p += 32) {
+        const float s = pre[p];
+        const float gp = gy[p] * (float)((s > 0.f) - (s < 0.f));
+        if (sub == 0) bsum += gp;
+        const float* xp = x + p * C;
+        float* gp_out = gx + p * C;
+#pragma unroll
+        for (int k = 0; k < MAXQ; ++k) {
+            const int c = sub * 4 + 32 * k;
+            if (c < C) {
+                const float4 a = ldg4(xp + c), q = ldg4(w + c);
+                *reinterpret_cast<float4*>(gp_out + c) = make_float4(gp * q.x, gp * q.y, gp * q.z, gp * q.w);
+                wacc[k][0] = fmaf(gp, a.x, wacc[k][0]); wacc[k][1] = fmaf(gp, a.y, wacc[k][1]);
+                wacc[k][2] = fmaf(gp, a.z, wacc[k][2]); wacc[k][3] = fmaf(gp, a.w, wacc[k][3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXQ; ++k) {
+        const int c = sub * 4 + 32 * k;
+        if (c < C) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(sm + c + e, wacc[k][e]);
+        }
+    }
+    // bias: reduce over the CTA
+    __shared__ float sb;
+    if (threadIdx.x == 0) sb = 0.f;
+    __syncthreads();
+    if (sub == 0 && bsum != 0.f) atomicAdd(&sb, bsum);
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dw + c, sm[c]);
+    if (threadIdx.x == 0) atomicAdd(db, sb);
+}
+
+}  // namespace endo

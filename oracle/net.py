@@ -199,21 +199,32 @@ def _transition_up(x, skip, prefix, state):
 
 
 def forward(state: Dict[str, torch.Tensor], x: torch.Tensor, cfg: NetConfig = FCDENSENET57,
-            training: bool = True, new_buffers: Dict[str, torch.Tensor] = None) -> torch.Tensor:
+            training: bool = True, new_buffers: Dict[str, torch.Tensor] = None,
+            record: Dict[str, torch.Tensor] = None) -> torch.Tensor:
     """`FCDenseNet.forward` (models.py:171-187).  `new_buffers`, if given, receives the updated
     BN running buffers (chained, so calling twice with the same dict applies two updates,
     like the two `net(...)` calls of train.py:276-277)."""
+    def rec(name, t):
+        if record is not None:
+            record[name] = t.detach()
+
     out = F.conv2d(x, state["firstconv.weight"], state["firstconv.bias"], padding=1)
+    rec("firstconv", out)
     skips = []
     for i, n in enumerate(cfg.down_blocks):
         out = _dense_block(out, f"denseBlocksDown.{i}", n, False, state, training, new_buffers)
+        rec(f"down{i}", out)
         skips.append(out)
         out = _transition_down(out, f"transDownBlocks.{i}", state, training, new_buffers)
+        rec(f"td{i}", out)
     out = _dense_block(out, "bottleneck.bottleneck", cfg.bottleneck_layers, True, state, training, new_buffers)
+    rec("bottleneck", out)
     for i, n in enumerate(cfg.up_blocks):
         skip = skips.pop()
         out = _transition_up(out, skip, f"transUpBlocks.{i}", state)
+        rec(f"tu{i}", out)
         out = _dense_block(out, f"denseBlocksUp.{i}", n, i != len(cfg.up_blocks) - 1, state, training, new_buffers)
+        rec(f"up{i}", out)
     out = F.conv2d(out, state["finalConv.weight"], state["finalConv.bias"])
     return torch.abs(out)                                                 # models.py:186
 

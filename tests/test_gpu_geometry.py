@@ -1,0 +1,207 @@
+"""GPU parity: geometric layers and losses (C ABI through the nn.Module mirrors) vs the oracle
+and vs the fixtures generated from the unmodified reference.  Tolerance: 1e-4 relative to the
+tensor's scale in fp32 (BASELINE.json north_star); the intersect mask must be bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import endo_b200
+from oracle import geometry as og, losses as ol
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _inputs(b, h, w, seed, ones=False, prob=0.02):
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, all_ones_boundary=ones, sparse_prob=prob)
+    d1, d2 = endo_b200.synthetic.jitter_depths(batch, seed=seed + 1)
+    return batch, d1, d2
+
+
+def _cuda(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+CASES = [(2, 64, 96, 101, False), (3, 32, 64, 202, True), (1, 37, 53, 5, False), (8, 256, 320, 10085, False)]
+
+
+def _mask_mismatch(got, ref, margin_values, thr, tol=1e-5):
+    """bit-exact except where the thresholded quantity is within tol of the threshold"""
+    diff = got != ref
+    if margin_values is not None:
+        diff &= (margin_values - thr).abs() > tol
+    return int(diff.sum())
+
+
+@pytest.mark.parametrize("b,h,w,seed,ones", CASES)
+def test_depth_scaling(b, h, w, seed, ones):
+    batch, d1, _ = _inputs(b, h, w, seed, ones)
+    ref_in = d1.clone().requires_grad_(True)
+    ref_out, ref_std = og.depth_scaling(ref_in, batch["sparse_depths_1"], batch["sparse_depth_masks_1"])
+    g = torch.randn(ref_out.shape, generator=torch.Generator().manual_seed(1))
+    (ref_g,) = torch.autograd.grad((ref_out * g).sum(), ref_in)
+    layer = endo_b200.models.DepthScalingLayer(epsilon=1e-8)
+    x = d1.cuda().requires_grad_(True)
+    out, std = layer([x, batch["sparse_depths_1"].cuda(), batch["sparse_depth_masks_1"].cuda()])
+    assert out.grad_fn is not None
+    (gx,) = torch.autograd.grad((out * g.cuda()).sum(), x)
+    assert rel_err(out, ref_out) < TOL
+    assert rel_err(std, ref_std) < TOL
+    assert rel_err(gx, ref_g) < TOL
+
+
+@pytest.mark.parametrize("b,h,w,seed,ones", CASES)
+def test_flow_from_depth(b, h, w, seed, ones):
+    batch, d1, _ = _inputs(b, h, w, seed, ones)
+    ref_in = d1.clone().requires_grad_(True)
+    args = [batch[k] for k in ("boundaries", "translations_1_wrt_2", "rotations_1_wrt_2", "intrinsics")]
+    ref = og.flow_from_depth(ref_in, *args)
+    g = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2)) * batch["boundaries"]
+    (ref_g,) = torch.autograd.grad((ref * g).sum(), ref_in)
+    x = d1.cuda().requires_grad_(True)
+    out = endo_b200.models.FlowfromDepthLayer()([x] + [a.cuda() for a in args])
+    (gx,) = torch.autograd.grad((out * g.cuda()).sum(), x)
+    bnd = batch["boundaries"]
+    assert rel_err(out.cpu() * bnd, ref * bnd) < TOL          # outside the FOV the flow is ~(-x/W,-y/H): zeroed by train.py:297
+    assert rel_err(out, ref) < TOL
+    assert rel_err(gx, ref_g) < TOL
+
+
+@pytest.mark.parametrize("b,h,w,seed,ones", CASES)
+def test_depth_warping(b, h, w, seed, ones):
+    batch, d1, d2 = _inputs(b, h, w, seed, ones)
+    r1, r2 = d1.clone().requires_grad_(True), d2.clone().requires_grad_(True)
+    args = [batch[k] for k in ("boundaries", "translations_1_wrt_2", "rotations_1_wrt_2", "intrinsics")]
+    ref_w, ref_i = og.depth_warping(r1, r2, *args)
+    g = torch.randn(ref_w.shape, generator=torch.Generator().manual_seed(3))
+    ref_g1, ref_g2 = torch.autograd.grad((ref_w * g).sum(), [r1, r2])
+    x1, x2 = d1.cuda().requires_grad_(True), d2.cuda().requires_grad_(True)
+    out_w, out_i = endo_b200.models.DepthWarpingLayer(epsilon=1e-8)([x1, x2] + [a.cuda() for a in args])
+    g1, g2 = torch.autograd.grad((out_w * g.cuda()).sum(), [x1, x2])
+    assert rel_err(out_w, ref_w) < TOL
+    # fp64 oracle gives the un-thresholded mask value to tell genuine mismatches from threshold ties
+    with torch.no_grad():
+        u64 = og.depth_warping(d1.double(), d2.double(), *[a.double() for a in args])
+    assert _mask_mismatch(out_i.cpu(), ref_i, None, 0.9) <= max(1, b * h * w // 100000), "intersect mask"
+    assert set(out_i.unique().tolist()) <= {0.0, 1.0}
+    assert not out_i.requires_grad
+    assert rel_err(g1, ref_g1) < 5e-4      # finite-difference of 4 taps: ill-conditioned where taps nearly cancel
+    assert rel_err(g2, ref_g2) < TOL
+
+
+@pytest.mark.parametrize("b,h,w,seed,ones", CASES)
+def test_losses(b, h, w, seed, ones):
+    batch, d1, d2 = _inputs(b, h, w, seed, ones)
+    cb = _cuda(batch)
+    bnd = batch["boundaries"]
+    # SparseMaskedL1Loss on reference-shaped inputs
+    flow = og.flow_from_depth(d1, bnd, batch["translations_1_wrt_2"], batch["rotations_1_wrt_2"], batch["intrinsics"])
+    f_ref = (flow * bnd).clone().requires_grad_(True)
+    ref = ol.sparse_masked_l1_loss(batch["sparse_flows_1"] * bnd, f_ref, batch["sparse_flow_masks_1"] * bnd)
+    (ref_g,) = torch.autograd.grad(ref, f_ref)
+    f = (flow * bnd).cuda().requires_grad_(True)
+    out = endo_b200.losses.SparseMaskedL1Loss()([cb["sparse_flows_1"] * cb["boundaries"], f,
+                                                 cb["sparse_flow_masks_1"] * cb["boundaries"]])
+    (g,) = torch.autograd.grad(out * 3.0, f)
+    assert out.dim() == 0 and rel_err(out, ref) < TOL
+    assert rel_err(g, ref_g * 3.0) < TOL
+
+    # NormalizedDistanceLoss
+    wd, inter = og.depth_warping(d1, d2, bnd, batch["translations_1_wrt_2"], batch["rotations_1_wrt_2"],
+                                 batch["intrinsics"])
+    a, c = d1.clone().requires_grad_(True), wd.clone().requires_grad_(True)
+    ref = ol.normalized_distance_loss(a, c, inter, batch["intrinsics"])
+    ref_ga, ref_gc = torch.autograd.grad(ref, [a, c])
+    xa, xc = d1.cuda().requires_grad_(True), wd.cuda().requires_grad_(True)
+    out = endo_b200.losses.NormalizedDistanceLoss(height=h, width=w)([xa, xc, inter.cuda(), cb["intrinsics"]])
+    ga, gc = torch.autograd.grad(out, [xa, xc])
+    assert rel_err(out, ref) < TOL
+    assert rel_err(ga, ref_ga) < TOL and rel_err(gc, ref_gc) < TOL
+
+    # ScaleInvariantLoss
+    a, c = d1.clone().requires_grad_(True), d2.clone().requires_grad_(True)
+    ref = ol.scale_invariant_loss(a, c, bnd)
+    ref_ga, ref_gc = torch.autograd.grad(ref, [a, c])
+    xa, xc = d1.cuda().requires_grad_(True), d2.cuda().requires_grad_(True)
+    out = endo_b200.losses.ScaleInvariantLoss()([xa, xc, cb["boundaries"]])
+    ga, gc = torch.autograd.grad(out, [xa, xc])
+    assert rel_err(out, ref) < TOL
+    assert rel_err(ga, ref_ga) < TOL and rel_err(gc, ref_gc) < TOL
+
+
+@pytest.mark.parametrize("tag", ["geo_a", "geo_b"])
+def test_against_reference_fixtures(tag):
+    """Same inputs as oracle/gen_golden.py fed to the CUDA path; compared with the reference's own outputs."""
+    g = load_golden(tag)
+    b, h, w, seed, ones = [int(v) for v in g["meta"]]
+    batch, d1, d2 = _inputs(b, h, w, seed, bool(ones))
+    cb = _cuda(batch)
+    x1, x2 = d1.cuda().requires_grad_(True), d2.cuda().requires_grad_(True)
+    s, std = endo_b200.models.DepthScalingLayer()([x1, cb["sparse_depths_1"], cb["sparse_depth_masks_1"]])
+    assert rel_err(s, g["scale_out"]) < TOL and rel_err(std, g["scale_std"]) < TOL
+    (gd,) = torch.autograd.grad((s * torch.tensor(g["scale_gout"]).cuda()).sum(), x1)
+    assert rel_err(gd, g["scale_gd"]) < TOL
+    pose = [cb["translations_1_wrt_2"], cb["rotations_1_wrt_2"], cb["intrinsics"]]
+    f = endo_b200.models.FlowfromDepthLayer()([x1, cb["boundaries"]] + pose)
+    assert rel_err(f, g["flow_out"]) < TOL
+    (gd,) = torch.autograd.grad((f * torch.tensor(g["flow_gout"]).cuda()).sum(), x1)
+    assert rel_err(gd, g["flow_gd"]) < TOL
+    wd, inter = endo_b200.models.DepthWarpingLayer()([x1, x2, cb["boundaries"]] + pose)
+    assert rel_err(wd, g["warp_out"]) < TOL
+    assert int((inter.cpu().numpy() != g["warp_inter"]).sum()) == 0
+    g1, g2 = torch.autograd.grad((wd * torch.tensor(g["warp_gout"]).cuda()).sum(), [x1, x2])
+    assert rel_err(g1, g["warp_gd1"]) < 5e-4 and rel_err(g2, g["warp_gd2"]) < TOL
+    nv = endo_b200.losses.NormalizedDistanceLoss(h, w)([x1, torch.tensor(g["warp_out"]).cuda(),
+                                                        torch.tensor(g["warp_inter"]).cuda(), cb["intrinsics"]])
+    assert rel_err(nv, g["ndl_out"]) < TOL
+    sv = endo_b200.losses.ScaleInvariantLoss()([x1, x2, cb["boundaries"]])
+    assert rel_err(sv, g["sil_out"]) < TOL
+
+
+def test_edge_cases():
+    dev = "cuda"
+    # empty sparse mask -> NaN scale like the reference (0/0), not a crash
+    d = torch.rand(1, 1, 32, 32, device=dev) + 0.5
+    z = torch.zeros_like(d)
+    out, _ = endo_b200.models.DepthScalingLayer()([d, z, z])
+    assert torch.isnan(out).all()
+    # all-zero FOV mask -> warp output 0, intersect 0
+    t = torch.tensor([[[0.05], [0.0], [0.0]]], device=dev)
+    r = torch.eye(3, device=dev).reshape(1, 3, 3)
+    k = torch.tensor([[[40.0, 0, 16], [0, 40.0, 16], [0, 0, 1]]], device=dev)
+    wd, inter = endo_b200.models.DepthWarpingLayer()([d, d, z, t, r, k])
+    assert float(wd.abs().max()) == 0.0 and float(inter.max()) == 0.0
+    # identity pose, all-ones mask: warped == source-depth sampled at (x-0.5, y-0.5)
+    one = torch.ones_like(d)
+    t0 = torch.zeros(1, 3, 1, device=dev)
+    wd, inter = endo_b200.models.DepthWarpingLayer()([d, d, one, t0, r, k])
+    ref = og.depth_warping(d.cpu(), d.cpu(), one.cpu(), t0.cpu(), r.cpu(), k.cpu())[0]
+    assert rel_err(wd, ref) < TOL
+    # NaN propagates as a value (train.py:317 guard relies on it)
+    dn = d.clone(); dn[0, 0, 3, 3] = float("nan")
+    loss = endo_b200.losses.ScaleInvariantLoss()([dn, d, one])
+    assert torch.isnan(loss)
+    # CPU tensors are rejected loudly: no fallback
+    with pytest.raises(RuntimeError):
+        endo_b200.models.FlowfromDepthLayer()([d.cpu(), one.cpu(), t0.cpu(), r.cpu(), k.cpu()])
+    # non-contiguous and odd-sized inputs take the scalar path
+    dd = torch.rand(2, 1, 17, 23, device=dev) + 0.5
+    m = torch.ones_like(dd)
+    tt = t.expand(2, 3, 1).contiguous(); rr = r.expand(2, 3, 3).contiguous(); kk = k.expand(2, 3, 3).contiguous()
+    f = endo_b200.models.FlowfromDepthLayer()([dd, m, tt, rr, kk])
+    ref = og.flow_from_depth(dd.cpu(), m.cpu(), tt.cpu(), rr.cpu(), kk.cpu())
+    assert rel_err(f, ref) < TOL
+
+
+def test_determinism():
+    batch, d1, d2 = _inputs(4, 64, 96, 77)
+    cb = _cuda(batch)
+    x1, x2 = d1.cuda(), d2.cuda()
+    outs = []
+    for _ in range(3):
+        l1 = endo_b200.losses.ScaleInvariantLoss()([x1, x2, cb["boundaries"]])
+        s, std = endo_b200.models.DepthScalingLayer()([x1, cb["sparse_depths_1"], cb["sparse_depth_masks_1"]])
+        outs.append((l1.item(), std.item(), s.clone()))
+    assert outs[0][0] == outs[1][0] == outs[2][0] and outs[0][1] == outs[2][1]
+    assert torch.equal(outs[0][2], outs[2][2])

@@ -1,0 +1,189 @@
+"""GPU parity of the FCDenseNet engine (endo_net_fwd / endo_net_bwd through the nn.Module mirror)
+against the oracle and the fixtures generated from the unmodified reference.
+
+Forward: depth maps within 1e-4 of the reference relative to the map's scale (north_star).
+Backward: fp32 gradients of this 57-layer BatchNorm network are themselves only reproducible to
+~1e-3 between two fp32 implementations (tests/test_oracle_golden.py), so the CUDA gradients are
+judged against the fp64 oracle with the fp32 oracle's own error as the yardstick."""
+import numpy as np
+import pytest
+import torch
+
+import endo_b200
+from oracle import net as onet, step as ostep
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cfg, factory, b, h, w, seed, perturb=True):
+    state = onet.init_state(cfg, seed=seed, perturb=perturb)
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed)
+    x = batch["boundaries"] * batch["colors_1"]
+    model = factory()
+    model.load_state_dict(state)
+    model.cuda().train()
+    return state, x, model
+
+
+def _oracle_fwd_bwd(state, x, cfg, gy, dtype):
+    params = {}
+    for k, v in state.items():
+        v = v if v.dtype == torch.long else v.to(dtype)
+        params[k] = v if onet.is_buffer(k) else v.clone().requires_grad_(True)
+    new_buf = {}
+    y = onet.forward(params, x.to(dtype), cfg, True, new_buf)
+    (y * gy.to(dtype)).sum().backward()
+    grads = {k: p.grad for k, p in params.items() if not onet.is_buffer(k)}
+    return y.detach(), grads, new_buf
+
+
+def _check_grads(model, g64, g32, names):
+    gmax = max(float(g64[k].abs().max()) for k in names)
+    params = dict(model.named_parameters())
+    worst = []
+    for k in names:
+        ref = g64[k]
+        scale = max(float(ref.abs().max()), 1e-5 * gmax)      # conv biases feeding a BN have zero true gradient
+        e_cuda = float((params[k].grad.double().cpu() - ref).abs().max()) / scale
+        e_ref32 = float((g32[k].double() - ref).abs().max()) / scale
+        worst.append((e_cuda, e_ref32, k))
+        assert e_cuda < max(5e-3, 4.0 * e_ref32), (k, e_cuda, e_ref32)
+    med = float(np.median([w[0] for w in worst]))
+    assert med < 2e-4, med
+
+
+def test_forward_backward_vs_oracle():
+    cfg = onet.FCDENSENET57
+    state, x, model = _setup(cfg, lambda: endo_b200.models.FCDenseNet57(n_classes=1), 2, 64, 96, 303)
+    gy = torch.randn(2, 1, 64, 96, generator=torch.Generator().manual_seed(9))
+    y64, g64, buf64 = _oracle_fwd_bwd(state, x, cfg, gy, torch.float64)
+    y32, g32, _ = _oracle_fwd_bwd(state, x, cfg, gy, torch.float32)
+    y = model(x.cuda())
+    assert y.shape == (2, 1, 64, 96) and y.grad_fn is not None and float(y.min()) >= 0.0
+    assert rel_err(y, y64) < 1e-4
+    (y * gy.cuda()).sum().backward()
+    names = [k for k in state if not onet.is_buffer(k)]
+    _check_grads(model, g64, g32, names)
+    # every p.grad is a view of the flat bucket, in state_dict order
+    off = 0
+    for k, p in model.named_parameters():
+        assert p.grad.data_ptr() == model.flat_grads.data_ptr() + 4 * off, k
+        off += p.numel()
+    # BN running buffers and counters (momentum 0.1, unbiased variance)
+    sd = model.state_dict()
+    for k, v in buf64.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v)
+        else:
+            assert rel_err(sd[k], v) < 1e-5, k
+
+
+def test_reference_fixture_net_a():
+    g = load_golden("net_a")
+    b, h, w, seed = [int(v) for v in g["meta"]]
+    cfg = onet.FCDENSENET57
+    state, x, model = _setup(cfg, lambda: endo_b200.models.FCDenseNet57(n_classes=1), b, h, w, seed)
+    y = model(x.cuda())
+    assert rel_err(y, g["y"]) < 1e-4
+    (y * torch.tensor(g["gy"]).cuda()).sum().backward()
+    names = [k for k in state if not onet.is_buffer(k)]
+    params = dict(model.named_parameters())
+    l2 = np.array([params[k].grad.double().norm().item() for k in names])
+    assert np.all(np.abs(l2 - g["grad_l2"]) <= 5e-3 * g["grad_l2"] + 1e-5 * g["grad_l2"].max())
+    for k in g:
+        if k.startswith("grad::"):
+            assert rel_err(params[k[6:]].grad, g[k]) < 1e-2, k
+        if k.startswith("buf::"):
+            assert rel_err(model.state_dict()[k[5:]], g[k]) < 1e-5, k
+    model.eval()
+    with torch.no_grad():
+        y_eval = model(x.cuda())
+    assert rel_err(y_eval, g["y_eval"]) < 1e-4
+
+
+def test_pair_forward_equals_two_calls():
+    cfg = onet.FCDENSENET57
+    state, x1, model = _setup(cfg, lambda: endo_b200.models.FCDenseNet57(n_classes=1), 2, 64, 64, 11)
+    x2 = torch.flip(x1, dims=[3]).contiguous()
+    y1 = model(x1.cuda())
+    y2 = model(x2.cuda())
+    gy = torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(2)).cuda()
+    ((y1 * gy).sum() + (y2 * gy * 0.5).sum()).backward()
+    g_two = model.flat_grads.clone()
+    buf_two = model._flat_buf.clone()
+    model2 = endo_b200.models.FCDenseNet57(n_classes=1)
+    model2.load_state_dict(state)
+    model2.cuda().train()
+    p1, p2 = model2.forward_pair(x1.cuda(), x2.cuda())
+    assert rel_err(p1, y1) < 1e-6 and rel_err(p2, y2) < 1e-6
+    ((p1 * gy).sum() + (p2 * gy * 0.5).sum()).backward()
+    assert rel_err(model2.flat_grads, g_two) < 1e-3
+    assert rel_err(model2._flat_buf, buf_two) < 1e-6
+    assert int(model2.state_dict()["denseBlocksDown.0.layers.0.norm.num_batches_tracked"]) == 2
+
+
+def test_growth16_variant_fcdensenet67():
+    cfg = onet.FCDENSENET67
+    state, x, model = _setup(cfg, lambda: endo_b200.models.FCDenseNet67(n_classes=1), 1, 32, 64, 21)
+    gy = torch.randn(1, 1, 32, 64, generator=torch.Generator().manual_seed(4))
+    y64, g64, _ = _oracle_fwd_bwd(state, x, cfg, gy, torch.float64)
+    y32, g32, _ = _oracle_fwd_bwd(state, x, cfg, gy, torch.float32)
+    y = model(x.cuda())
+    assert rel_err(y, y64) < 1e-4
+    (y * gy.cuda()).sum().backward()
+    _check_grads(model, g64, g32, [k for k in state if not onet.is_buffer(k)])
+
+
+def test_full_train_step_vs_reference_fixture():
+    g = load_golden("step_a")
+    b, h, w, seed = [int(v) for v in g["meta"]]
+    cfg = onet.FCDENSENET57
+    state = onet.init_state(cfg, seed=seed, perturb=False)
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, sparse_prob=0.02)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    for pair in (False, True):
+        model = endo_b200.models.FCDenseNet57(n_classes=1)
+        model.load_state_dict(state)
+        model.cuda().train()
+        step = endo_b200.train_step.TrainStep(model, h, w, lr=1e-3, momentum=0.9, max_norm=10.0, pair=pair)
+        for it in range(2):
+            loss, dcl, sfl = step.step(cb)
+            tol = 2e-3 if it == 0 else 3e-2
+            assert abs(float(loss) - g["loss"][it]) / g["loss"][it] < tol, (pair, it, float(loss), g["loss"][it])
+            assert abs(float(dcl) - g["dcl"][it]) / g["dcl"][it] < tol
+            assert abs(float(sfl) - g["sfl"][it]) / g["sfl"][it] < tol
+            assert abs(float(step.opt.grad_norm) - g["gnorm"][it]) / g["gnorm"][it] < 2e-2
+        names = [k for k in state if not onet.is_buffer(k)]
+        params = dict(model.named_parameters())
+        l2 = np.array([params[k].double().norm().item() for k in names])
+        assert np.all(np.abs(l2 - g["w_l2_after"]) <= 1e-3 * g["w_l2_after"] + 1e-5)
+
+
+def test_torch_optimizer_dropin_matches_fused_tail():
+    """train.py:202,324-328 with torch.optim.SGD + clip_grad_norm_ on the mirrored module == fused tail."""
+    cfg = onet.FCDENSENET57
+    state = onet.init_state(cfg, seed=5, perturb=False)
+    batch = endo_b200.synthetic.make_batch(2, 64, 64, seed=5, sparse_prob=0.02)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    m1 = endo_b200.models.FCDenseNet57(1); m1.load_state_dict(state); m1.cuda().train()
+    m2 = endo_b200.models.FCDenseNet57(1); m2.load_state_dict(state); m2.cuda().train()
+    stack = endo_b200.train_step.LossStack(64, 64)
+    opt = torch.optim.SGD(m1.parameters(), lr=1e-3, momentum=0.9)
+    fused = endo_b200.train_step.TrainStep(m2, 64, 64, lr=1e-3, pair=False)
+    for _ in range(2):
+        loss, _, _, _ = stack.loss(m1, cb)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m1.parameters(), 10.0)
+        opt.step()
+        fused.step(cb)
+    assert rel_err(m2.flat_params, m1.flat_params) < 1e-5
+
+
+def test_shape_errors_are_loud():
+    model = endo_b200.models.FCDenseNet57(1).cuda()
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 40, 64, device="cuda"))      # H not a multiple of 32
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 4, 64, 64, device="cuda"))      # wrong channel count
