@@ -31,6 +31,10 @@ _SIGNATURES = {
     "endo_version": (c_int, []),
     "endo_strerror": (ctypes.c_char_p, [c_int]),
     "endo_launch_count": (c_ulonglong, []),
+    "endo_prof_enable": (None, [c_int]),
+    "endo_prof_categories": (c_int, []),
+    "endo_prof_category_name": (ctypes.c_char_p, [c_int]),
+    "endo_prof_collect": (c_int, [_P, _P]),
     "endo_depth_scale_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "endo_depth_scale_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
     "endo_depth_scale_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P, c_size_t, _P]),
@@ -122,3 +126,25 @@ def workspace(device, nbytes: int) -> torch.Tensor:
 
 def launch_count() -> int:
     return int(lib().endo_launch_count())
+
+
+class profile:
+    """Context manager around endo_prof_*: per-category device milliseconds and launch-site counts."""
+
+    def __enter__(self):
+        lib().endo_prof_collect(None, None)      # drop stale records
+        lib().endo_prof_enable(1)
+        self.ms, self.counts = {}, {}
+        return self
+
+    def __exit__(self, *exc):
+        l = lib()
+        l.endo_prof_enable(0)
+        n = l.endo_prof_categories()
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_ulonglong * n)()
+        check(l.endo_prof_collect(ms, cnt), "prof_collect")
+        for i in range(n):
+            name = l.endo_prof_category_name(i).decode()
+            self.ms[name], self.counts[name] = float(ms[i]), int(cnt[i])
+        return False

@@ -282,6 +282,7 @@ extern "C" size_t endo_loss_workspace_bytes(int B, int H, int W) {
     unsigned* counter = reinterpret_cast<unsigned*>(ws);                                              \
     double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + ENDO_WS_HEADER_BYTES); \
     cudaStream_t s = (cudaStream_t)stream;                                                            \
+    ProfScope prof(PC_LOSS, s);                                                                       \
     const int HW = H * W;                                                                             \
     dim3 rgrid(loss_nblk(HW), B)
 
@@ -303,6 +304,7 @@ extern "C" int endo_sparse_l1_bwd(const float* g_loss, const float* flows, const
                                   int B, int H, int W, float eps, endo_stream_t stream) {
     REQ_DIMS(B, H, W); REQ(g_loss); REQ(flows); REQ(flows_from_depth); REQ(masks); REQ(stats); REQ(g_flows_from_depth);
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PC_LOSS, s);
     const int HW = H * W;
     if (v4ok(HW, W, {flows, flows_from_depth, masks, g_flows_from_depth, g_flows}))
         sparse_l1_bwd_kernel<4><<<dim3(cdiv(HW, kLT * 4), B), kLT, 0, s>>>(g_loss, flows, flows_from_depth, masks, stats,
@@ -333,6 +335,7 @@ extern "C" int endo_norm_dist_bwd(const float* g_loss, const float* depth, const
     (void)eps;
     REQ_DIMS(B, H, W); REQ(g_loss); REQ(depth); REQ(warped); REQ(intersect); REQ(K); REQ(stats); REQ(g_depth); REQ(g_warped);
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PC_LOSS, s);
     const int HW = H * W;
     if (v4ok(HW, W, {depth, warped, intersect, g_depth, g_warped}))
         norm_dist_bwd_kernel<4><<<dim3(cdiv(HW, kLT * 4), B), kLT, 0, s>>>(g_loss, depth, warped, intersect, K, stats,
@@ -362,6 +365,7 @@ extern "C" int endo_scale_inv_bwd(const float* g_loss, const float* pred, const 
                                   endo_stream_t stream) {
     REQ_DIMS(B, H, W); REQ(g_loss); REQ(pred); REQ(goal); REQ(boundaries); REQ(stats); REQ(g_pred);
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PC_LOSS, s);
     const int HW = H * W;
     if (v4ok(HW, W, {pred, goal, boundaries, g_pred, g_goal}))
         scale_inv_bwd_kernel<4><<<dim3(cdiv(HW, kLT * 4), B), kLT, 0, s>>>(g_loss, pred, goal, boundaries, stats, g_pred,

@@ -18,6 +18,7 @@ static int launch_conv(const ConvArgs& a, cudaStream_t s) {
     }
     const int tiles = cdiv(a.ow, 32) * cdiv(a.oh, NW * PX);
     dim3 grid(tiles, cdiv(a.N, CO), a.B);
+    ProfScope prof(WM == WM_DGRAD ? PC_DGRAD : ((LM == LM_BNRELU && EM == EM_STORE) ? PC_CONV_DENSE_FWD : PC_CONV_TRANS_FWD), s);
     kern<<<grid, NW * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -39,6 +40,7 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
     if (want > a.n_tiles) want = a.n_tiles;
     a.tiles_per_cta = cdiv(a.n_tiles, want);
     dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
+    ProfScope prof(PC_WGRAD, s);
     kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -67,6 +69,7 @@ static int bn_prepare(const Ctx& c, const BnP& bn, int level, int ch_off) {
     a.rmean = c.bnbuf + bn.rmean; a.rvar = c.bnbuf + bn.rvar;
     a.C = bn.c; a.Ctot = c.P.Ctot[level]; a.ch_off = ch_off; a.G = c.P.G; a.training = c.training;
     a.count = c.count(level);
+    ProfScope prof(PC_BN, c.s);
     bn_prepare_kernel<<<cdiv(bn.c, 128), 128, 0, c.s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -121,6 +124,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(d.bn); b.mi = c.MI(l); b.ab = c.AB(l);
     b.dgamma = c.gparams + d.bn.gamma; b.dbeta = c.gparams + d.bn.beta;
     b.C = d.cin; b.Ctot = P.Ctot[l]; b.ch_off = d.in_off; b.G = P.G; b.count = c.count(l);
+    ProfScope prof(PC_BN, c.s);
     bn_bwd_finalize_kernel<<<cdiv(d.cin, 128), 128, 0, c.s>>>(b);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -164,6 +168,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(t.bn); b.mi = c.MI(l); b.ab = c.AB(l);
     b.dgamma = c.gparams + t.bn.gamma; b.dbeta = c.gparams + t.bn.beta;
     b.C = cs; b.Ctot = P.Ctot[l]; b.ch_off = P.offIn[l]; b.G = P.G; b.count = c.count(l);
+    ProfScope prof(PC_BN, c.s);
     bn_bwd_finalize_kernel<<<cdiv(cs, 128), 128, 0, c.s>>>(b);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -265,6 +270,7 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
     {   // abs(finalConv(out)), :186
         const long long npix = (long long)B * H * W;
         float* pre = reinterpret_cast<float*>(c.acts + P.pre_off);
+        ProfScope prof(PC_FINAL, c.s);
         final_fwd_kernel<<<cdiv(npix * 8, 256), 256, 0, c.s>>>(c.X(0), params + P.final_.w, params + P.final_.b, pre, y,
                                                                npix, P.Ctot[0]);
         ENDO_CHECK_LAUNCH();
@@ -298,6 +304,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         const long long npix = (long long)B * H * W;
         const float* pre = reinterpret_cast<const float*>(c.acts + P.pre_off);
         const int ppc = (int)((npix + 2 * kNumSMs - 1) / (2 * kNumSMs));
+        ProfScope prof(PC_FINAL, c.s);
         final_bwd_kernel<<<cdiv(npix, ppc), 256, sizeof(float) * P.Ctot[0], c.s>>>(
             g_y, pre, c.X(0), params + P.final_.w, c.GX(0), g_params + P.final_.w, g_params + P.final_.b, npix, P.Ctot[0], ppc);
         ENDO_CHECK_LAUNCH();

@@ -93,6 +93,7 @@ extern "C" int endo_sgd_clip_step(float* params, float* grads, float* momentum_b
     if (!aligned16(params) || !aligned16(grads) || !aligned16(momentum_buf)) return ENDO_ERR_BAD_POINTER;
     if (!ws || ws_bytes < endo_sgd_workspace_bytes(n) || !aligned16(ws)) return ENDO_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PC_OPT, s);
     unsigned* counter = reinterpret_cast<unsigned*>(ws) + 8;    // separate ticket from the loss kernels
     double* total = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + ENDO_WS_HEADER_BYTES);
     double* partials = total + 2;

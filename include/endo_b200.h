@@ -48,6 +48,15 @@ int endo_version(void);                 /* 100 * major + minor */
 const char* endo_strerror(int code);
 /* number of kernels this library has launched in the calling process (monotonic; for bench.py's gpu_launches) */
 unsigned long long endo_launch_count(void);
+/* Per-category device timing for bench.py's roofline: while enabled, each entry point brackets its launches
+ * with CUDA events on the launching stream; endo_prof_collect() synchronises the device, ADDS the elapsed
+ * milliseconds / launch-site counts per category to ms[] / counts[] (endo_prof_categories() entries) and
+ * clears the records.  Categories that enqueue several kernels back to back (depth_scale, optimizer) are
+ * timed as one span. */
+void endo_prof_enable(int on);
+int endo_prof_categories(void);
+const char* endo_prof_category_name(int category);
+int endo_prof_collect(double* ms, unsigned long long* counts);
 
 /* ------------------------------------------------------------------------------------------------
  * DepthScalingLayer.forward  (models.py:346-363)   x = [depth, sparse_depth, sparse_mask]

@@ -60,6 +60,16 @@ def flow_from_depth(depth, mask, translation, rotation, intrinsics):
     return torch.cat([(u2 - x) / float(w), (v2 - y) / float(h)], dim=1)          # :449-451
 
 
+LIBRARY_OPS = False   # see oracle/net.py: call F.grid_sample like the reference (CPU-baseline timing only)
+
+
+def _bilinear_library(src, u, v):
+    b, _, h, w = src.shape
+    grid = torch.cat([(2.0 * (u.reshape(b, h, w, 1) / float(w)) - 1.0), (2.0 * (v.reshape(b, h, w, 1) / float(h)) - 1.0)],
+                     dim=-1)
+    return torch.nn.functional.grid_sample(src, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+
+
 def bilinear_zero_pad(src, u, v):
     """`_bilinear_interpolate` (models.py:325-336) restated on pixel coordinates.
 
@@ -67,6 +77,8 @@ def bilinear_zero_pad(src, u, v):
     grid_sample(align_corners=False, zeros)) => sample location ix = u-0.5, iy = v-0.5, four
     taps, a tap contributes only when it lies inside the image.
     """
+    if LIBRARY_OPS:
+        return _bilinear_library(src, u, v)
     b, _, h, w = src.shape
     # grid_sample un-normalisation: ix = ((g + 1) * W - 1) / 2 with g = 2u/W - 1
     gx = 2.0 * (u / float(w)) - 1.0

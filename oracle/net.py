@@ -158,7 +158,29 @@ def _batch_norm_eval(x, prefix, state):
     return xhat * state[prefix + ".weight"][None, :, None, None] + state[prefix + ".bias"][None, :, None, None]
 
 
+# When True the oracle calls the same torch library ops the reference calls (F.batch_norm, F.interpolate)
+# instead of the written-out restatements above.  Same semantics (tests/test_oracle_golden.py checks both);
+# used for the CPU-baseline timing in bench.py so that the reported baseline is not slowed down by the
+# explicit multi-pass BatchNorm of the restatement.
+LIBRARY_OPS = False
+
+
+def _batch_norm_library(x, prefix, state, training, new_buffers):
+    if not training:
+        return F.batch_norm(x, state[prefix + ".running_mean"], state[prefix + ".running_var"],
+                            state[prefix + ".weight"], state[prefix + ".bias"], False, BN_MOMENTUM, BN_EPS)
+    rm = new_buffers.get(prefix + ".running_mean", state[prefix + ".running_mean"]).clone()
+    rv = new_buffers.get(prefix + ".running_var", state[prefix + ".running_var"]).clone()
+    nb = new_buffers.get(prefix + ".num_batches_tracked", state[prefix + ".num_batches_tracked"])
+    y = F.batch_norm(x, rm, rv, state[prefix + ".weight"], state[prefix + ".bias"], True, BN_MOMENTUM, BN_EPS)
+    new_buffers[prefix + ".running_mean"], new_buffers[prefix + ".running_var"] = rm, rv
+    new_buffers[prefix + ".num_batches_tracked"] = nb + 1
+    return y
+
+
 def _bn(x, prefix, state, training, new_buffers):
+    if LIBRARY_OPS:
+        return _batch_norm_library(x, prefix, state, training, new_buffers if new_buffers is not None else {})
     if training:
         return _batch_norm_train(x, prefix, state, new_buffers)
     return _batch_norm_eval(x, prefix, state)
@@ -189,7 +211,10 @@ def _transition_down(x, prefix, state, training, new_buffers):
 
 def _transition_up(x, skip, prefix, state):
     """nearest x2 -> conv3x3 -> centre crop -> cat([up, skip]) (models.py:70-80, 93-97)."""
-    up = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)          # nn.Upsample nearest x2
+    if LIBRARY_OPS:
+        up = F.interpolate(x, scale_factor=2, mode="nearest")
+    else:
+        up = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)      # nn.Upsample nearest x2
     out = F.conv2d(up, state[prefix + ".convTrans.1.weight"], state[prefix + ".convTrans.1.bias"], padding=1)
     h, w = skip.shape[2], skip.shape[3]
     x1 = (out.shape[3] - w) // 2

@@ -49,8 +49,8 @@ def _check_grads(model, g64, g32, names):
         e_ref32 = float((g32[k].double() - ref).abs().max()) / scale
         worst.append((e_cuda, e_ref32, k))
         assert e_cuda < max(5e-3, 4.0 * e_ref32), (k, e_cuda, e_ref32)
-    med = float(np.median([w[0] for w in worst]))
-    assert med < 2e-4, med
+    med, med32 = float(np.median([w[0] for w in worst])), float(np.median([w[1] for w in worst]))
+    assert med < max(2e-4, 2.0 * med32), (med, med32)    # as accurate as the fp32 reference implementation
 
 
 def test_forward_backward_vs_oracle():

@@ -145,3 +145,21 @@ def test_full_step():
     names = [k for k in state if not net.is_buffer(k)]
     l2 = np.array([state[k].double().norm().item() for k in names])
     assert np.all(np.abs(l2 - g["w_l2_after"]) <= 1e-3 * g["w_l2_after"] + 1e-5)   # biases start at 0
+
+
+def test_library_ops_mode_matches_restatement():
+    """bench.py times the oracle with LIBRARY_OPS=True (F.batch_norm / F.interpolate / F.grid_sample, the ops
+    the reference itself calls); that mode must be the same function as the written-out restatement."""
+    from oracle import net as onet, geometry as ogeo
+    g = load_golden("step_a")
+    b, h, w, seed = [int(v) for v in g["meta"]]
+    state = onet.init_state(onet.FCDENSENET57, seed=seed, perturb=False)
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, sparse_prob=0.02)
+    try:
+        onet.LIBRARY_OPS = ogeo.LIBRARY_OPS = True
+        loss, dcl, sfl, grads, new_buf, ex = step.forward_backward(state, batch, onet.FCDENSENET57, 5.0, 20.0)
+    finally:
+        onet.LIBRARY_OPS = ogeo.LIBRARY_OPS = False
+    assert abs(float(loss) - g["loss"][0]) / g["loss"][0] < 2e-3
+    assert rel_err(ex["depth_1"], g["p1"]) < 1e-4
+    assert int(new_buf["denseBlocksDown.0.layers.0.norm.num_batches_tracked"]) == 2
