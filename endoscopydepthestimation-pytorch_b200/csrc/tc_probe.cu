@@ -1,0 +1,106 @@
+// tcgen05 bring-up probe: D[128][N] = A[shift .. shift+128][K] * B[N][K]^T on the 5th-generation tensor
+// cores, with the operands staged by ordinary threads into the SWIZZLE_NONE canonical layouts that the
+// convolution kernels use (K-major with 16-byte row pitch, or MN-major), tf32 or bf16, fp32 accumulation
+// in TMEM.  It exists so that every descriptor convention the conv kernels rely on (row sliding through
+// the start address, LBO/SBO meaning, instruction-descriptor fields, TMEM lane/column mapping) is checked
+// against a plain matmul on real hardware by tests/test_gpu_tc_probe.py.
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace endo {
+
+struct ProbeArgs {
+    const float* A; const float* B; float* D;
+    int a_rows, N, K, shift, fmt, a_mn, b_mn;
+};
+
+__global__ void __launch_bounds__(128)
+tc_probe_kernel(const ProbeArgs P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int es = (P.fmt == tc::FMT_TF32) ? 4 : 2;       // element size in shared memory
+    const int T = 16 / es;                                // elements per 16-byte chunk
+    const int kstep = 32 / es;                            // K per MMA: 8 (tf32) or 16 (bf16)
+    // ---- shared layout
+    unsigned char* a_s = smem;
+    const uint32_t a_bytes = (uint32_t)P.a_rows * P.K * es;
+    unsigned char* b_s = smem + ((a_bytes + 127) / 128) * 128;
+    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+    if (!P.a_mn) { a_sbo = 128; a_lbo = (uint32_t)P.a_rows * 16; }         // K-major: planes of rows x 16 B
+    else { a_sbo = 128; a_lbo = (uint32_t)(P.a_rows / T) * 128; }          // MN-major: 128-B blocks (T mn x 8 k)
+    if (!P.b_mn) { b_sbo = 128; b_lbo = (uint32_t)P.N * 16; }
+    else { b_sbo = 128; b_lbo = (uint32_t)(P.N / T) * 128; }
+
+    auto put = [&](unsigned char* base, bool mn, uint32_t lbo, uint32_t sbo, int r, int k, float v) {
+        uint32_t off;
+        if (!mn) off = (uint32_t)(k / T) * lbo + (uint32_t)r * 16 + (uint32_t)(k % T) * es;
+        else off = (uint32_t)(r % T) * es + (uint32_t)(k % 8) * 16 + (uint32_t)(r / T) * sbo + (uint32_t)(k / 8) * lbo;
+        if (es == 4) *reinterpret_cast<float*>(base + off) = v;
+        else *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(v);
+    };
+    for (int i = tid; i < P.a_rows * P.K; i += 128) put(a_s, P.a_mn, a_lbo, a_sbo, i / P.K, i % P.K, P.A[i]);
+    for (int i = tid; i < P.N * P.K; i += 128) put(b_s, P.b_mn, b_lbo, b_sbo, i / P.K, i % P.K, P.B[i]);
+
+    const uint32_t ncols = P.N <= 32 ? 32 : (P.N <= 64 ? 64 : (P.N <= 128 ? 128 : 256));
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (tid == 0) {
+        const uint32_t idesc = tc::instr_desc(P.fmt, 128, P.N, P.a_mn, P.b_mn);
+        for (int k0 = 0; k0 < P.K; k0 += kstep) {
+            uint32_t a_addr = tc::smem_u32(a_s), b_addr = tc::smem_u32(b_s);
+            if (!P.a_mn) a_addr += (uint32_t)(k0 / T) * a_lbo + (uint32_t)P.shift * 16;
+            else a_addr += (uint32_t)(k0 / 8) * a_lbo + (uint32_t)(P.shift / T) * a_sbo;
+            if (!P.b_mn) b_addr += (uint32_t)(k0 / T) * b_lbo;
+            else b_addr += (uint32_t)(k0 / 8) * b_lbo;
+            const uint64_t ad = tc::smem_desc(a_addr, a_lbo, a_sbo), bd = tc::smem_desc(b_addr, b_lbo, b_sbo);
+            if (P.fmt == tc::FMT_TF32) tc::mma_tf32(tmem, ad, bd, idesc, k0 > 0);
+            else tc::mma_f16(tmem, ad, bd, idesc, k0 > 0);
+        }
+        tc::tc_commit(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    tc::tc_fence_after();
+    for (int c0 = 0; c0 < P.N; c0 += 8) {
+        float v[8];
+        tc::tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+        for (int j = 0; j < 8; ++j) P.D[(size_t)(warp * 32 + lane) * P.N + c0 + j] = v[j];
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
+}  // namespace endo
+
+using namespace endo;
+
+extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, int K, int shift, int fmt,
+                             int a_mn_major, int b_mn_major, endo_stream_t stream) {
+    if (!A || !B || !D) return ENDO_ERR_BAD_POINTER;
+    const int kstep = (fmt == tc::FMT_TF32) ? 8 : 16;
+    const int T = (fmt == tc::FMT_TF32) ? 4 : 8;
+    if ((fmt != tc::FMT_TF32 && fmt != tc::FMT_BF16) || N < 16 || N > 256 || (N % 16) || K < kstep || (K % kstep) ||
+        shift < 0 || a_rows < 128 + shift || (a_rows % 8) || (a_mn_major && ((shift % T) || (a_rows % T))))
+        return ENDO_ERR_BAD_SHAPE;
+    const int es = (fmt == tc::FMT_TF32) ? 4 : 2;
+    const size_t smem = ((size_t)a_rows * K * es + 127) / 128 * 128 + (size_t)N * K * es + 256;
+    if (smem > 200 * 1024) return ENDO_ERR_BAD_SHAPE;
+    static bool configured = false;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    ProbeArgs p{A, B, D, a_rows, N, K, shift, fmt, a_mn_major, b_mn_major};
+    tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}

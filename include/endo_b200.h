@@ -184,6 +184,14 @@ int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long lo
                        float momentum, float max_norm, int first_step, const float* finite_flag,
                        float* grad_norm_out, void* ws, size_t ws_bytes, endo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 bring-up probe (tests only): D[128][N] = A[shift..shift+128][K] * B[N][K]^T computed with
+ * tcgen05.mma from operands staged in the shared-memory layouts the convolution kernels use.
+ * fmt: 2 = tf32, 1 = bf16; a_mn_major / b_mn_major select the MN-major canonical layout.
+ * ---------------------------------------------------------------------------------------------- */
+int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, int K, int shift, int fmt,
+                  int a_mn_major, int b_mn_major, endo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,11 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# the oracle runs on the CPU: keep its thread count sane on many-core hosts (128 logical CPUs on the GPU box
+# make torch's default intra-op pool ~50x slower on these small tensors than 16 threads)
+torch.set_num_threads(min(16, os.cpu_count() or 1))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
