@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "bf16"],
+                    help="override the arithmetic of the conv path (default: the config's, fp32)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel development runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -227,6 +230,8 @@ def main():
     if world > 1:
         ddp.init_from_env("nccl")
     bsz, h, w, math_mode, desc = CONFIGS[args.config]
+    if args.math:
+        math_mode = args.math
     peaks = measured_peaks()
 
     torch.manual_seed(10085 + rank)
@@ -297,16 +302,17 @@ def main():
         opt.step()                                                             # :328
         return val
 
-    for _ in range(args.warmup):
+    e2e_steps = 0 if args.no_e2e else args.steps
+    for _ in range(args.warmup if e2e_steps else 0):
         e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(max(e2e_steps, 1)):
         e2e_step()
     e1.record()
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) * (args.steps / max(e2e_steps, 1))
     e2e_value = world * bsz * args.steps / (e2e_ms / 1e3)
 
     # ------------------------------------------------------------------ per-kernel-class timing (roofline)

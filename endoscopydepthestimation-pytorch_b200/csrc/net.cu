@@ -3,6 +3,7 @@
 // net_kernels.cuh on the caller's stream; no allocation, no synchronisation.
 #include "net_kernels.cuh"
 #include "net_plan.cuh"
+#include "net_tc.cuh"
 
 namespace endo {
 
@@ -52,6 +53,7 @@ struct Ctx {
     const float* params; float* gparams; float* bnbuf;
     cudaStream_t s;
     int training;
+    int math;
     float* X(int l) const { return reinterpret_cast<float*>(acts + P.x_off[l]); }
     double* ST(int l) const { return reinterpret_cast<double*>(acts + P.stat_off[l]); }
     float* MI(int l) const { return reinterpret_cast<float*>(acts + P.mi_off[l]); }
@@ -96,6 +98,24 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
     a.w = c.params + d.conv.w; a.bias = c.params + d.conv.b; a.w_cin = d.cin;
     a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = d.out_off; a.N = d.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l); a.stats_C = P.Ctot[l];
+    if (c.math == ENDO_MATH_TF32) {
+        // tcgen05 path: tf32 operands (what cuDNN runs the reference's convs in by default), fp32 accumulate in TMEM
+        tcconv::FwdArgs t;
+        t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
+        t.in_C = a.in_C; t.in_off = a.in_off; t.K = a.K; t.out_C = a.out_C; t.out_off = a.out_off; t.N = a.N;
+        t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C;
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcconv::SMEM_BYTES));
+            configured = true;
+        }
+        dim3 grid(cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH), 1, t.B);
+        ProfScope prof(PC_CONV_DENSE_FWD, c.s);
+        tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(t);
+        ENDO_CHECK_LAUNCH();
+        return ENDO_OK;
+    }
     if (d.conv.cout == 12) return launch_conv<3, 8, 12, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
     return launch_conv<3, 6, 16, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
 }
@@ -118,8 +138,26 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     a.w = c.params + d.conv.w; a.w_cin = d.cin;
     a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = d.in_off; a.N = d.cin; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.BNRED(); a.stats_C = P.maxC;
-    a.x = c.X(l); a.ep_coef = c.COEF(d.bn); a.ep_mi = c.MI(l);
-    ENDO_TRY((launch_conv<3, 2, 48, 8, LM_GRAD, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+    a.x = c.X(l); a.ep_coef = c.COEF(d.bn);
+    if (c.math == ENDO_MATH_TF32) {
+        tcdgrad::Args t;
+        t.g = c.GX(l); t.x = c.X(l); t.ab = c.AB(l); t.coef = c.COEF(d.bn); t.w = c.params + d.conv.w;
+        t.gout = c.GX(l); t.red = c.BNRED(); t.red_C = P.maxC;
+        t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
+        t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcdgrad::dense_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcdgrad::SMEM_BYTES));
+            configured = true;
+        }
+        dim3 grid(cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH), 1, t.B);
+        ProfScope prof(PC_DGRAD, c.s);
+        tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(t);
+        ENDO_CHECK_LAUNCH();
+    } else {
+        ENDO_TRY((launch_conv<3, 2, 48, 8, LM_GRAD, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+    }
     BnBwdArgs b;
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(d.bn); b.mi = c.MI(l); b.ab = c.AB(l);
     b.dgamma = c.gparams + d.bn.gamma; b.dbeta = c.gparams + d.bn.beta;
@@ -162,7 +200,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
     a.w = c.params + t.conv.w; a.w_cin = cs;
     a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = P.offIn[l]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.BNRED(); a.stats_C = P.maxC;
-    a.x = c.X(l); a.ep_coef = c.COEF(t.bn); a.ep_mi = c.MI(l);
+    a.x = c.X(l); a.ep_coef = c.COEF(t.bn);
     ENDO_TRY((launch_conv<1, 2, 48, 8, LM_GRADPOOL, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
     BnBwdArgs b;
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(t.bn); b.mi = c.MI(l); b.ab = c.AB(l);
@@ -237,7 +275,7 @@ extern "C" size_t endo_net_backward_scratch_bytes(const endo_net_config* cfg, in
 extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const float* params, float* bn_buffers,
                             float* y, void* acts, size_t acts_bytes, int B, int H, int W, int groups, int training,
                             int math, endo_stream_t stream) {
-    if (math != ENDO_MATH_FP32) return ENDO_ERR_CONFIG;
+    if (math != ENDO_MATH_FP32 && math != ENDO_MATH_TF32) return ENDO_ERR_CONFIG;
     if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
     if (!x || !params || !bn_buffers || !y || !acts) return ENDO_ERR_BAD_POINTER;
     if (!aligned16(x) || !aligned16(params) || !aligned16(y) || (reinterpret_cast<uintptr_t>(acts) & 255u))
@@ -246,7 +284,7 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
     NetPlan P;
     ENDO_TRY(build_plan(cfg, B, H, W, groups, P));
     if (acts_bytes < (size_t)P.acts_bytes) return ENDO_ERR_WORKSPACE;
-    Ctx c{P, static_cast<char*>(acts), nullptr, params, nullptr, bn_buffers, (cudaStream_t)stream, training};
+    Ctx c{P, static_cast<char*>(acts), nullptr, params, nullptr, bn_buffers, (cudaStream_t)stream, training, math};
     const int nd = cfg->n_down;
     // statistics accumulate with atomics: clear them
     ENDO_CUDA(cudaMemsetAsync(c.acts + P.stat_off[0], 0, (size_t)(P.mi_off[0] - P.stat_off[0]), c.s));
@@ -282,7 +320,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
                             float* g_params, float* g_x, void* acts, size_t acts_bytes, void* scratch,
                             size_t scratch_bytes, int B, int H, int W, int groups, int accumulate, int math,
                             endo_stream_t stream) {
-    if (math != ENDO_MATH_FP32) return ENDO_ERR_CONFIG;
+    if (math != ENDO_MATH_FP32 && math != ENDO_MATH_TF32) return ENDO_ERR_CONFIG;
     if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
     if (g_x != nullptr) return ENDO_ERR_CONFIG;              // train.py never differentiates w.r.t. the images
     if (!g_y || !x || !params || !g_params || !acts || !scratch) return ENDO_ERR_BAD_POINTER;
@@ -294,7 +332,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
     ENDO_TRY(build_plan(cfg, B, H, W, groups, P));
     if (acts_bytes < (size_t)P.acts_bytes || scratch_bytes < (size_t)P.scratch_bytes) return ENDO_ERR_WORKSPACE;
     if (P.Ctot[0] > 384) return ENDO_ERR_CONFIG;
-    Ctx c{P, static_cast<char*>(acts), static_cast<char*>(scratch), params, g_params, nullptr, (cudaStream_t)stream, 1};
+    Ctx c{P, static_cast<char*>(acts), static_cast<char*>(scratch), params, g_params, nullptr, (cudaStream_t)stream, 1, math};
     const int nd = cfg->n_down;
     // gradient buffers of levels >= 1, the lazy-correction arrays and the BN sums start at zero; the level-0
     // gradient buffer (the largest) is fully written by the finalConv backward and needs no clearing

@@ -33,7 +33,7 @@ struct ConvArgs {
     const float* in;          // activation / gradient buffer the loader reads (NHWC, or NCHW for LM_NCHW)
     const float* in2;         // LM_GRAD*: activation buffer x matching `in` (lazy correction needs x)
     const float* in_ab;       // LM_GRAD*: [G][in_C][2] (A, Bc) of that buffer
-    const float* coef;        // LM_BNRELU: [G][K][2] (a, b) of this layer's BatchNorm
+    const float* coef;        // LM_BNRELU: [G][K][4] (a = gamma*invstd, beta, mean, invstd) of this layer's BatchNorm
     const unsigned char* argmax;  // LM_GRADPOOL: [B, ih, iw, K] window index chosen by the forward pool
     int in_C, in_off, K;      // channel stride of the buffer, first channel, number of GEMM-K channels
     int ih, iw;               // spatial size of the buffer the loader reads
@@ -51,8 +51,7 @@ struct ConvArgs {
     unsigned char* argmax_out;    // EM_POOL: [B, oh/2, ow/2, N]
     // ---- EM_DGRAD_BN
     const float* x;           // activation buffer (same geometry as `out`)
-    const float* ep_coef;     // [G][N][2] (a, b) of the BatchNorm being differentiated
-    const float* ep_mi;       // [G][out_C][2] (mean, invstd), absolute channel index
+    const float* ep_coef;     // [G][N][4] (a, beta, mean, invstd) of the BatchNorm being differentiated
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -67,10 +66,13 @@ __device__ __forceinline__ float4 load_a4(const ConvArgs& A, int b, int g, int y
         const int sy = UP ? (y >> 1) : y, sx = UP ? (x >> 1) : x;
         return ldg4(A.in + ((size_t)(b * A.ih + sy) * A.iw + sx) * A.in_C + A.in_off + c);
     } else if constexpr (LM == LM_BNRELU) {
+        // relu(a * (x - mean) + beta): subtracting the mean first keeps the pre-activation as well conditioned as the
+        // reference's (x - mean) / sqrt(var + eps) * gamma + beta, so ReLU masks agree with it up to fp32 rounding
         const float4 v = ldg4(A.in + ((size_t)(b * A.ih + y) * A.iw + x) * A.in_C + A.in_off + c);
-        const float4 c0 = ldg4(A.coef + ((size_t)g * A.K + c) * 2), c1 = ldg4(A.coef + ((size_t)g * A.K + c) * 2 + 4);
-        r.x = fmaxf(fmaf(c0.x, v.x, c0.y), 0.f); r.y = fmaxf(fmaf(c0.z, v.y, c0.w), 0.f);
-        r.z = fmaxf(fmaf(c1.x, v.z, c1.y), 0.f); r.w = fmaxf(fmaf(c1.z, v.w, c1.w), 0.f);
+        const float* cf = A.coef + ((size_t)g * A.K + c) * 4;
+        const float4 c0 = ldg4(cf), c1 = ldg4(cf + 4), c2 = ldg4(cf + 8), c3 = ldg4(cf + 12);
+        r.x = fmaxf(fmaf(c0.x, v.x - c0.z, c0.y), 0.f); r.y = fmaxf(fmaf(c1.x, v.y - c1.z, c1.y), 0.f);
+        r.z = fmaxf(fmaf(c2.x, v.z - c2.z, c2.y), 0.f); r.w = fmaxf(fmaf(c3.x, v.w - c3.z, c3.y), 0.f);
         return r;
     } else if constexpr (LM == LM_GRAD) {
         const size_t o = ((size_t)(b * A.ih + y) * A.iw + x) * A.in_C + A.in_off + c;
@@ -265,20 +267,20 @@ conv_kernel(const ConvArgs A) {
                 for (int j = 0; j < CO; j += 4) {
                     if (n0 + j < A.N) {
                         const float4 xq = ldg4(A.x + o + j);
-                        const float* cf = A.ep_coef + ((size_t)g * A.N + n0 + j) * 2;
-                        const float* mi = A.ep_mi + ((size_t)g * A.out_C + A.out_off + n0 + j) * 2;
-                        const float4 c0 = ldg4(cf), c1 = ldg4(cf + 4), m0 = ldg4(mi), m1 = ldg4(mi + 4);
+                        const float* cf = A.ep_coef + ((size_t)g * A.N + n0 + j) * 4;
+                        const float4 c0 = ldg4(cf), c1 = ldg4(cf + 4), c2 = ldg4(cf + 8), c3 = ldg4(cf + 12);
                         float4 gq = *reinterpret_cast<const float4*>(A.out + o + j);
-                        const float g0 = fmaf(c0.x, xq.x, c0.y) > 0.f ? acc[i][j] : 0.f;
-                        const float g1 = fmaf(c0.z, xq.y, c0.w) > 0.f ? acc[i][j + 1] : 0.f;
-                        const float g2 = fmaf(c1.x, xq.z, c1.y) > 0.f ? acc[i][j + 2] : 0.f;
-                        const float g3 = fmaf(c1.z, xq.w, c1.w) > 0.f ? acc[i][j + 3] : 0.f;
-                        s1[j] += g0; s2[j] += g0 * ((xq.x - m0.x) * m0.y);
-                        s1[j + 1] += g1; s2[j + 1] += g1 * ((xq.y - m0.z) * m0.w);
-                        s1[j + 2] += g2; s2[j + 2] += g2 * ((xq.z - m1.x) * m1.y);
-                        s1[j + 3] += g3; s2[j + 3] += g3 * ((xq.w - m1.z) * m1.w);
-                        gq.x = fmaf(c0.x, g0, gq.x); gq.y = fmaf(c0.z, g1, gq.y);
-                        gq.z = fmaf(c1.x, g2, gq.z); gq.w = fmaf(c1.z, g3, gq.w);
+                        const float d0 = xq.x - c0.z, d1 = xq.y - c1.z, d2 = xq.z - c2.z, d3 = xq.w - c3.z;
+                        const float g0 = fmaf(c0.x, d0, c0.y) > 0.f ? acc[i][j] : 0.f;
+                        const float g1 = fmaf(c1.x, d1, c1.y) > 0.f ? acc[i][j + 1] : 0.f;
+                        const float g2 = fmaf(c2.x, d2, c2.y) > 0.f ? acc[i][j + 2] : 0.f;
+                        const float g3 = fmaf(c3.x, d3, c3.y) > 0.f ? acc[i][j + 3] : 0.f;
+                        s1[j] += g0; s2[j] += g0 * (d0 * c0.w);
+                        s1[j + 1] += g1; s2[j + 1] += g1 * (d1 * c1.w);
+                        s1[j + 2] += g2; s2[j + 2] += g2 * (d2 * c2.w);
+                        s1[j + 3] += g3; s2[j + 3] += g3 * (d3 * c3.w);
+                        gq.x = fmaf(c0.x, g0, gq.x); gq.y = fmaf(c1.x, g1, gq.y);
+                        gq.z = fmaf(c2.x, g2, gq.z); gq.w = fmaf(c3.x, g3, gq.w);
                         *reinterpret_cast<float4*>(A.out + o + j) = gq;
                     }
                 }
@@ -475,7 +477,7 @@ constexpr size_t wgrad_smem_bytes() {
 struct BnPrepArgs {
     const double* stats;      // [G][Ctot][2] of the level buffer
     float* mi;                // [G][Ctot][2] (mean, invstd)
-    float* coef;              // [G][C][2] (a, b) for this BN
+    float* coef;              // [G][C][4] (a, beta, mean, invstd) for this BN
     const float* gamma; const float* beta;
     float* rmean; float* rvar;
     int C, Ctot, ch_off, G, training;
@@ -489,8 +491,8 @@ __global__ void bn_prepare_kernel(const BnPrepArgs A) {
     if (!A.training) {
         const float inv = 1.0f / sqrtf(A.rvar[c] + kBnEps);
         for (int g = 0; g < A.G; ++g) {
-            A.coef[((size_t)g * A.C + c) * 2] = gam * inv;
-            A.coef[((size_t)g * A.C + c) * 2 + 1] = bet - A.rmean[c] * gam * inv;
+            float* cf = A.coef + ((size_t)g * A.C + c) * 4;
+            cf[0] = gam * inv; cf[1] = bet; cf[2] = A.rmean[c]; cf[3] = inv;
             A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2] = A.rmean[c];
             A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1] = inv;
         }
@@ -504,9 +506,8 @@ __global__ void bn_prepare_kernel(const BnPrepArgs A) {
         double var = q / A.count - mean * mean;
         if (var < 0.0) var = 0.0;
         const double inv = 1.0 / sqrt(var + (double)kBnEps);
-        const float a = (float)((double)gam * inv);
-        A.coef[((size_t)g * A.C + c) * 2] = a;
-        A.coef[((size_t)g * A.C + c) * 2 + 1] = (float)((double)bet - mean * (double)gam * inv);
+        float* cf = A.coef + ((size_t)g * A.C + c) * 4;
+        cf[0] = (float)((double)gam * inv); cf[1] = bet; cf[2] = (float)mean; cf[3] = (float)inv;
         A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2] = (float)mean;
         A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1] = (float)inv;
         // running buffers: momentum 0.1, unbiased variance (nn.BatchNorm2d); groups update in order
@@ -520,8 +521,8 @@ __global__ void bn_prepare_kernel(const BnPrepArgs A) {
 struct BnBwdArgs {
     double* red;              // [G][maxC][2] sums (sum gy, sum gy*xhat); zeroed again on exit
     int red_C;
-    const float* coef;        // [G][C][2]
-    const float* mi;          // [G][Ctot][2]
+    const float* coef;        // [G][C][4] (a, beta, mean, invstd)
+    const float* mi;          // unused (kept for ABI stability of the struct)
     float* ab;                // [G][Ctot][2] lazy correction of the level buffer (accumulated)
     float* dgamma; float* dbeta;
     int C, Ctot, ch_off, G;
@@ -537,9 +538,8 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
         const double s1 = r[0], s2 = r[1];
         r[0] = 0.0; r[1] = 0.0;
         dg += s2; db += s1;
-        const double a = A.coef[((size_t)g * A.C + c) * 2];
-        const double mean = A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2];
-        const double inv = A.mi[((size_t)g * A.Ctot + A.ch_off + c) * 2 + 1];
+        const float* cf = A.coef + ((size_t)g * A.C + c) * 4;
+        const double a = cf[0], mean = cf[2], inv = cf[3];
         // dL/dx = a*gy - (a/N) * (S1 + xhat * S2),  xhat = (x - mean) * inv   ->  affine in x, applied lazily
         float* ab = A.ab + ((size_t)g * A.Ctot + A.ch_off + c) * 2;
         ab[0] += (float)(-(a / A.count) * (s1 - mean * inv * s2));

@@ -161,7 +161,7 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
     }
     for (int l = 0; l <= nd; ++l) { P.stat_off[l] = off; off = align_up(off + 16ll * P.G * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.mi_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }
-    auto coef = [&](BnP& q) { q.coef = off / 4; off = align_up(off + 8ll * P.G * q.c, 256); };
+    auto coef = [&](BnP& q) { q.coef = off / 4; off = align_up(off + 16ll * P.G * q.c, 256); };   // [G][C][4]
     for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) coef(d.bn);
     for (int l = 0; l < nd; ++l) coef(P.td[l].bn);
     for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) coef(d.bn);

@@ -1,0 +1,478 @@
+// Tensor-core (tcgen05 / TMEM) kernels of the FC-DenseNet engine for sm_100a.
+//
+// DenseLayer forward (reference models.py:19-28: BN -> ReLU -> conv3x3 Cin -> 12|16) as an implicit GEMM on
+// the 5th-generation tensor cores:
+//
+//   * A operand = the BN+ReLU-transformed activation tile, produced on the fly by the staging warps while
+//     they copy it from the NHWC level buffer into shared memory (no normalised copy ever exists in HBM);
+//     it is stored as K-major SWIZZLE_NONE "planes": plane p holds channels 4p..4p+3 (one 16-byte chunk)
+//     of every pixel of the (32+2) x (32+2) halo tile, pixels in row-major order with pitch 34, 16 bytes
+//     apart.  Because rows are uniformly 16 B apart, a vertical filter tap is just a start-address offset
+//     of +-34 rows in the matrix descriptor: nothing is re-staged per tap.
+//   * the three horizontal taps are folded into the GEMM N dimension: N = 3 (kx) x 16 (co, 12 real) = 48,
+//     so one 128 x 48 x 8 MMA consumes a 4 KB A tile for 3 taps (the shared-memory read of A, 128 B/clk,
+//     is what bounds a small-N MMA).  D'[q][kx][co] = sum_ky sum_c A[q + (ky-1)*34][c] * W[co][c][ky][kx]
+//     accumulates in TMEM over ky (3 descriptors) and over all input channels;
+//   * the epilogue finishes the horizontal part: out[p][co] = D'[p-1][0][co] + D'[p][1][co] + D'[p+1][2][co];
+//     p-1 / p+1 are the neighbouring TMEM lanes, i.e. the neighbouring threads of the warp (shuffles), with a
+//     tiny shared-memory exchange at the 32-lane boundaries.  It adds the bias, writes the 12 new channels
+//     in place into the level buffer and emits the per-channel sum / sum of squares for the next BatchNorms.
+//
+// Warp roles (288 threads): warps 0-7 stage operands (and later run the epilogue), warp 8 issues the MMAs.
+// Two shared-memory stages, mbarrier full/empty pipeline, accumulators for the whole 32x32 tile (9 M-blocks
+// of 128 linear pixels x 48 columns = 432 TMEM columns) stay resident in TMEM across the channel loop.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace endo {
+namespace tcconv {
+
+constexpr int TH = 32, TW = 32, PITCH = 34;
+constexpr int REAL_ROWS = PITCH * (TH + 2);            // 1156 halo-tile pixels
+constexpr int MBLK = 9;                                // ceil(TH * PITCH / 128)
+constexpr int PLANE_ROWS = 1226;                       // >= 34 + 9*128 + 34 ; 1226*16 % 128 == 32 (bank spread)
+constexpr int PLANE_BYTES = PLANE_ROWS * 16;
+constexpr int KCH = 16;                                // input channels per stage (tf32: 4 planes)
+constexpr int A_STAGE_BYTES = (KCH / 4) * PLANE_BYTES; // 78,464
+constexpr int NB = 48;                                 // MMA N = 3 kx * 16
+constexpr int B_BLOCK_BYTES = 2 * NB * 16;             // one (ky, k8) weight block: 2 chunks x 48 rows x 16 B
+constexpr int B_STAGE_BYTES = 3 * (KCH / 8) * B_BLOCK_BYTES;
+constexpr int NUNITS = MBLK * 4;                       // (M-block, lane quadrant) epilogue units
+constexpr int EDGE_FLOATS = NUNITS * 2 * 16;
+constexpr int SMEM_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES + EDGE_FLOATS * 4 + 8 * 16 * 2 * 4 + 128;
+constexpr int NTHREADS = 288;
+
+struct FwdArgs {
+    const float* in; const float* coef; const float* w; const float* bias; float* out; double* stats;
+    int in_C, in_off, K, out_C, out_off, N, H, W, B, G, stats_C;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dense_fwd_tf32_kernel(const FwdArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* a_st0 = smem;
+    unsigned char* b_st0 = smem + 2 * A_STAGE_BYTES;
+    float* edge = reinterpret_cast<float*>(smem + 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES);   // [NUNITS][2][16]
+    float* red = edge + EDGE_FLOATS;                                                        // [8][16][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * 16 * 2);                         // full[2], empty[2], accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (A.W + TW - 1) / TW;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    const int b = blockIdx.z;
+    const int g = b / (A.B / A.G);
+    const int nchunks = (A.K + KCH - 1) / KCH;
+
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        tc::mbar_init(bars + 0, 256); tc::mbar_init(bars + 1, 256);
+        tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
+        tc::mbar_init(bars + 4, 1);
+        tc::fence_mbar_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ======================================================================== producers
+        const int grp = tid & 3;                                  // this thread always stages the same 4-channel group
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1;
+            if (c >= 2) tc::mbar_wait(bars + 2 + s, ((c >> 1) - 1) & 1);
+            unsigned char* a_s = a_st0 + s * A_STAGE_BYTES + grp * PLANE_BYTES;
+            const int ch = c * KCH + grp * 4;
+            float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
+            const bool ch_ok = ch < A.K;
+            if (ch_ok) {
+                const float* cf = A.coef + ((size_t)g * A.K + ch) * 4;
+                k0 = __ldg(reinterpret_cast<const float4*>(cf)); k1 = __ldg(reinterpret_cast<const float4*>(cf + 4));
+                k2 = __ldg(reinterpret_cast<const float4*>(cf + 8)); k3 = __ldg(reinterpret_cast<const float4*>(cf + 12));
+            }
+            const float* in_b = A.in + (size_t)b * A.H * A.W * A.in_C + A.in_off + ch;
+#pragma unroll 4
+            for (int px = tid >> 2; px < REAL_ROWS; px += 64) {
+                const int r = px / PITCH, cc = px - r * PITCH;
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ch_ok && y >= 0 && y < A.H && x >= 0 && x < A.W) {
+                    const float4 q = __ldg(reinterpret_cast<const float4*>(in_b + ((size_t)y * A.W + x) * A.in_C));
+                    v.x = fmaxf(fmaf(k0.x, q.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q.y - k1.z, k1.y), 0.f);
+                    v.z = fmaxf(fmaf(k2.x, q.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q.w - k3.z, k3.y), 0.f);
+                }
+                *reinterpret_cast<float4*>(a_s + (size_t)px * 16) = v;
+            }
+            // weights of this channel chunk: block (ky, k8) = [2 chunks][48 rows (kx*16 + co)][4 tf32]
+            unsigned char* b_s = b_st0 + s * B_STAGE_BYTES;
+            for (int idx = tid; idx < 3 * (KCH / 8) * NB * 8; idx += 256) {
+                const int k = idx & 7, n = (idx >> 3) % NB, blk = idx / (8 * NB);      // blk = ky * 2 + k8
+                const int ky = blk >> 1, k8 = blk & 1;
+                const int co = n & 15, kx = n >> 4, cin = c * KCH + k8 * 8 + k;
+                float v = 0.f;
+                if (co < A.N && cin < A.K) v = __ldg(A.w + (((size_t)co * A.K + cin) * 3 + ky) * 3 + kx);
+                *reinterpret_cast<float*>(b_s + blk * B_BLOCK_BYTES + (k >> 2) * (NB * 16) + n * 16 + (k & 3) * 4) = v;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bars + s);
+        }
+        // ======================================================================== epilogue
+        tc::mbar_wait(bars + 4, 0);
+        tc::tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        // pass 1: publish the values the neighbouring 32-lane units need
+        for (int mb = half; mb < MBLK; mb += 2) {
+            const int u = mb * 4 + q;
+            float v0[16], v2[16];
+            tc::tmem_ld16(tmem + lane_base + mb * NB + 0, v0);
+            tc::tmem_ld16(tmem + lane_base + mb * NB + 32, v2);
+            if (lane == 31) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) edge[(u * 2 + 1) * 16 + j] = v0[j];    // kx = 0 part of my last pixel
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) edge[(u * 2 + 0) * 16 + j] = v2[j];    // kx = 2 part of my first pixel
+            }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float s1[16], s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        float bias[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) bias[j] = (j < A.N) ? __ldg(A.bias + j) : 0.f;
+        for (int mb = half; mb < MBLK; mb += 2) {
+            const int u = mb * 4 + q;
+            float v0[16], v1[16], v2[16];
+            tc::tmem_ld16(tmem + lane_base + mb * NB + 0, v0);
+            tc::tmem_ld16(tmem + lane_base + mb * NB + 16, v1);
+            tc::tmem_ld16(tmem + lane_base + mb * NB + 32, v2);
+            const int L = PITCH + mb * 128 + q * 32 + lane;           // linear index in the halo tile
+            const int r = L / PITCH, cc = L - r * PITCH;
+            const int y = y0 + r - 1, x = x0 + cc - 1;
+            const bool ok = (r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W);
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float left = __shfl_up_sync(0xffffffffu, v0[j], 1);
+                float right = __shfl_down_sync(0xffffffffu, v2[j], 1);
+                if (lane == 0) left = (u > 0) ? edge[((u - 1) * 2 + 1) * 16 + j] : 0.f;
+                if (lane == 31) right = (u < NUNITS - 1) ? edge[((u + 1) * 2 + 0) * 16 + j] : 0.f;
+                o[j] = (left + v1[j]) + right + bias[j];
+            }
+            if (ok) {
+                float* op = A.out + ((size_t)(b * A.H + y) * A.W + x) * A.out_C + A.out_off;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    if (j < A.N) {
+                        *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { s1[j + e] += o[j + e]; s2[j + e] += o[j + e] * o[j + e]; }
+                    }
+                }
+            }
+        }
+        // per-channel statistics: warp tree -> shared -> one fp64 atomic per channel per CTA
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float a = s1[j], c2 = s2[j];
+#pragma unroll
+            for (int o2 = 16; o2 > 0; o2 >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o2);
+                c2 += __shfl_xor_sync(0xffffffffu, c2, o2);
+            }
+            if (lane == 0) { red[(warp * 16 + j) * 2] = a; red[(warp * 16 + j) * 2 + 1] = c2; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (tid < 2 * A.N) {
+            const int j = tid >> 1, which = tid & 1;
+            double sum = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * 16 + j) * 2 + which];
+            atomicAdd(A.stats + ((size_t)g * A.stats_C + A.out_off + j) * 2 + which, sum);
+        }
+    } else if (lane == 0) {
+        // ======================================================================== MMA issuer (one thread)
+        const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NB);
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c & 1;
+            tc::mbar_wait(bars + s, (c >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t a_base = tc::smem_u32(a_st0 + s * A_STAGE_BYTES);
+            const uint32_t b_base = tc::smem_u32(b_st0 + s * B_STAGE_BYTES);
+            const int nk8 = (A.K - c * KCH > 8) ? 2 : 1;           // skip an all-zero K half on the last chunk
+#pragma unroll 1
+            for (int mb = 0; mb < MBLK; ++mb) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    for (int k8 = 0; k8 < nk8; ++k8) {
+                        const uint32_t a_addr = a_base + (uint32_t)(2 * k8) * PLANE_BYTES +
+                                                (uint32_t)(PITCH + mb * 128 + (ky - 1) * PITCH) * 16u;
+                        const uint32_t b_addr = b_base + (uint32_t)(ky * 2 + k8) * B_BLOCK_BYTES;
+                        tc::mma_tf32(tmem + mb * NB, tc::smem_desc(a_addr, PLANE_BYTES, 128), tc::smem_desc(b_addr, NB * 16, 128),
+                                     idesc, (uint32_t)((c | ky | k8) != 0));
+                    }
+                }
+            }
+            tc::tc_commit(bars + 2 + s);
+        }
+        tc::tc_commit(bars + 4);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace tcconv
+}  // namespace endo
+
+namespace endo {
+// =====================================================================================================
+// DenseLayer data gradient on tcgen05 (backward of conv3x3 -> ReLU -> BatchNorm, first term; see the
+// lazy-correction scheme in net_kernels.cuh).
+//
+//   gA[p][ci] = sum_{ky,kx} sum_co G[p + (ky-1, kx-1)][co] * W[co][ci][2-ky][2-kx]
+//
+// GEMM per 128-pixel M-block: M = 128 linear pixels of the halo tile, N = 64 input channels (one "ci chunk"),
+// K = 9 taps x 16 (12 real output channels + zero padding).  The A operand is the output-gradient tile
+// (with the lazy BN correction g + A_c + B_c x applied while staging), stored once per CTA in the same
+// 16-byte-pitch plane layout as the forward kernel, so BOTH tap offsets are start-address offsets.  The
+// accumulator (128 lanes x 64 columns) is double-buffered in TMEM (8 buffers) so the tensor core runs ahead
+// of the epilogue.  The epilogue is the memory-bound part (reads x and the gradient buffer, writes the
+// gradient buffer: 12 B per pixel-channel): TMEM -> registers -> shared (transposed) so that the global
+// read-modify-write is done with lane = channel quad (256 contiguous bytes per pixel) and the per-channel
+// BatchNorm-backward sums (sum gy, sum gy*xhat) live in registers of the lane that owns the channel.
+// =====================================================================================================
+namespace tcdgrad {
+
+using tcconv::PITCH; using tcconv::TH; using tcconv::TW; using tcconv::MBLK; using tcconv::PLANE_BYTES;
+using tcconv::REAL_ROWS;
+constexpr int NC = 64;                                    // input channels per chunk (MMA N)
+constexpr int KG = 16;                                    // output-gradient channels incl. padding (MMA K per tap)
+constexpr int G_BYTES = (KG / 4) * PLANE_BYTES;           // 78,464
+constexpr int WBLK_BYTES = 2 * NC * 16;                   // one (tap, k8) block
+constexpr int W_BYTES = 9 * 2 * WBLK_BYTES;               // 36,864
+constexpr int TB_PITCH = NC * 4 + 16;                     // 272 B per pixel row (bank spread)
+constexpr int TB_BYTES = 128 * TB_PITCH;                  // 34,816
+constexpr int NBUF = 8;                                   // TMEM accumulator buffers (8 x 64 = 512 columns)
+constexpr int SMEM_BYTES = G_BYTES + W_BYTES + TB_BYTES + NC * 4 * 4 + 8 * NC * 2 * 4 + 256;
+constexpr int NTHREADS = 288;
+
+struct Args {
+    const float* g; const float* x; const float* ab;      // gradient buffer, activation buffer, lazy correction [G][C][2]
+    const float* coef;                                    // this BN's (a, beta, mean, invstd) [G][Cin][4]
+    const float* w;                                       // OIHW [Cout][Cin][3][3]
+    float* gout;                                          // gradient buffer (same as g), accumulated at in_off..in_off+Cin
+    double* red; int red_C;                               // [G][red_C][2] BN backward sums
+    int C, out_off, Cout, in_off, Cin, H, W, B, G;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dense_dgrad_tf32_kernel(const Args A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* g_s = smem;
+    unsigned char* w_s = smem + G_BYTES;
+    unsigned char* tb = smem + G_BYTES + W_BYTES;
+    float* ctab = reinterpret_cast<float*>(tb + TB_BYTES);                 // [NC][4] a, beta, mean, invstd
+    float* red = ctab + NC * 4;                                            // [8][NC][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * NC * 2);        // w_full, acc_full[8], acc_empty[8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NBUF);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_x = (A.W + TW - 1) / TW;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    const int b = blockIdx.z;
+    const int g = b / (A.B / A.G);
+    const int nchunks = (A.Cin + NC - 1) / NC;
+
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        tc::mbar_init(bars + 0, 256);
+        for (int i = 0; i < NBUF; ++i) { tc::mbar_init(bars + 1 + i, 1); tc::mbar_init(bars + 1 + NBUF + i, 128); }
+        tc::fence_mbar_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ---------------------------------------------------------------- stage the output-gradient tile once
+        {
+            const int grp = tid & 3;
+            const int ch = grp * 4;
+            const bool ch_ok = ch < A.Cout;
+            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+            if (ch_ok) {
+                const float* abp = A.ab + ((size_t)g * A.C + A.out_off + ch) * 2;
+                c0 = __ldg(reinterpret_cast<const float4*>(abp));
+                c1 = __ldg(reinterpret_cast<const float4*>(abp + 4));
+            }
+            const size_t img = (size_t)b * A.H * A.W;
+#pragma unroll 4
+            for (int px = tid >> 2; px < REAL_ROWS; px += 64) {
+                const int r = px / PITCH, cc = px - r * PITCH;
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ch_ok && y >= 0 && y < A.H && x >= 0 && x < A.W) {
+                    const size_t o = (img + (size_t)y * A.W + x) * A.C + A.out_off + ch;
+                    const float4 gq = __ldg(reinterpret_cast<const float4*>(A.g + o));
+                    const float4 xq = __ldg(reinterpret_cast<const float4*>(A.x + o));
+                    v.x = gq.x + fmaf(c0.y, xq.x, c0.x); v.y = gq.y + fmaf(c0.w, xq.y, c0.z);
+                    v.z = gq.z + fmaf(c1.y, xq.z, c1.x); v.w = gq.w + fmaf(c1.w, xq.w, c1.z);
+                }
+                *reinterpret_cast<float4*>(g_s + grp * PLANE_BYTES + (size_t)(px + 1) * 16) = v;   // row 0 is a margin row
+            }
+        }
+        const int q = warp & 3, chalf = warp >> 2;            // TMEM lane quadrant, column half (32 columns)
+        const int quad = lane & 15, psub = lane >> 4;         // phase-2 mapping: channel quad, pixel parity
+        int unit = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int ci0 = c * NC;
+            // ------------------------------------------------------------ weights + BN table of this ci chunk
+            for (int idx = tid; idx < 9 * 2 * NC * 8; idx += 256) {
+                const int k = idx & 7, n = (idx >> 3) % NC, blk = idx / (8 * NC);          // blk = tap * 2 + k8
+                const int tap = blk >> 1, k8 = blk & 1;
+                const int co = k8 * 8 + k, ci = ci0 + n;
+                float v = 0.f;
+                if (co < A.Cout && ci < A.Cin) v = __ldg(A.w + ((size_t)co * A.Cin + ci) * 9 + (8 - tap));
+                *reinterpret_cast<float*>(w_s + blk * WBLK_BYTES + (k >> 2) * (NC * 16) + n * 16 + (k & 3) * 4) = v;
+            }
+            if (tid < NC) {
+                const int ci = ci0 + tid;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ci < A.Cin) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)g * A.Cin + ci) * 4));
+                *reinterpret_cast<float4*>(ctab + tid * 4) = e;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bars + 0);                         // w_full: phase c
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // ctab visible to all epilogue threads
+            // per-lane constants for the 4 channels this lane owns in phase 2
+            float ca[4], cb[4], cm[4], cs[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 t4 = *reinterpret_cast<const float4*>(ctab + (quad * 4 + e) * 4);
+                ca[e] = t4.x; cb[e] = t4.y; cm[e] = t4.z; cs[e] = t4.w;
+            }
+            const bool quad_ok = (ci0 + quad * 4) < A.Cin;
+            float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int mb = 0; mb < MBLK; ++mb, ++unit) {
+                const int buf = unit % NBUF;
+                tc::mbar_wait(bars + 1 + buf, (unit / NBUF) & 1);
+                tc::tc_fence_after();
+                // phase 1: TMEM -> registers -> transposed shared tile [pixel][channel]
+                {
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * NC + chalf * 32;
+                    float v[16];
+                    unsigned char* row = tb + (size_t)(q * 32 + lane) * TB_PITCH + chalf * 128;
+                    tc::tmem_ld16(taddr, v);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(row + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    tc::tmem_ld16(taddr + 16, v);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(row + 64 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                tc::tc_fence_before();
+                asm volatile("bar.sync 1, 256;" ::: "memory");               // all 8 warps have drained their TMEM part
+                if (chalf == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);      // 128 arrivals: accumulator buffer free again
+                // phase 2: lane = (pixel parity, channel quad); 16 pixels per warp
+                if (quad_ok) {
+#pragma unroll 2
+                    for (int it = 0; it < 8; ++it) {
+                        const int p = warp * 16 + it * 2 + psub;
+                        const int L = PITCH + mb * 128 + p;
+                        const int r = L / PITCH, cc = L - r * PITCH;
+                        const int y = y0 + r - 1, x = x0 + cc - 1;
+                        if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
+                            const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
+                            const size_t o = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
+                            const float4 xq = __ldg(reinterpret_cast<const float4*>(A.x + o));
+                            float4 gq = *reinterpret_cast<const float4*>(A.gout + o);
+                            const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
+                            const float g0 = fmaf(ca[0], e0, cb[0]) > 0.f ? d.x : 0.f;
+                            const float g1 = fmaf(ca[1], e1, cb[1]) > 0.f ? d.y : 0.f;
+                            const float g2 = fmaf(ca[2], e2, cb[2]) > 0.f ? d.z : 0.f;
+                            const float g3 = fmaf(ca[3], e3, cb[3]) > 0.f ? d.w : 0.f;
+                            s1[0] += g0; s2[0] += g0 * (e0 * cs[0]);
+                            s1[1] += g1; s2[1] += g1 * (e1 * cs[1]);
+                            s1[2] += g2; s2[2] += g2 * (e2 * cs[2]);
+                            s1[3] += g3; s2[3] += g3 * (e3 * cs[3]);
+                            gq.x = fmaf(ca[0], g0, gq.x); gq.y = fmaf(ca[1], g1, gq.y);
+                            gq.z = fmaf(ca[2], g2, gq.z); gq.w = fmaf(ca[3], g3, gq.w);
+                            *reinterpret_cast<float4*>(A.gout + o) = gq;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");           // transposed tile free for the next unit
+            }
+            // ------------------------------------------------------------ BN-backward sums of this chunk
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+                if (psub == 0) {
+                    red[(warp * NC + quad * 4 + e) * 2] = s1[e];
+                    red[(warp * NC + quad * 4 + e) * 2 + 1] = s2[e];
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < 2 * NC) {
+                const int j = tid >> 1, which = tid & 1;
+                if (ci0 + j < A.Cin) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * NC + j) * 2 + which];
+                    atomicAdd(A.red + ((size_t)g * A.red_C + ci0 + j) * 2 + which, sum);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // red / ctab / weights reusable
+        }
+    } else if (lane == 0) {
+        // -------------------------------------------------------------------- MMA issuer
+        const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NC);
+        const uint32_t g_base = tc::smem_u32(g_s), w_base = tc::smem_u32(w_s);
+        int unit = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            tc::mbar_wait(bars + 0, c & 1);
+            tc::tc_fence_after();
+            for (int mb = 0; mb < MBLK; ++mb, ++unit) {
+                const int buf = unit % NBUF;
+                if (unit >= NBUF) tc::mbar_wait(bars + 1 + NBUF + buf, ((unit / NBUF) - 1) & 1);
+                tc::tc_fence_after();
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+#pragma unroll
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        const uint32_t a_addr = g_base + (uint32_t)(2 * k8) * PLANE_BYTES +
+                                                (uint32_t)(1 + PITCH + mb * 128 + (ky - 1) * PITCH + (kx - 1)) * 16u;
+                        const uint32_t b_addr = w_base + (uint32_t)(tap * 2 + k8) * WBLK_BYTES;
+                        tc::mma_tf32(tmem + buf * NC, tc::smem_desc(a_addr, PLANE_BYTES, 128), tc::smem_desc(b_addr, NC * 16, 128),
+                                     idesc, (uint32_t)((tap | k8) != 0));
+                    }
+                }
+                tc::tc_commit(bars + 1 + buf);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace tcdgrad
+}  // namespace endo

@@ -194,3 +194,27 @@ def test_shape_errors_are_loud():
         model(torch.zeros(1, 3, 40, 64, device="cuda"))      # H not a multiple of 32
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 4, 64, 64, device="cuda"))      # wrong channel count
+
+
+def test_tf32_tensor_core_forward():
+    """math="tf32": DenseLayer convolutions on tcgen05 with tf32 operands and fp32 accumulation (the arithmetic
+    cuDNN uses for the reference's convs by default, torch.backends.cudnn.allow_tf32=True).  Looser bound than
+    the fp32 path: 10-bit operand mantissas through 44 stacked convolutions."""
+    cfg = onet.FCDENSENET57
+    state, x, _ = _setup(cfg, lambda: endo_b200.models.FCDenseNet57(n_classes=1), 2, 128, 160, 303)
+    model = endo_b200.models.FCDenseNet57(n_classes=1, math="tf32")
+    model.load_state_dict(state)
+    model.cuda().train()
+    gy = torch.randn(2, 1, 128, 160, generator=torch.Generator().manual_seed(9))
+    y64, g64, buf64 = _oracle_fwd_bwd(state, x, cfg, gy, torch.float64)
+    y = model(x.cuda())
+    err = rel_err(y, y64)
+    print("tf32 forward rel err", err)
+    assert err < 2e-2, err
+    (y * gy.cuda()).sum().backward()
+    params = dict(model.named_parameters())
+    e = rel_err(params["finalConv.weight"].grad, g64["finalConv.weight"])
+    assert e < 5e-2, e
+    sd = model.state_dict()
+    for k in ("denseBlocksDown.0.layers.1.norm.running_mean", "denseBlocksUp.4.layers.3.norm.running_var"):
+        assert rel_err(sd[k], buf64[k]) < 2e-2, k

@@ -40,6 +40,7 @@ def rel(a, b):
 
 def main():
     B, H, W = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (2, 64, 96)
+    math_mode = sys.argv[4] if len(sys.argv) >= 5 else "fp32"
     cfg = onet.FCDENSENET57
     state = onet.init_state(cfg, seed=303, perturb=True)
     batch = endo_b200.synthetic.make_batch(B, H, W, seed=303)
@@ -51,7 +52,7 @@ def main():
     gy = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(5))
     (y_ref * gy.double()).sum().backward()
 
-    model = endo_b200.models.FCDenseNet57(1)
+    model = endo_b200.models.FCDenseNet57(1, math=math_mode)
     model.load_state_dict(state)
     model.cuda().train()
     model._debug_keep_acts = True
