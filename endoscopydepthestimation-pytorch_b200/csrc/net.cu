@@ -1,6 +1,7 @@
 // FCDenseNet forward / backward entry points (reference models.py:100-187 and the autograd backward
 // PyTorch derives from it), fp32 FFMA path.  Host side: walks the NetPlan and enqueues the kernels of
 // net_kernels.cuh on the caller's stream; no allocation, no synchronisation.
+#include <cstdlib>
 #include "net_kernels.cuh"
 #include "net_plan.cuh"
 #include "net_tc.cuh"
@@ -45,6 +46,13 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
     kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
+}
+
+// ENDO_TC_DISABLE (bit mask, debugging / A-B tests only): 1 = forward, 2 = data gradient, 4 = weight gradient fall back
+// to the FFMA kernels even when the math mode asks for tensor cores.
+static int tc_disable_mask() {
+    const char* e = getenv("ENDO_TC_DISABLE");
+    return e ? atoi(e) : 0;
 }
 
 struct Ctx {
@@ -98,7 +106,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
     a.w = c.params + d.conv.w; a.bias = c.params + d.conv.b; a.w_cin = d.cin;
     a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = d.out_off; a.N = d.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l); a.stats_C = P.Ctot[l];
-    if (c.math == ENDO_MATH_TF32) {
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 1)) {
         // tcgen05 path: tf32 operands (what cuDNN runs the reference's convs in by default), fp32 accumulate in TMEM
         tcconv::FwdArgs t;
         t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
@@ -129,8 +137,33 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = d.out_off; w.g_K = d.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + d.conv.w; w.db = c.gparams + d.conv.b; w.w_cin = d.cin;
-    if (d.conv.cout == 12) ENDO_TRY((launch_wgrad<3, 12, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
-    else ENDO_TRY((launch_wgrad<3, 16, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 4)) {
+        // bf16 tensor-core weight gradient (pixels are the GEMM K dimension); the bias gradient comes from the dgrad kernel
+        tcwgrad::Args t;
+        t.x = c.X(l); t.coef = c.COEF(d.bn); t.g = c.GX(l); t.ab = c.AB(l); t.dw = c.gparams + d.conv.w;
+        t.C = P.Ctot[l]; t.in_off = d.in_off; t.Cin = d.cin; t.out_off = d.out_off; t.Cout = d.conv.cout;
+        t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
+        t.n_tiles = P.B * cdiv(t.H, tcwgrad::TR) * cdiv(t.W, tcwgrad::TW);
+        const int yblocks = cdiv(d.cin, tcwgrad::MCH);
+        int want = (2 * kNumSMs) / yblocks;
+        if (want < 1) want = 1;
+        if (want > t.n_tiles) want = t.n_tiles;
+        t.tiles_per_cta = cdiv(t.n_tiles, want);
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcwgrad::dense_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcwgrad::SMEM_BYTES));
+            configured = true;
+        }
+        dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
+        ProfScope prof(PC_WGRAD, c.s);
+        tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(t);
+        ENDO_CHECK_LAUNCH();
+    } else if (d.conv.cout == 12) {
+        ENDO_TRY((launch_wgrad<3, 12, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+    } else {
+        ENDO_TRY((launch_wgrad<3, 16, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+    }
     // data gradient through conv, ReLU and BatchNorm (first term; the mean terms are applied lazily)
     ConvArgs a = base_args(c);
     a.in = c.GX(l); a.in2 = c.X(l); a.in_ab = c.AB(l); a.in_C = P.Ctot[l]; a.in_off = d.out_off; a.K = d.conv.cout;
@@ -139,10 +172,10 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = d.in_off; a.N = d.cin; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.BNRED(); a.stats_C = P.maxC;
     a.x = c.X(l); a.ep_coef = c.COEF(d.bn);
-    if (c.math == ENDO_MATH_TF32) {
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 2)) {
         tcdgrad::Args t;
         t.g = c.GX(l); t.x = c.X(l); t.ab = c.AB(l); t.coef = c.COEF(d.bn); t.w = c.params + d.conv.w;
-        t.gout = c.GX(l); t.red = c.BNRED(); t.red_C = P.maxC;
+        t.gout = c.GX(l); t.db = c.gparams + d.conv.b; t.red = c.BNRED(); t.red_C = P.maxC;
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         static bool configured = false;

@@ -94,17 +94,36 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 k2 = __ldg(reinterpret_cast<const float4*>(cf + 8)); k3 = __ldg(reinterpret_cast<const float4*>(cf + 12));
             }
             const float* in_b = A.in + (size_t)b * A.H * A.W * A.in_C + A.in_off + ch;
-#pragma unroll 4
-            for (int px = tid >> 2; px < REAL_ROWS; px += 64) {
-                const int r = px / PITCH, cc = px - r * PITCH;
-                const int y = y0 + r - 1, x = x0 + cc - 1;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch_ok && y >= 0 && y < A.H && x >= 0 && x < A.W) {
-                    const float4 q = __ldg(reinterpret_cast<const float4*>(in_b + ((size_t)y * A.W + x) * A.in_C));
-                    v.x = fmaxf(fmaf(k0.x, q.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q.y - k1.z, k1.y), 0.f);
-                    v.z = fmaxf(fmaf(k2.x, q.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q.w - k3.z, k3.y), 0.f);
+            // 19 pixels per thread, issued as two batches of 10 independent 16-byte loads (memory-level parallelism:
+            // the kernel is bound by how many bytes each SM keeps in flight, not by the tensor core)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float4 q[10];
+                unsigned okmask = 0u;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const int px = (tid >> 2) + 64 * (half * 10 + j);
+                    const int r = px / PITCH, cc = px - r * PITCH;
+                    const int y = y0 + r - 1, x = x0 + cc - 1;
+                    const bool ok = ch_ok && (px < REAL_ROWS) && y >= 0 && y < A.H && x >= 0 && x < A.W;
+                    q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) {
+                        q[j] = __ldg(reinterpret_cast<const float4*>(in_b + ((size_t)y * A.W + x) * A.in_C));
+                        okmask |= 1u << j;
+                    }
                 }
-                *reinterpret_cast<float4*>(a_s + (size_t)px * 16) = v;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    const int px = (tid >> 2) + 64 * (half * 10 + j);
+                    if (px < REAL_ROWS) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (okmask & (1u << j)) {
+                            v.x = fmaxf(fmaf(k0.x, q[j].x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q[j].y - k1.z, k1.y), 0.f);
+                            v.z = fmaxf(fmaf(k2.x, q[j].z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q[j].w - k3.z, k3.y), 0.f);
+                        }
+                        *reinterpret_cast<float4*>(a_s + (size_t)px * 16) = v;
+                    }
+                }
             }
             // weights of this channel chunk: block (ky, k8) = [2 chunks][48 rows (kx*16 + co)][4 tf32]
             unsigned char* b_s = b_st0 + s * B_STAGE_BYTES;
@@ -271,6 +290,7 @@ struct Args {
     const float* coef;                                    // this BN's (a, beta, mean, invstd) [G][Cin][4]
     const float* w;                                       // OIHW [Cout][Cin][3][3]
     float* gout;                                          // gradient buffer (same as g), accumulated at in_off..in_off+Cin
+    float* db;                                            // conv bias gradient [Cout] (sum of the output gradient), accumulated
     double* red; int red_C;                               // [G][red_C][2] BN backward sums
     int C, out_off, Cout, in_off, Cin, H, W, B, G;
 };
@@ -318,19 +338,48 @@ dense_dgrad_tf32_kernel(const Args A) {
                 c1 = __ldg(reinterpret_cast<const float4*>(abp + 4));
             }
             const size_t img = (size_t)b * A.H * A.W;
-#pragma unroll 4
-            for (int px = tid >> 2; px < REAL_ROWS; px += 64) {
-                const int r = px / PITCH, cc = px - r * PITCH;
-                const int y = y0 + r - 1, x = x0 + cc - 1;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch_ok && y >= 0 && y < A.H && x >= 0 && x < A.W) {
-                    const size_t o = (img + (size_t)y * A.W + x) * A.C + A.out_off + ch;
-                    const float4 gq = __ldg(reinterpret_cast<const float4*>(A.g + o));
-                    const float4 xq = __ldg(reinterpret_cast<const float4*>(A.x + o));
-                    v.x = gq.x + fmaf(c0.y, xq.x, c0.x); v.y = gq.y + fmaf(c0.w, xq.y, c0.z);
-                    v.z = gq.z + fmaf(c1.y, xq.z, c1.x); v.w = gq.w + fmaf(c1.w, xq.w, c1.z);
+            float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int part = 0; part < 4; ++part) {                    // 19 pixels per thread in batches of 5 (2 loads each)
+                float4 gq[5], xq[5];
+                unsigned okmask = 0u;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int px = (tid >> 2) + 64 * (part * 5 + j);
+                    const int r = px / PITCH, cc = px - r * PITCH;
+                    const int y = y0 + r - 1, x = x0 + cc - 1;
+                    gq[j] = make_float4(0.f, 0.f, 0.f, 0.f); xq[j] = gq[j];
+                    if (ch_ok && px < REAL_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) {
+                        const size_t o = (img + (size_t)y * A.W + x) * A.C + A.out_off + ch;
+                        gq[j] = __ldg(reinterpret_cast<const float4*>(A.g + o));
+                        xq[j] = __ldg(reinterpret_cast<const float4*>(A.x + o));
+                        okmask |= 1u << j;
+                    }
                 }
-                *reinterpret_cast<float4*>(g_s + grp * PLANE_BYTES + (size_t)(px + 1) * 16) = v;   // row 0 is a margin row
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int px = (tid >> 2) + 64 * (part * 5 + j);
+                    if (px < REAL_ROWS) {
+                        const int r = px / PITCH, cc = px - r * PITCH;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (okmask & (1u << j)) {
+                            v.x = gq[j].x + fmaf(c0.y, xq[j].x, c0.x); v.y = gq[j].y + fmaf(c0.w, xq[j].y, c0.z);
+                            v.z = gq[j].z + fmaf(c1.y, xq[j].z, c1.x); v.w = gq[j].w + fmaf(c1.w, xq[j].w, c1.z);
+                            if (r >= 1 && r <= TH && cc >= 1 && cc <= TW) { bs.x += v.x; bs.y += v.y; bs.z += v.z; bs.w += v.w; }
+                        }
+                        *reinterpret_cast<float4*>(g_s + grp * PLANE_BYTES + (size_t)(px + 1) * 16) = v;   // row 0 is a margin row
+                    }
+                }
+            }
+            // conv bias gradient = sum of the output gradient over the tile interior (each pixel is interior to one tile)
+#pragma unroll
+            for (int o2 = 4; o2 < 32; o2 <<= 1) {
+                bs.x += __shfl_xor_sync(0xffffffffu, bs.x, o2); bs.y += __shfl_xor_sync(0xffffffffu, bs.y, o2);
+                bs.z += __shfl_xor_sync(0xffffffffu, bs.z, o2); bs.w += __shfl_xor_sync(0xffffffffu, bs.w, o2);
+            }
+            if (A.db && lane < 4 && ch_ok) {
+                atomicAdd(A.db + ch, bs.x); atomicAdd(A.db + ch + 1, bs.y);
+                atomicAdd(A.db + ch + 2, bs.z); atomicAdd(A.db + ch + 3, bs.w);
             }
         }
         const int q = warp & 3, chalf = warp >> 2;            // TMEM lane quadrant, column half (32 columns)
@@ -388,17 +437,30 @@ dense_dgrad_tf32_kernel(const Args A) {
                 if (chalf == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);      // 128 arrivals: accumulator buffer free again
                 // phase 2: lane = (pixel parity, channel quad); 16 pixels per warp
                 if (quad_ok) {
-#pragma unroll 2
-                    for (int it = 0; it < 8; ++it) {
+                    float4 xv[8], gv[8];
+                    unsigned okmask = 0u;
+                    size_t off[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {                     // all 16 loads of this unit in flight at once
                         const int p = warp * 16 + it * 2 + psub;
                         const int L = PITCH + mb * 128 + p;
                         const int r = L / PITCH, cc = L - r * PITCH;
                         const int y = y0 + r - 1, x = x0 + cc - 1;
+                        off[it] = 0;
                         if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
+                            off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
+                            xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
+                            gv[it] = *reinterpret_cast<const float4*>(A.gout + off[it]);
+                            okmask |= 1u << it;
+                        }
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        if (okmask & (1u << it)) {
+                            const int p = warp * 16 + it * 2 + psub;
                             const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
-                            const size_t o = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
-                            const float4 xq = __ldg(reinterpret_cast<const float4*>(A.x + o));
-                            float4 gq = *reinterpret_cast<const float4*>(A.gout + o);
+                            const float4 xq = xv[it];
+                            float4 gq = gv[it];
                             const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
                             const float g0 = fmaf(ca[0], e0, cb[0]) > 0.f ? d.x : 0.f;
                             const float g1 = fmaf(ca[1], e1, cb[1]) > 0.f ? d.y : 0.f;
@@ -410,7 +472,7 @@ dense_dgrad_tf32_kernel(const Args A) {
                             s1[3] += g3; s2[3] += g3 * (e3 * cs[3]);
                             gq.x = fmaf(ca[0], g0, gq.x); gq.y = fmaf(ca[1], g1, gq.y);
                             gq.z = fmaf(ca[2], g2, gq.z); gq.w = fmaf(ca[3], g3, gq.w);
-                            *reinterpret_cast<float4*>(A.gout + o) = gq;
+                            *reinterpret_cast<float4*>(A.gout + off[it]) = gq;
                         }
                     }
                 }
@@ -475,4 +537,212 @@ dense_dgrad_tf32_kernel(const Args A) {
 }
 
 }  // namespace tcdgrad
+
+// =====================================================================================================
+// DenseLayer weight gradient on tcgen05 (bf16 operands, fp32 accumulation in TMEM).
+//
+//   dW[co][ci][ky][kx] = sum_p G[p][co] * act[p + (ky-1, kx-1)][ci],   act = relu(bn(x)), zero outside the image
+//
+// The reduction runs over PIXELS, so pixels are the GEMM K dimension and both operands are "MN-major": for a
+// group of 8 channels, 8 consecutive pixels x 16 bytes form one 128-byte core matrix -- which is exactly the
+// plane layout of the forward kernel (pixels 16 B apart), with bf16 packing 8 channels into the 16 bytes.
+//   A = act planes          M = 64 input channels of this CTA's channel block (rows 64..127 of the MMA read
+//                           whatever follows in shared memory and are ignored), K = 16 pixels
+//   B = shifted G planes    N = 3 (kx) x 16 (co): the horizontal taps are folded into N by writing each staged
+//                           gradient pixel into three planes shifted by kx-1 rows; the vertical tap is an A
+//                           start-address offset of +-34 rows.  Three accumulators D_ky[ci][kx*16+co] (144 TMEM
+//                           columns) stay resident while the CTA walks over its share of 8x32-pixel tiles; one
+//                           fp32 atomicAdd per weight at the end.
+// =====================================================================================================
+namespace tcwgrad {
+
+constexpr int PITCH = 34, TR = 8, TW = 32;
+constexpr int KPX = TR * PITCH;                          // 272 pixels = 17 K-steps of 16
+constexpr int A_ROWS = (TR + 2) * PITCH;                 // 340 staged activation pixels
+constexpr int PLANE_BYTES = 345 * 16;                    // 5,520: = 16 (mod 128) so the 8 channel groups of one pixel spread over all banks
+constexpr int MCH = 64;                                  // input channels per CTA block
+constexpr int A_STAGE = (MCH / 8) * PLANE_BYTES;         // 44,160
+constexpr int G_STAGE = 6 * PLANE_BYTES;                 // 33,120   planes [kx][co half], one margin row in front
+constexpr int STAGE = A_STAGE + G_STAGE;                 // 77,280
+constexpr int SMEM_BYTES = 2 * STAGE + 8 * PLANE_BYTES + 256;   // tail pad: the M = 128 read of stage 1 stays inside the allocation
+constexpr int NB = 48;
+constexpr int NTHREADS = 288;
+
+struct Args {
+    const float* x; const float* coef;                   // activations + this BN's (a, beta, mean, invstd) [G][Cin][4]
+    const float* g; const float* ab;                     // gradient buffer + lazy correction [G][C][2]
+    float* dw;                                           // OIHW gradient (accumulated); the bias gradient comes from the dgrad kernel
+    int C, in_off, Cin, out_off, Cout, H, W, B, G;
+    int tiles_per_cta, n_tiles;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+dense_wgrad_bf16_kernel(const Args A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE + 8 * PLANE_BYTES);   // full[2], empty[2], accum
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ci0 = blockIdx.y * MCH;
+    const int tiles_x = (A.W + TW - 1) / TW, tiles_y = (A.H + TR - 1) / TR;
+    const int t_begin = blockIdx.x * A.tiles_per_cta;
+    const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
+    const int ntiles = t_end - t_begin;
+
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 256);
+    if (tid == 0) {
+        tc::mbar_init(bars + 0, 256); tc::mbar_init(bars + 1, 256);
+        tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
+        tc::mbar_init(bars + 4, 1);
+        tc::fence_mbar_init();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        for (int it = 0; it < ntiles; ++it) {
+            const int s = it & 1;
+            if (it >= 2) tc::mbar_wait(bars + 2 + s, ((it >> 1) - 1) & 1);
+            const int t = t_begin + it;
+            const int b = t / (tiles_x * tiles_y), rem = t - b * (tiles_x * tiles_y);
+            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int y0 = ty * TR, x0 = tx * TW;
+            const int g = b / (A.B / A.G);
+            unsigned char* a_s = smem + s * STAGE;
+            unsigned char* g_s = a_s + A_STAGE;
+            const size_t img = (size_t)b * A.H * A.W;
+            // ---- activations: (pixel, 8-channel group) items, BN+ReLU, bf16
+            {
+                const int grp = tid & 7;
+                const int ch = ci0 + grp * 8;
+                const bool ch_ok = ch < A.Cin;                       // Cin is a multiple of 4: a group may be half valid
+                const bool hi_ok = ch + 4 < A.Cin;
+                float4 k[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) k[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ch_ok) {
+                    const float* cf = A.coef + ((size_t)g * A.Cin + ch) * 4;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
+                    if (hi_ok) {
+#pragma unroll
+                        for (int e = 4; e < 8; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
+                    }
+                }
+#pragma unroll 2
+                for (int px = tid >> 3; px < A_ROWS; px += 32) {
+                    const int r = px / PITCH, cc = px - r * PITCH;
+                    const int y = y0 + r - 1, x = x0 + cc - 1;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (ch_ok && y >= 0 && y < A.H && x >= 0 && x < A.W) {
+                        const float* p = A.x + (img + (size_t)y * A.W + x) * A.C + A.in_off + ch;
+                        const float4 q0 = __ldg(reinterpret_cast<const float4*>(p));
+                        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (hi_ok) q1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+                        const float v0 = fmaxf(fmaf(k[0].x, q0.x - k[0].z, k[0].y), 0.f), v1 = fmaxf(fmaf(k[1].x, q0.y - k[1].z, k[1].y), 0.f);
+                        const float v2 = fmaxf(fmaf(k[2].x, q0.z - k[2].z, k[2].y), 0.f), v3 = fmaxf(fmaf(k[3].x, q0.w - k[3].z, k[3].y), 0.f);
+                        float v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
+                        if (hi_ok) {
+                            v4 = fmaxf(fmaf(k[4].x, q1.x - k[4].z, k[4].y), 0.f); v5 = fmaxf(fmaf(k[5].x, q1.y - k[5].z, k[5].y), 0.f);
+                            v6 = fmaxf(fmaf(k[6].x, q1.z - k[6].z, k[6].y), 0.f); v7 = fmaxf(fmaf(k[7].x, q1.w - k[7].z, k[7].y), 0.f);
+                        }
+                        o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
+                    }
+                    *reinterpret_cast<uint4*>(a_s + grp * PLANE_BYTES + (size_t)px * 16) = o;
+                }
+            }
+            // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile interior
+            for (int idx = tid; idx < 6 * (A_ROWS + 2); idx += 256) {
+                const int pl = idx % 6, row = idx / 6;                // row 0 and A_ROWS+1 are margins
+                const int kx = pl >> 1, half = pl & 1;
+                const int src = row - 1 - (kx - 1);                   // source pixel (linear index in the halo tile)
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (src >= 0 && src < A_ROWS) {
+                    const int r = src / PITCH, cc = src - r * PITCH;
+                    const int y = y0 + r - 1, x = x0 + cc - 1;
+                    const int ch = half * 8;
+                    if (r >= 1 && r <= TR && cc >= 1 && cc <= TW && y < A.H && x < A.W && ch < A.Cout) {
+                        const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + ch;
+                        const float* abp = A.ab + ((size_t)g * A.C + A.out_off + ch) * 2;
+                        float v[8];
+#pragma unroll
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            if (ch + h4 * 4 < A.Cout) {
+                                const float4 gq = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
+                                const float4 xq = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
+                                const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
+                                const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
+                                v[h4 * 4 + 0] = gq.x + fmaf(c0.y, xq.x, c0.x); v[h4 * 4 + 1] = gq.y + fmaf(c0.w, xq.y, c0.z);
+                                v[h4 * 4 + 2] = gq.z + fmaf(c1.y, xq.z, c1.x); v[h4 * 4 + 3] = gq.w + fmaf(c1.w, xq.w, c1.z);
+                            } else {
+                                v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
+                            }
+                        }
+                        o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    }
+                }
+                *reinterpret_cast<uint4*>(g_s + pl * PLANE_BYTES + (size_t)row * 16) = o;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bars + s);
+        }
+        // ---- epilogue: D_ky[ci][kx*16 + co] -> atomicAdd into OIHW
+        tc::mbar_wait(bars + 4, 0);
+        tc::tc_fence_after();
+        if (warp < 2 && ntiles > 0) {
+            const int ci = ci0 + warp * 32 + lane;
+#pragma unroll 1
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll 1
+                for (int kx = 0; kx < 3; ++kx) {
+                    float v[16];
+                    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + ky * NB + kx * 16, v);
+                    if (ci < A.Cin) {
+#pragma unroll
+                        for (int co = 0; co < 16; ++co)
+                            if (co < A.Cout) atomicAdd(A.dw + (((size_t)co * A.Cin + ci) * 3 + ky) * 3 + kx, v[co]);
+                    }
+                }
+            }
+        }
+    } else if (lane == 0) {
+        const uint32_t idesc = tc::instr_desc(tc::FMT_BF16, 128, NB, 1, 1);
+        for (int it = 0; it < ntiles; ++it) {
+            const int s = it & 1;
+            tc::mbar_wait(bars + s, (it >> 1) & 1);
+            tc::tc_fence_after();
+            const uint32_t a_base = tc::smem_u32(smem + s * STAGE);
+            const uint32_t g_base = a_base + A_STAGE;
+#pragma unroll 1
+            for (int k16 = 0; k16 < KPX / 16; ++k16) {
+                const uint32_t b_addr = g_base + (uint32_t)(1 + PITCH + k16 * 16) * 16u;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t a_addr = a_base + (uint32_t)(PITCH + k16 * 16 + (ky - 1) * PITCH) * 16u;
+                    // MN-major: SBO = stride between 8-channel groups (planes), LBO = stride between 8-pixel groups (128 B)
+                    tc::mma_f16(tmem + ky * NB, tc::smem_desc(a_addr, 128, PLANE_BYTES), tc::smem_desc(b_addr, 128, PLANE_BYTES),
+                                idesc, (uint32_t)((it | k16) != 0));
+                }
+            }
+            tc::tc_commit(bars + 2 + s);
+        }
+        tc::tc_commit(bars + 4);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        __syncwarp();
+        tc::tmem_dealloc(tmem, 256);
+    }
+}
+
+}  // namespace tcwgrad
 }  // namespace endo
