@@ -137,7 +137,18 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = d.out_off; w.g_K = d.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + d.conv.w; w.db = c.gparams + d.conv.b; w.w_cin = d.cin;
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 4)) {
+    const bool tc_w = c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 4);
+    const bool tc_d = c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 2);
+    // the conv bias gradient is produced by exactly one kernel: the tcgen05 dgrad if it runs, else the FFMA wgrad if it
+    // runs, else a tiny dedicated reduction
+    if (tc_d) w.db = nullptr;
+    if (tc_w && !tc_d) {
+        ProfScope prof(PC_WGRAD, c.s);
+        bias_grad_kernel<<<kNumSMs, 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + d.conv.b, P.Ctot[l], d.out_off, d.conv.cout,
+                                                  (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
+        ENDO_CHECK_LAUNCH();
+    }
+    if (tc_w) {
         // bf16 tensor-core weight gradient (pixels are the GEMM K dimension); the bias gradient comes from the dgrad kernel
         tcwgrad::Args t;
         t.x = c.X(l); t.coef = c.COEF(d.bn); t.g = c.GX(l); t.ab = c.AB(l); t.dw = c.gparams + d.conv.w;
@@ -172,7 +183,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = d.in_off; a.N = d.cin; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.BNRED(); a.stats_C = P.maxC;
     a.x = c.X(l); a.ep_coef = c.COEF(d.bn);
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 2)) {
+    if (tc_d) {
         tcdgrad::Args t;
         t.g = c.GX(l); t.x = c.X(l); t.ab = c.AB(l); t.coef = c.COEF(d.bn); t.w = c.params + d.conv.w;
         t.gout = c.GX(l); t.db = c.gparams + d.conv.b; t.red = c.BNRED(); t.red_C = P.maxC;

@@ -550,6 +550,43 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Conv bias gradient alone: db[co] = sum_p (g + A + B x)[p][co].  Only used when the weight gradient runs on the
+// tensor cores but the data gradient does not (debug A/B combinations); normally the dgrad kernel produces it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bias_grad_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ ab, float* __restrict__ db,
+                 int C, int off, int Cout, long long npix_per_group, int G) {
+    __shared__ float red[8][16];
+    const int grp = threadIdx.x & 3, ch = grp * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch < Cout) {
+        for (int gi = 0; gi < G; ++gi) {
+            const float* abp = ab + ((size_t)gi * C + off + ch) * 2;
+            const float4 c0 = ldg4(abp), c1 = ldg4(abp + 4);
+            for (long long p = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); p < npix_per_group; p += (long long)gridDim.x * 64) {
+                const size_t o = ((size_t)gi * npix_per_group + p) * C + off + ch;
+                const float4 gq = ldg4(g + o), xq = ldg4(x + o);
+                s.x += gq.x + fmaf(c0.y, xq.x, c0.x); s.y += gq.y + fmaf(c0.w, xq.y, c0.z);
+                s.z += gq.z + fmaf(c1.y, xq.z, c1.x); s.w += gq.w + fmaf(c1.w, xq.w, c1.z);
+            }
+        }
+    }
+#pragma unroll
+    for (int o2 = 4; o2 < 32; o2 <<= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o2); s.y += __shfl_xor_sync(0xffffffffu, s.y, o2);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o2); s.w += __shfl_xor_sync(0xffffffffu, s.w, o2);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 4) { red[warp][lane * 4] = s.x; red[warp][lane * 4 + 1] = s.y; red[warp][lane * 4 + 2] = s.z; red[warp][lane * 4 + 3] = s.w; }
+    __syncthreads();
+    if (threadIdx.x < 16 && threadIdx.x < Cout) {
+        float t = 0.f;
+        for (int wq = 0; wq < 8; ++wq) t += red[wq][threadIdx.x];
+        atomicAdd(db + threadIdx.x, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // finalConv 1x1 C -> 1 followed by abs (models.py:167-169, 186): 8 lanes per pixel, HBM-bound
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -225,17 +225,18 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             const uint32_t a_base = tc::smem_u32(a_st0 + s * A_STAGE_BYTES);
             const uint32_t b_base = tc::smem_u32(b_st0 + s * B_STAGE_BYTES);
             const int nk8 = (A.K - c * KCH > 8) ? 2 : 1;           // skip an all-zero K half on the last chunk
+            // A tcgen05.mma that accumulates into the SAME TMEM tile as its predecessor waits ~266 cycles for it
+            // (measured, tests/test_gpu_tc_probe.py::test_mma_cost_by_operand_layout), whatever its size.  Consecutive
+            // MMAs therefore target different M-blocks: 9 independent accumulator chains keep the pipe busy.
 #pragma unroll 1
-            for (int mb = 0; mb < MBLK; ++mb) {
+            for (int ky = 0; ky < 3; ++ky) {
+                for (int k8 = 0; k8 < nk8; ++k8) {
+                    const uint64_t bd = tc::smem_desc(b_base + (uint32_t)(ky * 2 + k8) * B_BLOCK_BYTES, NB * 16, 128);
+                    const uint32_t a0 = a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)(PITCH + (ky - 1) * PITCH) * 16u;
+                    const uint32_t acc = (uint32_t)((c | ky | k8) != 0);
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    for (int k8 = 0; k8 < nk8; ++k8) {
-                        const uint32_t a_addr = a_base + (uint32_t)(2 * k8) * PLANE_BYTES +
-                                                (uint32_t)(PITCH + mb * 128 + (ky - 1) * PITCH) * 16u;
-                        const uint32_t b_addr = b_base + (uint32_t)(ky * 2 + k8) * B_BLOCK_BYTES;
-                        tc::mma_tf32(tmem + mb * NB, tc::smem_desc(a_addr, PLANE_BYTES, 128), tc::smem_desc(b_addr, NB * 16, 128),
-                                     idesc, (uint32_t)((c | ky | k8) != 0));
-                    }
+                    for (int mb = 0; mb < MBLK; ++mb)
+                        tc::mma_tf32(tmem + mb * NB, tc::smem_desc(a0 + (uint32_t)(mb * 128) * 16u, PLANE_BYTES, 128), bd, idesc, acc);
                 }
             }
             tc::tc_commit(bars + 2 + s);
@@ -508,23 +509,32 @@ dense_dgrad_tf32_kernel(const Args A) {
         for (int c = 0; c < nchunks; ++c) {
             tc::mbar_wait(bars + 0, c & 1);
             tc::tc_fence_after();
-            for (int mb = 0; mb < MBLK; ++mb, ++unit) {
-                const int buf = unit % NBUF;
-                if (unit >= NBUF) tc::mbar_wait(bars + 1 + NBUF + buf, ((unit / NBUF) - 1) & 1);
+            // groups of up to 4 M-blocks are issued interleaved (independent accumulators: a dependent MMA waits
+            // ~266 cycles for its predecessor); the other 4 TMEM buffers belong to the group the epilogue is draining
+            for (int mb0 = 0; mb0 < MBLK; mb0 += 4) {
+                const int gsz = (MBLK - mb0) < 4 ? (MBLK - mb0) : 4;
+                for (int u = 0; u < gsz; ++u) {
+                    const int un = unit + u, buf = un % NBUF;
+                    if (un >= NBUF) tc::mbar_wait(bars + 1 + NBUF + buf, ((un / NBUF) - 1) & 1);
+                }
                 tc::tc_fence_after();
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap - 3 * ky;
 #pragma unroll
                     for (int k8 = 0; k8 < 2; ++k8) {
-                        const uint32_t a_addr = g_base + (uint32_t)(2 * k8) * PLANE_BYTES +
-                                                (uint32_t)(1 + PITCH + mb * 128 + (ky - 1) * PITCH + (kx - 1)) * 16u;
-                        const uint32_t b_addr = w_base + (uint32_t)(tap * 2 + k8) * WBLK_BYTES;
-                        tc::mma_tf32(tmem + buf * NC, tc::smem_desc(a_addr, PLANE_BYTES, 128), tc::smem_desc(b_addr, NC * 16, 128),
-                                     idesc, (uint32_t)((tap | k8) != 0));
+                        const uint64_t bd = tc::smem_desc(w_base + (uint32_t)(tap * 2 + k8) * WBLK_BYTES, NC * 16, 128);
+                        const uint32_t a0 = g_base + (uint32_t)(2 * k8) * PLANE_BYTES +
+                                            (uint32_t)(1 + PITCH + (ky - 1) * PITCH + (kx - 1)) * 16u;
+                        for (int u = 0; u < gsz; ++u) {
+                            const int buf = (unit + u) % NBUF;
+                            tc::mma_tf32(tmem + buf * NC, tc::smem_desc(a0 + (uint32_t)((mb0 + u) * 128) * 16u, PLANE_BYTES, 128), bd,
+                                         idesc, (uint32_t)((tap | k8) != 0));
+                        }
                     }
                 }
-                tc::tc_commit(bars + 1 + buf);
+                for (int u = 0; u < gsz; ++u) tc::tc_commit(bars + 1 + (unit + u) % NBUF);
+                unit += gsz;
             }
         }
     }
@@ -595,7 +605,7 @@ dense_wgrad_bf16_kernel(const Args A) {
     const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
     const int ntiles = t_end - t_begin;
 
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 256);
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         tc::mbar_init(bars + 0, 256); tc::mbar_init(bars + 1, 256);
         tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
@@ -637,26 +647,42 @@ dense_wgrad_bf16_kernel(const Args A) {
                         for (int e = 4; e < 8; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
                     }
                 }
-#pragma unroll 2
-                for (int px = tid >> 3; px < A_ROWS; px += 32) {
-                    const int r = px / PITCH, cc = px - r * PITCH;
-                    const int y = y0 + r - 1, x = x0 + cc - 1;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                    if (ch_ok && y >= 0 && y < A.H && x >= 0 && x < A.W) {
-                        const float* p = A.x + (img + (size_t)y * A.W + x) * A.C + A.in_off + ch;
-                        const float4 q0 = __ldg(reinterpret_cast<const float4*>(p));
-                        float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (hi_ok) q1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-                        const float v0 = fmaxf(fmaf(k[0].x, q0.x - k[0].z, k[0].y), 0.f), v1 = fmaxf(fmaf(k[1].x, q0.y - k[1].z, k[1].y), 0.f);
-                        const float v2 = fmaxf(fmaf(k[2].x, q0.z - k[2].z, k[2].y), 0.f), v3 = fmaxf(fmaf(k[3].x, q0.w - k[3].z, k[3].y), 0.f);
-                        float v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
-                        if (hi_ok) {
-                            v4 = fmaxf(fmaf(k[4].x, q1.x - k[4].z, k[4].y), 0.f); v5 = fmaxf(fmaf(k[5].x, q1.y - k[5].z, k[5].y), 0.f);
-                            v6 = fmaxf(fmaf(k[6].x, q1.z - k[6].z, k[6].y), 0.f); v7 = fmaxf(fmaf(k[7].x, q1.w - k[7].z, k[7].y), 0.f);
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {               // 11 pixels per thread: batches of 6 and 5, loads first
+                    float4 q0[6], q1[6];
+                    unsigned okmask = 0u;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int px = (tid >> 3) + 32 * (part * 6 + j);
+                        const int r = px / PITCH, cc = px - r * PITCH;
+                        const int y = y0 + r - 1, x = x0 + cc - 1;
+                        q0[j] = make_float4(0.f, 0.f, 0.f, 0.f); q1[j] = q0[j];
+                        if (ch_ok && px < A_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) {
+                            const float* p = A.x + (img + (size_t)y * A.W + x) * A.C + A.in_off + ch;
+                            q0[j] = __ldg(reinterpret_cast<const float4*>(p));
+                            if (hi_ok) q1[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                            okmask |= 1u << j;
                         }
-                        o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
                     }
-                    *reinterpret_cast<uint4*>(a_s + grp * PLANE_BYTES + (size_t)px * 16) = o;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int px = (tid >> 3) + 32 * (part * 6 + j);
+                        if (px < A_ROWS) {
+                            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                            if (okmask & (1u << j)) {
+                                const float4 a0 = q0[j], a1 = q1[j];
+                                const float v0 = fmaxf(fmaf(k[0].x, a0.x - k[0].z, k[0].y), 0.f), v1 = fmaxf(fmaf(k[1].x, a0.y - k[1].z, k[1].y), 0.f);
+                                const float v2 = fmaxf(fmaf(k[2].x, a0.z - k[2].z, k[2].y), 0.f), v3 = fmaxf(fmaf(k[3].x, a0.w - k[3].z, k[3].y), 0.f);
+                                float v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
+                                if (hi_ok) {
+                                    v4 = fmaxf(fmaf(k[4].x, a1.x - k[4].z, k[4].y), 0.f); v5 = fmaxf(fmaf(k[5].x, a1.y - k[5].z, k[5].y), 0.f);
+                                    v6 = fmaxf(fmaf(k[6].x, a1.z - k[6].z, k[6].y), 0.f); v7 = fmaxf(fmaf(k[7].x, a1.w - k[7].z, k[7].y), 0.f);
+                                }
+                                o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
+                            }
+                            *reinterpret_cast<uint4*>(a_s + grp * PLANE_BYTES + (size_t)px * 16) = o;
+                        }
+                    }
                 }
             }
             // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile interior
@@ -703,8 +729,12 @@ dense_wgrad_bf16_kernel(const Args A) {
             for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll 1
                 for (int kx = 0; kx < 3; ++kx) {
-                    float v[16];
+                    float v[16], v1[16], v2[16];                      // the three interleaved accumulator sets
                     tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + ky * NB + kx * 16, v);
+                    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (3 + ky) * NB + kx * 16, v1);
+                    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (6 + ky) * NB + kx * 16, v2);
+#pragma unroll
+                    for (int co = 0; co < 16; ++co) v[co] += v1[co] + v2[co];
                     if (ci < A.Cin) {
 #pragma unroll
                         for (int co = 0; co < 16; ++co)
@@ -721,15 +751,18 @@ dense_wgrad_bf16_kernel(const Args A) {
             tc::tc_fence_after();
             const uint32_t a_base = tc::smem_u32(smem + s * STAGE);
             const uint32_t g_base = a_base + A_STAGE;
+            // consecutive K-steps rotate over three accumulator sets (9 independent chains): an MMA that accumulates
+            // into the tile its predecessor wrote waits ~266 cycles for it
 #pragma unroll 1
             for (int k16 = 0; k16 < KPX / 16; ++k16) {
+                const int set = k16 % 3;
                 const uint32_t b_addr = g_base + (uint32_t)(1 + PITCH + k16 * 16) * 16u;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     const uint32_t a_addr = a_base + (uint32_t)(PITCH + k16 * 16 + (ky - 1) * PITCH) * 16u;
                     // MN-major: SBO = stride between 8-channel groups (planes), LBO = stride between 8-pixel groups (128 B)
-                    tc::mma_f16(tmem + ky * NB, tc::smem_desc(a_addr, 128, PLANE_BYTES), tc::smem_desc(b_addr, 128, PLANE_BYTES),
-                                idesc, (uint32_t)((it | k16) != 0));
+                    tc::mma_f16(tmem + (set * 3 + ky) * NB, tc::smem_desc(a_addr, 128, PLANE_BYTES), tc::smem_desc(b_addr, 128, PLANE_BYTES),
+                                idesc, (uint32_t)(it != 0 || k16 >= 3));
                 }
             }
             tc::tc_commit(bars + 2 + s);
@@ -740,7 +773,7 @@ dense_wgrad_bf16_kernel(const Args A) {
     __syncthreads();
     if (warp == 8) {
         __syncwarp();
-        tc::tmem_dealloc(tmem, 256);
+        tc::tmem_dealloc(tmem, 512);
     }
 }
 

@@ -92,6 +92,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 
+// SWIZZLE_128B K-major operand: every row is 128 bytes of K (32 tf32 / 64 bf16), rows 128 B apart, 8-row atoms of
+// 1024 B (SBO = 1024); the 16-byte chunk index is XOR-ed with (row & 7).  When the start address is not 1024-byte
+// aligned (row sliding), base_offset = (start >> 7) & 7 keeps the XOR phase tied to the absolute address.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           ((uint64_t)((saddr >> 7) & 7u) << 49) | (2ull << 61);
+}
+
 // Instruction descriptor (upper 32 bits of the "idesc" operand), dense, fp32 accumulate:
 //   [4,6) D format: 1 = F32   [7,10) A format  [10,13) B format (0 = F16, 1 = BF16, 2 = TF32)
 //   [15] A major (0 = K)      [16] B major (0 = K)   [17,23) N >> 3    [24,29) M >> 4

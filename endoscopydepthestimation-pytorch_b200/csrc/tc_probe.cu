@@ -13,11 +13,12 @@ namespace endo {
 struct ProbeArgs {
     const float* A; const float* B; float* D;
     int a_rows, N, K, shift, fmt, a_mn, b_mn;
+    int swz, reps; long long* cycles;      // swz: 0 = SWIZZLE_NONE, 2 = SWIZZLE_128B (K-major only); reps: repeat the MMA chain (timing)
 };
 
 __global__ void __launch_bounds__(128)
 tc_probe_kernel(const ProbeArgs P) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -27,16 +28,22 @@ tc_probe_kernel(const ProbeArgs P) {
     // ---- shared layout
     unsigned char* a_s = smem;
     const uint32_t a_bytes = (uint32_t)P.a_rows * P.K * es;
-    unsigned char* b_s = smem + ((a_bytes + 127) / 128) * 128;
+    unsigned char* b_s = smem + ((a_bytes + 1023) / 1024) * 1024;
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
     if (!P.a_mn) { a_sbo = 128; a_lbo = (uint32_t)P.a_rows * 16; }         // K-major: planes of rows x 16 B
     else { a_sbo = 128; a_lbo = (uint32_t)(P.a_rows / T) * 128; }          // MN-major: 128-B blocks (T mn x 8 k)
     if (!P.b_mn) { b_sbo = 128; b_lbo = (uint32_t)P.N * 16; }
     else { b_sbo = 128; b_lbo = (uint32_t)(P.N / T) * 128; }
 
+    const int kpr = 128 / es;                             // K elements per 128-byte swizzled row
     auto put = [&](unsigned char* base, bool mn, uint32_t lbo, uint32_t sbo, int r, int k, float v) {
         uint32_t off;
-        if (!mn) off = (uint32_t)(k / T) * lbo + (uint32_t)r * 16 + (uint32_t)(k % T) * es;
+        if (P.swz == 2) {                                 // slab (k / kpr) of [rows][128 B], chunk index XOR (row & 7)
+            const int rows = (base == a_s) ? P.a_rows : P.N;
+            const int kk = k % kpr;
+            off = (uint32_t)(k / kpr) * (uint32_t)rows * 128u + (uint32_t)r * 128u +
+                  (uint32_t)((((kk * es) >> 4) ^ (r & 7)) << 4) + (uint32_t)((kk * es) & 15);
+        } else if (!mn) off = (uint32_t)(k / T) * lbo + (uint32_t)r * 16 + (uint32_t)(k % T) * es;
         else off = (uint32_t)(r % T) * es + (uint32_t)(k % 8) * 16 + (uint32_t)(r / T) * sbo + (uint32_t)(k / 8) * lbo;
         if (es == 4) *reinterpret_cast<float*>(base + off) = v;
         else *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(v);
@@ -55,17 +62,29 @@ tc_probe_kernel(const ProbeArgs P) {
 
     if (tid == 0) {
         const uint32_t idesc = tc::instr_desc(P.fmt, 128, P.N, P.a_mn, P.b_mn);
-        for (int k0 = 0; k0 < P.K; k0 += kstep) {
-            uint32_t a_addr = tc::smem_u32(a_s), b_addr = tc::smem_u32(b_s);
-            if (!P.a_mn) a_addr += (uint32_t)(k0 / T) * a_lbo + (uint32_t)P.shift * 16;
-            else a_addr += (uint32_t)(k0 / 8) * a_lbo + (uint32_t)(P.shift / T) * a_sbo;
-            if (!P.b_mn) b_addr += (uint32_t)(k0 / T) * b_lbo;
-            else b_addr += (uint32_t)(k0 / 8) * b_lbo;
-            const uint64_t ad = tc::smem_desc(a_addr, a_lbo, a_sbo), bd = tc::smem_desc(b_addr, b_lbo, b_sbo);
-            if (P.fmt == tc::FMT_TF32) tc::mma_tf32(tmem, ad, bd, idesc, k0 > 0);
-            else tc::mma_f16(tmem, ad, bd, idesc, k0 > 0);
+        const long long t0 = clock64();
+        for (int rep = 0; rep < P.reps; ++rep) {
+            for (int k0 = 0; k0 < P.K; k0 += kstep) {
+                uint32_t a_addr = tc::smem_u32(a_s), b_addr = tc::smem_u32(b_s);
+                uint64_t ad, bd;
+                if (P.swz == 2) {
+                    a_addr += (uint32_t)(k0 / kpr) * (uint32_t)P.a_rows * 128u + (uint32_t)P.shift * 128u + (uint32_t)((k0 % kpr) * es);
+                    b_addr += (uint32_t)(k0 / kpr) * (uint32_t)P.N * 128u + (uint32_t)((k0 % kpr) * es);
+                    ad = tc::smem_desc_sw128(a_addr); bd = tc::smem_desc_sw128(b_addr);
+                } else {
+                    if (!P.a_mn) a_addr += (uint32_t)(k0 / T) * a_lbo + (uint32_t)P.shift * 16;
+                    else a_addr += (uint32_t)(k0 / 8) * a_lbo + (uint32_t)(P.shift / T) * a_sbo;
+                    if (!P.b_mn) b_addr += (uint32_t)(k0 / T) * b_lbo;
+                    else b_addr += (uint32_t)(k0 / 8) * b_lbo;
+                    ad = tc::smem_desc(a_addr, a_lbo, a_sbo); bd = tc::smem_desc(b_addr, b_lbo, b_sbo);
+                }
+                if (P.fmt == tc::FMT_TF32) tc::mma_tf32(tmem, ad, bd, idesc, (rep | k0) != 0);
+                else tc::mma_f16(tmem, ad, bd, idesc, (rep | k0) != 0);
+            }
         }
         tc::tc_commit(&bar);
+        tc::mbar_wait(&bar, 0);
+        if (P.cycles) P.cycles[0] = clock64() - t0;
     }
     tc::mbar_wait(&bar, 0);
     tc::tc_fence_after();
@@ -84,7 +103,8 @@ tc_probe_kernel(const ProbeArgs P) {
 using namespace endo;
 
 extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, int K, int shift, int fmt,
-                             int a_mn_major, int b_mn_major, endo_stream_t stream) {
+                             int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles,
+                             endo_stream_t stream) {
     if (!A || !B || !D) return ENDO_ERR_BAD_POINTER;
     const int kstep = (fmt == tc::FMT_TF32) ? 8 : 16;
     const int T = (fmt == tc::FMT_TF32) ? 4 : 8;
@@ -92,14 +112,17 @@ extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_row
         shift < 0 || a_rows < 128 + shift || (a_rows % 8) || (a_mn_major && ((shift % T) || (a_rows % T))))
         return ENDO_ERR_BAD_SHAPE;
     const int es = (fmt == tc::FMT_TF32) ? 4 : 2;
-    const size_t smem = ((size_t)a_rows * K * es + 127) / 128 * 128 + (size_t)N * K * es + 256;
+    if (swizzle != 0 && swizzle != 2) return ENDO_ERR_BAD_SHAPE;
+    if (swizzle == 2 && (a_mn_major || b_mn_major || (K * es) % 128)) return ENDO_ERR_BAD_SHAPE;
+    if (reps < 1) reps = 1;
+    const size_t smem = ((size_t)a_rows * K * es + 1023) / 1024 * 1024 + (size_t)N * K * es + 2048;
     if (smem > 200 * 1024) return ENDO_ERR_BAD_SHAPE;
     static bool configured = false;
     if (!configured) {
         ENDO_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    ProbeArgs p{A, B, D, a_rows, N, K, shift, fmt, a_mn_major, b_mn_major};
+    ProbeArgs p{A, B, D, a_rows, N, K, shift, fmt, a_mn_major, b_mn_major, swizzle, reps, cycles};
     tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;

