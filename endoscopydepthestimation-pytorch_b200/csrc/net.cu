@@ -50,6 +50,10 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
 
 // ENDO_TC_DISABLE (bit mask, debugging / A-B tests only): 1 = forward, 2 = data gradient, 4 = weight gradient fall back
 // to the FFMA kernels even when the math mode asks for tensor cores.
+static int tc_debug_mask() {
+    const char* e = getenv("ENDO_TC_DEBUG");
+    return e ? atoi(e) : 0;
+}
 static int tc_disable_mask() {
     const char* e = getenv("ENDO_TC_DISABLE");
     return e ? atoi(e) : 0;
@@ -66,6 +70,8 @@ struct Ctx {
     double* ST(int l) const { return reinterpret_cast<double*>(acts + P.stat_off[l]); }
     float* MI(int l) const { return reinterpret_cast<float*>(acts + P.mi_off[l]); }
     float* COEF(const BnP& b) const { return reinterpret_cast<float*>(acts) + b.coef; }
+    float* WPACK() const { return reinterpret_cast<float*>(acts + P.wpack_off); }
+    float* WPACK_BWD() const { return reinterpret_cast<float*>(scratch + P.wpack_bwd_off); }
     float* GX(int l) const { return reinterpret_cast<float*>(scratch + P.gx_off[l]); }
     float* AB(int l) const { return reinterpret_cast<float*>(scratch + P.ab_off[l]); }
     double* BNRED() const { return reinterpret_cast<double*>(scratch + P.bnred_off); }
@@ -111,7 +117,13 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         tcconv::FwdArgs t;
         t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
         t.in_C = a.in_C; t.in_off = a.in_off; t.K = a.K; t.out_C = a.out_C; t.out_off = a.out_off; t.N = a.N;
-        t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C;
+        t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask();
+        t.wpack = c.WPACK();
+        {
+            ProfScope prof(PC_BN, c.s);
+            tcconv::pack_w_fwd_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
+            ENDO_CHECK_LAUNCH();
+        }
         static bool configured = false;
         if (!configured) {
             ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -152,6 +164,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         // bf16 tensor-core weight gradient (pixels are the GEMM K dimension); the bias gradient comes from the dgrad kernel
         tcwgrad::Args t;
         t.x = c.X(l); t.coef = c.COEF(d.bn); t.g = c.GX(l); t.ab = c.AB(l); t.dw = c.gparams + d.conv.w;
+        t.xa = c.X(l); t.xa_C = P.Ctot[l]; t.up = 0;
         t.C = P.Ctot[l]; t.in_off = d.in_off; t.Cin = d.cin; t.out_off = d.out_off; t.Cout = d.conv.cout;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         t.n_tiles = P.B * cdiv(t.H, tcwgrad::TR) * cdiv(t.W, tcwgrad::TW);
@@ -189,6 +202,12 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.gout = c.GX(l); t.db = c.gparams + d.conv.b; t.red = c.BNRED(); t.red_C = P.maxC;
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
+        t.wpack = c.WPACK_BWD();
+        {
+            ProfScope prof(PC_BN, c.s);
+            tcconv::pack_w_dgrad_kernel<<<cdiv(t.Cin, 64), 256, 0, c.s>>>(t.w, t.Cin, t.Cout, c.WPACK_BWD());
+            ENDO_CHECK_LAUNCH();
+        }
         static bool configured = false;
         if (!configured) {
             ENDO_CUDA(cudaFuncSetAttribute(tcdgrad::dense_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -265,6 +284,33 @@ static int trans_up_fwd(const Ctx& c, int i) {
     a.w = c.params + t.conv.w; a.bias = c.params + t.conv.b; a.w_cin = t.cin;
     a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = 0; a.N = t.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l); a.stats_C = P.Ctot[l];
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 8)) {
+        // tcgen05: the DenseLayer forward kernel with the upsampling loader, 16 output channels per pass
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcconv::SMEM_BYTES));
+            configured = true;
+        }
+        for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
+            tcconv::FwdArgs f;
+            f.in = a.in; f.coef = nullptr; f.w = a.w + (size_t)co0 * t.cin * 9; f.bias = a.bias + co0; f.out = a.out; f.stats = a.stats;
+            f.in_C = a.in_C; f.in_off = a.in_off; f.K = a.K; f.out_C = a.out_C; f.out_off = a.out_off + co0;
+            f.N = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
+            f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.up = 1; f.dbg = 0;
+            f.wpack = c.WPACK();
+            {
+                ProfScope prof(PC_BN, c.s);
+                tcconv::pack_w_fwd_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
+                ENDO_CHECK_LAUNCH();
+            }
+            dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
+            ProfScope prof(PC_CONV_TRANS_FWD, c.s);
+            tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(f);
+            ENDO_CHECK_LAUNCH();
+        }
+        return ENDO_OK;
+    }
     return launch_conv<3, 2, 48, 8, LM_PLAIN, EM_STORE, WM_FWD, true>(a, c.s);
 }
 
@@ -277,7 +323,42 @@ static int trans_up_bwd(const Ctx& c, int i) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = 0; w.g_K = t.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = t.cin;
-    ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.s)));
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 16)) {
+        // tcgen05 (bf16): the DenseLayer weight-gradient kernel with the upsampling loader, 16 output channels per pass;
+        // the bias gradient comes from the small dedicated reduction
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcwgrad::dense_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcwgrad::SMEM_BYTES));
+            configured = true;
+        }
+        for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
+            const int nco = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
+            {
+                ProfScope prof(PC_WGRAD, c.s);
+                bias_grad_kernel<<<kNumSMs, 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b + co0, P.Ctot[l], co0, nco,
+                                                          (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
+                ENDO_CHECK_LAUNCH();
+            }
+            tcwgrad::Args q;
+            q.x = c.X(l); q.coef = nullptr; q.g = c.GX(l); q.ab = c.AB(l); q.dw = c.gparams + t.conv.w + (size_t)co0 * t.cin * 9;
+            q.xa = c.X(ls); q.xa_C = P.Ctot[ls]; q.up = 1;
+            q.C = P.Ctot[l]; q.in_off = t.src_off; q.Cin = t.cin; q.out_off = co0; q.Cout = nco;
+            q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
+            q.n_tiles = P.B * cdiv(q.H, tcwgrad::TR) * cdiv(q.W, tcwgrad::TW);
+            const int yblocks = cdiv(t.cin, tcwgrad::MCH);
+            int want = (2 * kNumSMs) / yblocks;
+            if (want > q.n_tiles) want = q.n_tiles;
+            if (want < 1) want = 1;
+            q.tiles_per_cta = cdiv(q.n_tiles, want);
+            dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
+            ProfScope prof(PC_WGRAD, c.s);
+            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(q);
+            ENDO_CHECK_LAUNCH();
+        }
+    } else {
+        ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.s)));
+    }
     ConvArgs a = base_args(c);
     a.in = c.GX(l); a.in2 = c.X(l); a.in_ab = c.AB(l); a.in_C = P.Ctot[l]; a.in_off = 0; a.K = t.conv.cout;
     a.ih = P.h[l]; a.iw = P.w[l];

@@ -43,11 +43,13 @@ struct NetPlan {
     long long stat_off[kMaxLevels];             // double [G][Ctot][2]  (sum, sumsq)
     long long mi_off[kMaxLevels];               // float  [G][Ctot][2]  (mean, invstd)
     long long pre_off;                          // float  [B*H*W] finalConv output before abs
+    long long wpack_off;                        // 256 KB: tensor-core weight image of the layer being run (forward)
     long long acts_bytes;
     // byte offsets inside the backward scratch block
     long long gx_off[kMaxLevels];               // float [B,h,w,Ctot] gradient buffers
     long long ab_off[kMaxLevels];               // float [G][Ctot][2] lazy BN-backward correction (A, Bc)
     long long bnred_off;                        // double [G][maxC][2] per-layer BN backward sums
+    long long wpack_bwd_off;                    // 256 KB: tensor-core weight image of the layer being run (backward)
     long long scratch_bytes;
     int maxC;
     ConvP first, final_;
@@ -170,12 +172,14 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         off = align_up(off + 1ll * B * P.h[l + 1] * P.w[l + 1] * (P.C0[l] + P.Dn[l]), 256);
     }
     P.pre_off = off; off = align_up(off + 4ll * B * H * W, 256);
+    P.wpack_off = off; off += 256 * 1024;
     P.acts_bytes = off;
     // ---- backward scratch block
     off = 0;
     for (int l = 0; l <= nd; ++l) { P.gx_off[l] = off; off = align_up(off + 4ll * B * P.h[l] * P.w[l] * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.ab_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }
     P.bnred_off = off; off = align_up(off + 16ll * P.G * P.maxC, 256);
+    P.wpack_bwd_off = off; off += 256 * 1024;
     P.scratch_bytes = off;
     return ENDO_OK;
 }

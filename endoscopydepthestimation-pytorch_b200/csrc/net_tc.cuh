@@ -43,9 +43,41 @@ constexpr int EDGE_FLOATS = NUNITS * 2 * 16;
 constexpr int SMEM_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES + EDGE_FLOATS * 4 + 8 * 16 * 2 * 4 + 128;
 constexpr int NTHREADS = 288;
 
+// Weight images: the exact shared-memory layout of one pipeline stage, built once per layer call by a tiny kernel so
+// that the producers copy them with coalesced 128-bit loads (staging OIHW weights with scalar, serialised loads cost
+// more than the activation stream in the first version of these kernels).
+//   forward : chunk c (16 input channels) -> [blk = ky*2 + k8][kc][n = kx*16 + co][4]           2304 floats
+//   dgrad   : chunk c (64 input channels) -> [blk = tap*2 + k8][kc][n = ci - 64c][4], taps flipped 9216 floats
+__global__ void __launch_bounds__(256)
+pack_w_fwd_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 2304; d += 256) {
+        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int ky = blk >> 1, k8 = blk & 1, co = n & 15, kx = n >> 4, cin = c * 16 + k8 * 8 + kc * 4 + e;
+        float v = 0.f;
+        if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
+        out[(size_t)c * 2304 + d] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+pack_w_dgrad_kernel(const float* __restrict__ w, int Cin, int Cout, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 9216; d += 256) {
+        const int blk = d >> 9, r = d & 511, kc = r >> 8, n = (r & 255) >> 2, e = r & 3;
+        const int tap = blk >> 1, k8 = blk & 1, co = k8 * 8 + kc * 4 + e, ci = c * 64 + n;
+        float v = 0.f;
+        if (co < Cout && ci < Cin) v = __ldg(w + ((size_t)co * Cin + ci) * 9 + (8 - tap));
+        out[(size_t)c * 9216 + d] = v;
+    }
+}
+
 struct FwdArgs {
     const float* in; const float* coef; const float* w; const float* bias; float* out; double* stats;
     int in_C, in_off, K, out_C, out_off, N, H, W, B, G, stats_C;
+    int up;      // 0: operand = relu(bn(x)) of the same-resolution buffer (DenseLayer); 1: operand = x of the half-resolution
+                 //    buffer, nearest-upsampled x2, no BatchNorm (TransitionUp, models.py:73-74)
+    int dbg;     // performance experiments only (ENDO_TC_DEBUG): 1 = skip the MMAs, 2 = skip the activation loads
+    const float* wpack;   // weight image built by pack_w_fwd_kernel (2304 floats per 16-channel chunk)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -88,12 +120,14 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             const int ch = c * KCH + grp * 4;
             float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
             const bool ch_ok = ch < A.K;
-            if (ch_ok) {
+            if (ch_ok && !A.up) {
                 const float* cf = A.coef + ((size_t)g * A.K + ch) * 4;
                 k0 = __ldg(reinterpret_cast<const float4*>(cf)); k1 = __ldg(reinterpret_cast<const float4*>(cf + 4));
                 k2 = __ldg(reinterpret_cast<const float4*>(cf + 8)); k3 = __ldg(reinterpret_cast<const float4*>(cf + 12));
             }
-            const float* in_b = A.in + (size_t)b * A.H * A.W * A.in_C + A.in_off + ch;
+            const int sh = A.up ? 1 : 0;                              // source = (y >> sh, x >> sh) of a (H >> sh) x (W >> sh) buffer
+            const int sW = A.W >> sh;
+            const float* in_b = A.in + (size_t)b * (A.H >> sh) * sW * A.in_C + A.in_off + ch;
             // 19 pixels per thread, issued as two batches of 10 independent 16-byte loads (memory-level parallelism:
             // the kernel is bound by how many bytes each SM keeps in flight, not by the tensor core)
 #pragma unroll
@@ -105,10 +139,10 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const int px = (tid >> 2) + 64 * (half * 10 + j);
                     const int r = px / PITCH, cc = px - r * PITCH;
                     const int y = y0 + r - 1, x = x0 + cc - 1;
-                    const bool ok = ch_ok && (px < REAL_ROWS) && y >= 0 && y < A.H && x >= 0 && x < A.W;
+                    const bool ok = ch_ok && (px < REAL_ROWS) && y >= 0 && y < A.H && x >= 0 && x < A.W && !(A.dbg & 2);
                     q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok) {
-                        q[j] = __ldg(reinterpret_cast<const float4*>(in_b + ((size_t)y * A.W + x) * A.in_C));
+                        q[j] = __ldg(reinterpret_cast<const float4*>(in_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.in_C));
                         okmask |= 1u << j;
                     }
                 }
@@ -118,22 +152,31 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     if (px < REAL_ROWS) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (okmask & (1u << j)) {
-                            v.x = fmaxf(fmaf(k0.x, q[j].x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q[j].y - k1.z, k1.y), 0.f);
-                            v.z = fmaxf(fmaf(k2.x, q[j].z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q[j].w - k3.z, k3.y), 0.f);
+                            if (A.up) v = q[j];
+                            else {
+                                v.x = fmaxf(fmaf(k0.x, q[j].x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q[j].y - k1.z, k1.y), 0.f);
+                                v.z = fmaxf(fmaf(k2.x, q[j].z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q[j].w - k3.z, k3.y), 0.f);
+                            }
                         }
                         *reinterpret_cast<float4*>(a_s + (size_t)px * 16) = v;
                     }
                 }
             }
-            // weights of this channel chunk: block (ky, k8) = [2 chunks][48 rows (kx*16 + co)][4 tf32]
-            unsigned char* b_s = b_st0 + s * B_STAGE_BYTES;
-            for (int idx = tid; idx < 3 * (KCH / 8) * NB * 8; idx += 256) {
-                const int k = idx & 7, n = (idx >> 3) % NB, blk = idx / (8 * NB);      // blk = ky * 2 + k8
-                const int ky = blk >> 1, k8 = blk & 1;
-                const int co = n & 15, kx = n >> 4, cin = c * KCH + k8 * 8 + k;
-                float v = 0.f;
-                if (co < A.N && cin < A.K) v = __ldg(A.w + (((size_t)co * A.K + cin) * 3 + ky) * 3 + kx);
-                *reinterpret_cast<float*>(b_s + blk * B_BLOCK_BYTES + (k >> 2) * (NB * 16) + n * 16 + (k & 3) * 4) = v;
+            // weights of this channel chunk: 9,216-byte image copied verbatim
+            {
+                unsigned char* b_s = b_st0 + s * B_STAGE_BYTES;
+                const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 2304);
+                float4 wq[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int i = tid + 256 * j;
+                    wq[j] = (i < 576) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int i = tid + 256 * j;
+                    if (i < 576) *reinterpret_cast<float4*>(b_s + (size_t)i * 16) = wq[j];
+                }
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bars + s);
@@ -228,15 +271,17 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             // A tcgen05.mma that accumulates into the SAME TMEM tile as its predecessor waits ~266 cycles for it
             // (measured, tests/test_gpu_tc_probe.py::test_mma_cost_by_operand_layout), whatever its size.  Consecutive
             // MMAs therefore target different M-blocks: 9 independent accumulator chains keep the pipe busy.
+            const uint64_t a_hi = tc::smem_desc(0, PLANE_BYTES, 128), b_hi = tc::smem_desc(0, NB * 16, 128);
 #pragma unroll 1
             for (int ky = 0; ky < 3; ++ky) {
                 for (int k8 = 0; k8 < nk8; ++k8) {
-                    const uint64_t bd = tc::smem_desc(b_base + (uint32_t)(ky * 2 + k8) * B_BLOCK_BYTES, NB * 16, 128);
-                    const uint32_t a0 = a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)(PITCH + (ky - 1) * PITCH) * 16u;
+                    if (A.dbg & 1) continue;
+                    const uint64_t bd = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + k8) * B_BLOCK_BYTES) >> 4);
+                    // address field counts 16-byte units = pixel rows: +128 per M-block
+                    const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)(PITCH + (ky - 1) * PITCH) * 16u) >> 4);
                     const uint32_t acc = (uint32_t)((c | ky | k8) != 0);
 #pragma unroll
-                    for (int mb = 0; mb < MBLK; ++mb)
-                        tc::mma_tf32(tmem + mb * NB, tc::smem_desc(a0 + (uint32_t)(mb * 128) * 16u, PLANE_BYTES, 128), bd, idesc, acc);
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, acc);
                 }
             }
             tc::tc_commit(bars + 2 + s);
@@ -290,6 +335,7 @@ struct Args {
     const float* g; const float* x; const float* ab;      // gradient buffer, activation buffer, lazy correction [G][C][2]
     const float* coef;                                    // this BN's (a, beta, mean, invstd) [G][Cin][4]
     const float* w;                                       // OIHW [Cout][Cin][3][3]
+    const float* wpack;                                   // weight image built by pack_w_dgrad_kernel (9216 floats per 64-channel chunk)
     float* gout;                                          // gradient buffer (same as g), accumulated at in_off..in_off+Cin
     float* db;                                            // conv bias gradient [Cout] (sum of the output gradient), accumulated
     double* red; int red_C;                               // [G][red_C][2] BN backward sums
@@ -389,13 +435,13 @@ dense_dgrad_tf32_kernel(const Args A) {
         for (int c = 0; c < nchunks; ++c) {
             const int ci0 = c * NC;
             // ------------------------------------------------------------ weights + BN table of this ci chunk
-            for (int idx = tid; idx < 9 * 2 * NC * 8; idx += 256) {
-                const int k = idx & 7, n = (idx >> 3) % NC, blk = idx / (8 * NC);          // blk = tap * 2 + k8
-                const int tap = blk >> 1, k8 = blk & 1;
-                const int co = k8 * 8 + k, ci = ci0 + n;
-                float v = 0.f;
-                if (co < A.Cout && ci < A.Cin) v = __ldg(A.w + ((size_t)co * A.Cin + ci) * 9 + (8 - tap));
-                *reinterpret_cast<float*>(w_s + blk * WBLK_BYTES + (k >> 2) * (NC * 16) + n * 16 + (k & 3) * 4) = v;
+            {   // 36,864-byte weight image of this chunk, copied verbatim (9 x 16 B per thread, all loads first)
+                const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 9216);
+                float4 wq[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) wq[j] = __ldg(src + tid + 256 * j);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) *reinterpret_cast<float4*>(w_s + (size_t)(tid + 256 * j) * 16) = wq[j];
             }
             if (tid < NC) {
                 const int ci = ci0 + tid;
@@ -518,18 +564,18 @@ dense_dgrad_tf32_kernel(const Args A) {
                     if (un >= NBUF) tc::mbar_wait(bars + 1 + NBUF + buf, ((un / NBUF) - 1) & 1);
                 }
                 tc::tc_fence_after();
+                const uint64_t a_hi = tc::smem_desc(0, PLANE_BYTES, 128), b_hi = tc::smem_desc(0, NC * 16, 128);
 #pragma unroll 1
                 for (int tap = 0; tap < 9; ++tap) {
                     const int ky = tap / 3, kx = tap - 3 * ky;
 #pragma unroll
                     for (int k8 = 0; k8 < 2; ++k8) {
-                        const uint64_t bd = tc::smem_desc(w_base + (uint32_t)(tap * 2 + k8) * WBLK_BYTES, NC * 16, 128);
-                        const uint32_t a0 = g_base + (uint32_t)(2 * k8) * PLANE_BYTES +
-                                            (uint32_t)(1 + PITCH + (ky - 1) * PITCH + (kx - 1)) * 16u;
+                        const uint64_t bd = b_hi | (uint64_t)((w_base + (uint32_t)(tap * 2 + k8) * WBLK_BYTES) >> 4);
+                        const uint64_t ad0 = a_hi | (uint64_t)((g_base + (uint32_t)(2 * k8) * PLANE_BYTES +
+                                                               (uint32_t)(1 + PITCH + (ky - 1) * PITCH + (kx - 1)) * 16u) >> 4);
                         for (int u = 0; u < gsz; ++u) {
                             const int buf = (unit + u) % NBUF;
-                            tc::mma_tf32(tmem + buf * NC, tc::smem_desc(a0 + (uint32_t)((mb0 + u) * 128) * 16u, PLANE_BYTES, 128), bd,
-                                         idesc, (uint32_t)((tap | k8) != 0));
+                            tc::mma_tf32(tmem + buf * NC, ad0 + (uint64_t)((mb0 + u) * 128), bd, idesc, (uint32_t)((tap | k8) != 0));
                         }
                     }
                 }
@@ -584,6 +630,8 @@ struct Args {
     float* dw;                                           // OIHW gradient (accumulated); the bias gradient comes from the dgrad kernel
     int C, in_off, Cin, out_off, Cout, H, W, B, G;
     int tiles_per_cta, n_tiles;
+    const float* xa; int xa_C, up;                       // activation source: buffer + channel stride; up = 1: half-resolution buffer,
+                                                         // nearest-upsampled x2, no BatchNorm (TransitionUp)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -638,7 +686,7 @@ dense_wgrad_bf16_kernel(const Args A) {
                 float4 k[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) k[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch_ok) {
+                if (ch_ok && !A.up) {
                     const float* cf = A.coef + ((size_t)g * A.Cin + ch) * 4;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
@@ -647,6 +695,9 @@ dense_wgrad_bf16_kernel(const Args A) {
                         for (int e = 4; e < 8; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
                     }
                 }
+                const int sh = A.up ? 1 : 0;
+                const int sW = A.W >> sh;
+                const float* xa_b = A.xa + (size_t)b * (A.H >> sh) * sW * A.xa_C + A.in_off + ch;
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {               // 11 pixels per thread: batches of 6 and 5, loads first
                     float4 q0[6], q1[6];
@@ -658,7 +709,7 @@ dense_wgrad_bf16_kernel(const Args A) {
                         const int y = y0 + r - 1, x = x0 + cc - 1;
                         q0[j] = make_float4(0.f, 0.f, 0.f, 0.f); q1[j] = q0[j];
                         if (ch_ok && px < A_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) {
-                            const float* p = A.x + (img + (size_t)y * A.W + x) * A.C + A.in_off + ch;
+                            const float* p = xa_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.xa_C;
                             q0[j] = __ldg(reinterpret_cast<const float4*>(p));
                             if (hi_ok) q1[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
                             okmask |= 1u << j;
@@ -671,12 +722,15 @@ dense_wgrad_bf16_kernel(const Args A) {
                             uint4 o = make_uint4(0u, 0u, 0u, 0u);
                             if (okmask & (1u << j)) {
                                 const float4 a0 = q0[j], a1 = q1[j];
-                                const float v0 = fmaxf(fmaf(k[0].x, a0.x - k[0].z, k[0].y), 0.f), v1 = fmaxf(fmaf(k[1].x, a0.y - k[1].z, k[1].y), 0.f);
-                                const float v2 = fmaxf(fmaf(k[2].x, a0.z - k[2].z, k[2].y), 0.f), v3 = fmaxf(fmaf(k[3].x, a0.w - k[3].z, k[3].y), 0.f);
-                                float v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f;
-                                if (hi_ok) {
-                                    v4 = fmaxf(fmaf(k[4].x, a1.x - k[4].z, k[4].y), 0.f); v5 = fmaxf(fmaf(k[5].x, a1.y - k[5].z, k[5].y), 0.f);
-                                    v6 = fmaxf(fmaf(k[6].x, a1.z - k[6].z, k[6].y), 0.f); v7 = fmaxf(fmaf(k[7].x, a1.w - k[7].z, k[7].y), 0.f);
+                                float v0 = a0.x, v1 = a0.y, v2 = a0.z, v3 = a0.w, v4 = a1.x, v5 = a1.y, v6 = a1.z, v7 = a1.w;
+                                if (!A.up) {
+                                    v0 = fmaxf(fmaf(k[0].x, a0.x - k[0].z, k[0].y), 0.f); v1 = fmaxf(fmaf(k[1].x, a0.y - k[1].z, k[1].y), 0.f);
+                                    v2 = fmaxf(fmaf(k[2].x, a0.z - k[2].z, k[2].y), 0.f); v3 = fmaxf(fmaf(k[3].x, a0.w - k[3].z, k[3].y), 0.f);
+                                    v4 = v5 = v6 = v7 = 0.f;
+                                    if (hi_ok) {
+                                        v4 = fmaxf(fmaf(k[4].x, a1.x - k[4].z, k[4].y), 0.f); v5 = fmaxf(fmaf(k[5].x, a1.y - k[5].z, k[5].y), 0.f);
+                                        v6 = fmaxf(fmaf(k[6].x, a1.z - k[6].z, k[6].y), 0.f); v7 = fmaxf(fmaf(k[7].x, a1.w - k[7].z, k[7].y), 0.f);
+                                    }
                                 }
                                 o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
                             }
@@ -685,37 +739,52 @@ dense_wgrad_bf16_kernel(const Args A) {
                     }
                 }
             }
-            // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile interior
-            for (int idx = tid; idx < 6 * (A_ROWS + 2); idx += 256) {
-                const int pl = idx % 6, row = idx / 6;                // row 0 and A_ROWS+1 are margins
-                const int kx = pl >> 1, half = pl & 1;
-                const int src = row - 1 - (kx - 1);                   // source pixel (linear index in the halo tile)
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (src >= 0 && src < A_ROWS) {
-                    const int r = src / PITCH, cc = src - r * PITCH;
-                    const int y = y0 + r - 1, x = x0 + cc - 1;
-                    const int ch = half * 8;
-                    if (r >= 1 && r <= TR && cc >= 1 && cc <= TW && y < A.H && x < A.W && ch < A.Cout) {
-                        const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + ch;
-                        const float* abp = A.ab + ((size_t)g * A.C + A.out_off + ch) * 2;
-                        float v[8];
+            // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile
+            //      interior.  One thread per interior pixel: all of its loads are issued before any use, then the 16
+            //      corrected channels are written into the three kx-shifted planes.
+            {
+                uint4* gz = reinterpret_cast<uint4*>(g_s);
+                for (int i = tid; i < G_STAGE / 16; i += 256) gz[i] = make_uint4(0u, 0u, 0u, 0u);
+                const int r = 1 + (tid >> 5), cc = 1 + (tid & 31);
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                const bool ok = (y < A.H) && (x < A.W);
+                float4 gq[4], xq[4];
 #pragma unroll
-                        for (int h4 = 0; h4 < 2; ++h4) {
-                            if (ch + h4 * 4 < A.Cout) {
-                                const float4 gq = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
-                                const float4 xq = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
-                                const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
-                                const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
-                                v[h4 * 4 + 0] = gq.x + fmaf(c0.y, xq.x, c0.x); v[h4 * 4 + 1] = gq.y + fmaf(c0.w, xq.y, c0.z);
-                                v[h4 * 4 + 2] = gq.z + fmaf(c1.y, xq.z, c1.x); v[h4 * 4 + 3] = gq.w + fmaf(c1.w, xq.w, c1.z);
-                            } else {
-                                v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
-                            }
+                for (int h4 = 0; h4 < 4; ++h4) { gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4]; }
+                const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off;
+                if (ok) {
+#pragma unroll
+                    for (int h4 = 0; h4 < 4; ++h4) {
+                        if (h4 * 4 < A.Cout) {
+                            gq[h4] = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
+                            xq[h4] = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
                         }
-                        o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                     }
                 }
-                *reinterpret_cast<uint4*>(g_s + pl * PLANE_BYTES + (size_t)row * 16) = o;
+                float v[16];
+                const float* abp = A.ab + ((size_t)g * A.C + A.out_off) * 2;
+#pragma unroll
+                for (int h4 = 0; h4 < 4; ++h4) {
+                    if (ok && h4 * 4 < A.Cout) {
+                        const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
+                        const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
+                        v[h4 * 4 + 0] = gq[h4].x + fmaf(c0.y, xq[h4].x, c0.x); v[h4 * 4 + 1] = gq[h4].y + fmaf(c0.w, xq[h4].y, c0.z);
+                        v[h4 * 4 + 2] = gq[h4].z + fmaf(c1.y, xq[h4].z, c1.x); v[h4 * 4 + 3] = gq[h4].w + fmaf(c1.w, xq[h4].w, c1.z);
+                    } else {
+                        v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");            // zero fill complete before the interior is written
+                if (ok) {
+                    const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    const int q = r * PITCH + cc;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + 0) * PLANE_BYTES + (size_t)(q + kx) * 16) = lo;
+                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + 1) * PLANE_BYTES + (size_t)(q + kx) * 16) = hi;
+                    }
+                }
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bars + s);
@@ -753,17 +822,16 @@ dense_wgrad_bf16_kernel(const Args A) {
             const uint32_t g_base = a_base + A_STAGE;
             // consecutive K-steps rotate over three accumulator sets (9 independent chains): an MMA that accumulates
             // into the tile its predecessor wrote waits ~266 cycles for it
+            const uint64_t d_hi = tc::smem_desc(0, 128, PLANE_BYTES);   // MN-major: LBO = 8-pixel groups (128 B), SBO = 8-channel groups (planes)
+            const uint64_t a_d0 = d_hi | (uint64_t)(a_base >> 4), b_d0 = d_hi | (uint64_t)((g_base + 16u) >> 4);
 #pragma unroll 1
             for (int k16 = 0; k16 < KPX / 16; ++k16) {
                 const int set = k16 % 3;
-                const uint32_t b_addr = g_base + (uint32_t)(1 + PITCH + k16 * 16) * 16u;
+                const uint64_t bd = b_d0 + (uint64_t)(PITCH + k16 * 16);
+                const uint32_t acc = (uint32_t)(it != 0 || k16 >= 3);
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const uint32_t a_addr = a_base + (uint32_t)(PITCH + k16 * 16 + (ky - 1) * PITCH) * 16u;
-                    // MN-major: SBO = stride between 8-channel groups (planes), LBO = stride between 8-pixel groups (128 B)
-                    tc::mma_f16(tmem + (set * 3 + ky) * NB, tc::smem_desc(a_addr, 128, PLANE_BYTES), tc::smem_desc(b_addr, 128, PLANE_BYTES),
-                                idesc, (uint32_t)(it != 0 || k16 >= 3));
-                }
+                for (int ky = 0; ky < 3; ++ky)
+                    tc::mma_f16(tmem + (set * 3 + ky) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16 + (ky - 1) * PITCH), bd, idesc, acc);
             }
             tc::tc_commit(bars + 2 + s);
         }

@@ -14,6 +14,7 @@ struct ProbeArgs {
     const float* A; const float* B; float* D;
     int a_rows, N, K, shift, fmt, a_mn, b_mn;
     int swz, reps; long long* cycles;      // swz: 0 = SWIZZLE_NONE, 2 = SWIZZLE_128B (K-major only); reps: repeat the MMA chain (timing)
+    int rotate;                            // timing only: consecutive reps target `rotate` different accumulator tiles
 };
 
 __global__ void __launch_bounds__(128)
@@ -51,7 +52,7 @@ tc_probe_kernel(const ProbeArgs P) {
     for (int i = tid; i < P.a_rows * P.K; i += 128) put(a_s, P.a_mn, a_lbo, a_sbo, i / P.K, i % P.K, P.A[i]);
     for (int i = tid; i < P.N * P.K; i += 128) put(b_s, P.b_mn, b_lbo, b_sbo, i / P.K, i % P.K, P.B[i]);
 
-    const uint32_t ncols = P.N <= 32 ? 32 : (P.N <= 64 ? 64 : (P.N <= 128 ? 128 : 256));
+    const uint32_t ncols = P.rotate > 1 ? 512u : (P.N <= 32 ? 32 : (P.N <= 64 ? 64 : (P.N <= 128 ? 128 : 256)));
     if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
     if (tid == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
     tc::fence_proxy_async();
@@ -78,8 +79,10 @@ tc_probe_kernel(const ProbeArgs P) {
                     else b_addr += (uint32_t)(k0 / 8) * b_lbo;
                     ad = tc::smem_desc(a_addr, a_lbo, a_sbo); bd = tc::smem_desc(b_addr, b_lbo, b_sbo);
                 }
-                if (P.fmt == tc::FMT_TF32) tc::mma_tf32(tmem, ad, bd, idesc, (rep | k0) != 0);
-                else tc::mma_f16(tmem, ad, bd, idesc, (rep | k0) != 0);
+                const uint32_t dcol = (P.rotate > 1) ? (uint32_t)((rep % P.rotate) * P.N) : 0u;
+                const uint32_t accf = (P.rotate > 1) ? (uint32_t)(rep >= P.rotate || k0 > 0) : (uint32_t)((rep | k0) != 0);
+                if (P.fmt == tc::FMT_TF32) tc::mma_tf32(tmem + dcol, ad, bd, idesc, accf);
+                else tc::mma_f16(tmem + dcol, ad, bd, idesc, accf);
             }
         }
         tc::tc_commit(&bar);
@@ -103,7 +106,7 @@ tc_probe_kernel(const ProbeArgs P) {
 using namespace endo;
 
 extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, int K, int shift, int fmt,
-                             int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles,
+                             int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles, int rotate,
                              endo_stream_t stream) {
     if (!A || !B || !D) return ENDO_ERR_BAD_POINTER;
     const int kstep = (fmt == tc::FMT_TF32) ? 8 : 16;
@@ -115,6 +118,8 @@ extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_row
     if (swizzle != 0 && swizzle != 2) return ENDO_ERR_BAD_SHAPE;
     if (swizzle == 2 && (a_mn_major || b_mn_major || (K * es) % 128)) return ENDO_ERR_BAD_SHAPE;
     if (reps < 1) reps = 1;
+    if (rotate < 1) rotate = 1;
+    if (rotate > 1 && rotate * N > 512) return ENDO_ERR_BAD_SHAPE;
     const size_t smem = ((size_t)a_rows * K * es + 1023) / 1024 * 1024 + (size_t)N * K * es + 2048;
     if (smem > 200 * 1024) return ENDO_ERR_BAD_SHAPE;
     static bool configured = false;
@@ -122,7 +127,7 @@ extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_row
         ENDO_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
-    ProbeArgs p{A, B, D, a_rows, N, K, shift, fmt, a_mn_major, b_mn_major, swizzle, reps, cycles};
+    ProbeArgs p{A, B, D, a_rows, N, K, shift, fmt, a_mn_major, b_mn_major, swizzle, reps, cycles, rotate};
     tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;

@@ -193,7 +193,8 @@ int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long lo
  * cycles from first issue to completion: the per-MMA cost of an operand layout can be read off directly.
  * ---------------------------------------------------------------------------------------------- */
 int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, int K, int shift, int fmt,
-                  int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles, endo_stream_t stream);
+                  int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles, int rotate,
+                  endo_stream_t stream);   /* rotate > 1 (timing only): reps cycle over that many accumulator tiles */
 
 #ifdef __cplusplus
 }

@@ -9,14 +9,14 @@ pytestmark = pytest.mark.gpu
 TF32, BF16 = 2, 1
 
 
-def _run(a_rows, n, k, shift, fmt, a_mn, b_mn, swz=0, reps=1):
+def _run(a_rows, n, k, shift, fmt, a_mn, b_mn, swz=0, reps=1, rotate=1):
     g = torch.Generator().manual_seed(a_rows * 7 + n * 3 + k + shift)
     a = torch.randn(a_rows, k, generator=g).cuda()
     b = torch.randn(n, k, generator=g).cuda()
     d = torch.full((128, n), float("nan"), device="cuda")
     cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
     _lib.check(_lib.lib().endo_tc_probe(a.data_ptr(), b.data_ptr(), d.data_ptr(), a_rows, n, k, shift, fmt, a_mn, b_mn,
-                                        swz, reps, cyc.data_ptr(), _lib.stream_ptr(a.device)), "tc_probe")
+                                        swz, reps, cyc.data_ptr(), rotate, _lib.stream_ptr(a.device)), "tc_probe")
     torch.cuda.synchronize()
     _run.cycles = int(cyc.item())
     if fmt == BF16:
@@ -26,7 +26,7 @@ def _run(a_rows, n, k, shift, fmt, a_mn, b_mn, swz=0, reps=1):
         # tf32 keeps 10 mantissa bits of each input (truncation or rounding is implementation-defined)
         ar, br = a.double(), b.double()
         tol = 2e-3
-    ref = (ar[shift:shift + 128] @ br.t()) * reps
+    ref = (ar[shift:shift + 128] @ br.t()) * ((reps + rotate - 1) // rotate)
     err = float((d.double() - ref).abs().max() / ref.abs().max())
     return err, tol
 
@@ -71,4 +71,16 @@ def test_mma_cost_by_operand_layout():
             err, tol = _run(168, n, k, 0, TF32, 0, 0, swz=swz, reps=reps)
             n_mma = reps * k // 8
             print(f"N={n:3d} swizzle={swz}: {_run.cycles / n_mma:7.1f} cycles per MMA ({n_mma} MMAs), err {err:.1e}")
+            assert err < 5e-3
+
+
+def test_mma_cost_independent_accumulators():
+    """Same microbenchmark, but consecutive MMAs rotate over several accumulator tiles (printed with -s): tells a
+    dependent-accumulate latency from a per-instruction throughput limit."""
+    for fmt, name, k in ((TF32, "tf32", 32), (BF16, "bf16", 64)):
+        for n, rot in ((48, 1), (48, 8), (64, 8), (128, 4), (256, 2)):
+            reps = 64
+            err, tol = _run(168, n, k, 0, fmt, 0, 0, swz=0, reps=reps, rotate=rot)
+            n_mma = reps * (k // (8 if fmt == TF32 else 16))
+            print(f"{name} N={n:3d} rotate={rot}: {_run.cycles / n_mma:7.1f} cycles per MMA, err {err:.1e}")
             assert err < 5e-3
