@@ -164,7 +164,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         // bf16 tensor-core weight gradient (pixels are the GEMM K dimension); the bias gradient comes from the dgrad kernel
         tcwgrad::Args t;
         t.x = c.X(l); t.coef = c.COEF(d.bn); t.g = c.GX(l); t.ab = c.AB(l); t.dw = c.gparams + d.conv.w;
-        t.xa = c.X(l); t.xa_C = P.Ctot[l]; t.up = 0;
+        t.xa = c.X(l); t.xa_C = P.Ctot[l]; t.up = 0; t.one = 0;
         t.C = P.Ctot[l]; t.in_off = d.in_off; t.Cin = d.cin; t.out_off = d.out_off; t.Cout = d.conv.cout;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         t.n_tiles = P.B * cdiv(t.H, tcwgrad::TR) * cdiv(t.W, tcwgrad::TW);
@@ -256,7 +256,44 @@ static int trans_down_bwd(const Ctx& c, int l) {
     w.g_off = P.offIn[l + 1]; w.g_K = cs; w.g_h = P.h[l + 1]; w.g_w = P.w[l + 1];
     w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = cs;
-    ENDO_TRY((launch_wgrad<1, 48, 1, 4, LM_BNRELU, LM_GRADPOOL, false>(w, c.s)));
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 32)) {
+        // tcgen05 (bf16): the weight-gradient kernel in 1x1 mode, 48 output channels per launch; bias gradient = sum of the
+        // routed (= of the pooled) gradient, reduced over the coarse buffer
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcwgrad::dense_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcwgrad::SMEM_BYTES));
+            configured = true;
+        }
+        for (int co0 = 0; co0 < cs; co0 += 16) {
+            const int nco = (cs - co0) < 16 ? (cs - co0) : 16;
+            ProfScope prof(PC_WGRAD, c.s);
+            bias_grad_kernel<<<kNumSMs / 2, 256, 0, c.s>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b + co0, P.Ctot[l + 1],
+                                                          P.offIn[l + 1] + co0, nco, (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
+            ENDO_CHECK_LAUNCH();
+        }
+        for (int co0 = 0; co0 < cs; co0 += 48) {
+            tcwgrad::Args q;
+            q.x = c.X(l); q.coef = c.COEF(t.bn); q.g = nullptr; q.ab = nullptr; q.dw = c.gparams + t.conv.w;
+            q.xa = c.X(l); q.xa_C = P.Ctot[l]; q.up = 0;
+            q.C = P.Ctot[l]; q.in_off = P.offIn[l]; q.Cin = cs; q.out_off = co0; q.Cout = cs;
+            q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
+            q.one = 1; q.argmax = am; q.gc = c.GX(l + 1); q.xc = c.X(l + 1); q.abc = c.AB(l + 1); q.cC = P.Ctot[l + 1];
+            q.c_off = P.offIn[l + 1]; q.cH = P.h[l + 1]; q.cW = P.w[l + 1];
+            q.n_tiles = P.B * cdiv(q.H, tcwgrad::TR) * cdiv(q.W, tcwgrad::TW);
+            const int yblocks = cdiv(cs, tcwgrad::MCH);
+            int want = (2 * kNumSMs) / yblocks;
+            if (want > q.n_tiles) want = q.n_tiles;
+            if (want < 1) want = 1;
+            q.tiles_per_cta = cdiv(q.n_tiles, want);
+            dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
+            ProfScope prof(PC_WGRAD, c.s);
+            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(q);
+            ENDO_CHECK_LAUNCH();
+        }
+    } else {
+        ENDO_TRY((launch_wgrad<1, 48, 1, 4, LM_BNRELU, LM_GRADPOOL, false>(w, c.s)));
+    }
     ConvArgs a = base_args(c);
     a.in = c.GX(l + 1); a.in2 = c.X(l + 1); a.in_ab = c.AB(l + 1); a.argmax = am; a.in_C = P.Ctot[l + 1];
     a.in_off = P.offIn[l + 1]; a.K = cs; a.ih = P.h[l + 1]; a.iw = P.w[l + 1];
@@ -342,7 +379,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
             }
             tcwgrad::Args q;
             q.x = c.X(l); q.coef = nullptr; q.g = c.GX(l); q.ab = c.AB(l); q.dw = c.gparams + t.conv.w + (size_t)co0 * t.cin * 9;
-            q.xa = c.X(ls); q.xa_C = P.Ctot[ls]; q.up = 1;
+            q.xa = c.X(ls); q.xa_C = P.Ctot[ls]; q.up = 1; q.one = 0;
             q.C = P.Ctot[l]; q.in_off = t.src_off; q.Cin = t.cin; q.out_off = co0; q.Cout = nco;
             q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
             q.n_tiles = P.B * cdiv(q.H, tcwgrad::TR) * cdiv(q.W, tcwgrad::TW);
@@ -489,5 +526,12 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         w.dw = g_params + P.first.w; w.db = g_params + P.first.b; w.w_cin = cfg->in_channels;
         ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.s)));
     }
+    return ENDO_OK;
+}
+
+extern "C" int endo_debug_trace_read(long long* host_out, int n) {
+    if (!host_out || n <= 0 || n > 2048) return ENDO_ERR_BAD_SHAPE;
+    ENDO_CUDA(cudaDeviceSynchronize());
+    ENDO_CUDA(cudaMemcpyFromSymbol(host_out, endo::g_tc_trace, sizeof(long long) * (size_t)n));
     return ENDO_OK;
 }

@@ -151,24 +151,58 @@ conv_kernel(const ConvArgs A) {
                 a_s[kk * PLANE + pix] = v;
             }
         } else {
-            for (int idx = threadIdx.x; idx < TRP * TWP * (KC / 4); idx += NT) {
-                const int q = idx % (KC / 4), pix = idx / (KC / 4);
-                const int r = pix / TWP, c = pix - r * TWP;
-                const float4 v = load_a4<LM, UP>(A, b, g, y0 + r - PAD, x0 + c - PAD, k0 + q * 4);
-                float* d = a_s + (q * 4) * PLANE + pix;
-                d[0] = v.x; d[PLANE] = v.y; d[2 * PLANE] = v.z; d[3 * PLANE] = v.w;
+            // loads first, stores second (batches of 6): every thread keeps several 16-byte loads in flight instead
+            // of one load -> transform -> store round trip per iteration
+            constexpr int NA = (TRP * TWP * (KC / 4) + NT - 1) / NT;
+#pragma unroll
+            for (int b0 = 0; b0 < NA; b0 += 6) {
+                float4 v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int idx = threadIdx.x + (b0 + j) * NT;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + j < NA && idx < TRP * TWP * (KC / 4)) {
+                        const int q = idx % (KC / 4), pix = idx / (KC / 4);
+                        const int r = pix / TWP, c = pix - r * TWP;
+                        v[j] = load_a4<LM, UP>(A, b, g, y0 + r - PAD, x0 + c - PAD, k0 + q * 4);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int idx = threadIdx.x + (b0 + j) * NT;
+                    if (b0 + j < NA && idx < TRP * TWP * (KC / 4)) {
+                        const int q = idx % (KC / 4), pix = idx / (KC / 4);
+                        float* d = a_s + (q * 4) * PLANE + pix;
+                        d[0] = v[j].x; d[PLANE] = v[j].y; d[2 * PLANE] = v[j].z; d[3 * PLANE] = v[j].w;
+                    }
+                }
             }
         }
-        // ---- stage weights: w_s[kk][tap][n]
-        for (int idx = threadIdx.x; idx < CO * KC * TAPS; idx += NT) {
-            const int tap = idx % TAPS, kk = (idx / TAPS) % KC, n = idx / (TAPS * KC);
-            const int k = k0 + kk, nn = n0 + n;
-            float v = 0.f;
-            if (k < A.K && nn < A.N) {
-                if constexpr (WM == WM_FWD) v = __ldg(A.w + ((size_t)nn * A.w_cin + k) * TAPS + tap);
-                else v = __ldg(A.w + ((size_t)k * A.w_cin + nn) * TAPS + (TAPS - 1 - tap));
+        // ---- stage weights: w_s[kk][tap][n]  (all loads of this chunk issued before the first store)
+        {
+            constexpr int NWV = (CO * KC * TAPS + NT - 1) / NT;
+            float wv[NWV];
+#pragma unroll
+            for (int j = 0; j < NWV; ++j) {
+                const int idx = threadIdx.x + j * NT;
+                wv[j] = 0.f;
+                if (idx < CO * KC * TAPS) {
+                    const int tap = idx % TAPS, kk = (idx / TAPS) % KC, n = idx / (TAPS * KC);
+                    const int k = k0 + kk, nn = n0 + n;
+                    if (k < A.K && nn < A.N) {
+                        if constexpr (WM == WM_FWD) wv[j] = __ldg(A.w + ((size_t)nn * A.w_cin + k) * TAPS + tap);
+                        else wv[j] = __ldg(A.w + ((size_t)k * A.w_cin + nn) * TAPS + (TAPS - 1 - tap));
+                    }
+                }
             }
-            w_s[(kk * TAPS + tap) * CO + n] = v;
+#pragma unroll
+            for (int j = 0; j < NWV; ++j) {
+                const int idx = threadIdx.x + j * NT;
+                if (idx < CO * KC * TAPS) {
+                    const int tap = idx % TAPS, kk = (idx / TAPS) % KC, n = idx / (TAPS * KC);
+                    w_s[(kk * TAPS + tap) * CO + n] = wv[j];
+                }
+            }
         }
         __syncthreads();
         // ---- main loop: PX x CO register tile per thread
@@ -411,19 +445,51 @@ wgrad_kernel(const WgradArgs A) {
                 a_s[pix * 32 + ci] = v;
             }
         } else {
-            for (int idx = threadIdx.x; idx < TRP * TWP * 8; idx += NT) {
-                const int q = idx & 7, pix = idx >> 3;
-                const int r = pix / TWP, c = pix - r * TWP;
-                const float4 v = load_a4<LMA, UP>(LA, b, g, y0 + r - PAD, x0 + c - PAD, c0 + q * 4);
-                *reinterpret_cast<float4*>(a_s + pix * 32 + q * 4) = v;
+            constexpr int NA = (TRP * TWP * 8 + NT - 1) / NT;       // loads first, stores second (batches of 7)
+#pragma unroll
+            for (int b0 = 0; b0 < NA; b0 += 7) {
+                float4 v[7];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int idx = threadIdx.x + (b0 + j) * NT;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + j < NA && idx < TRP * TWP * 8) {
+                        const int q = idx & 7, pix = idx >> 3;
+                        const int r = pix / TWP, c = pix - r * TWP;
+                        v[j] = load_a4<LMA, UP>(LA, b, g, y0 + r - PAD, x0 + c - PAD, c0 + q * 4);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const int idx = threadIdx.x + (b0 + j) * NT;
+                    if (b0 + j < NA && idx < TRP * TWP * 8) *reinterpret_cast<float4*>(a_s + (idx >> 3) * 32 + (idx & 7) * 4) = v[j];
+                }
             }
         }
         // stage g: [row][col][co]
-        for (int idx = threadIdx.x; idx < TR * 32 * (COT / 4); idx += NT) {
-            const int q = idx % (COT / 4), pix = idx / (COT / 4);
-            const int r = pix >> 5, c = pix & 31;
-            const float4 v = load_a4<LMG, false>(LG, b, g, y0 + r, x0 + c, co0 + q * 4);
-            *reinterpret_cast<float4*>(g_s + pix * COT + q * 4) = v;
+        {
+            constexpr int NG = (TR * 32 * (COT / 4) + NT - 1) / NT;
+#pragma unroll
+            for (int b0 = 0; b0 < NG; b0 += 6) {
+                float4 v[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int idx = threadIdx.x + (b0 + j) * NT;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b0 + j < NG && idx < TR * 32 * (COT / 4)) {
+                        const int q = idx % (COT / 4), pix = idx / (COT / 4);
+                        v[j] = load_a4<LMG, false>(LG, b, g, y0 + (pix >> 5), x0 + (pix & 31), co0 + q * 4);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int idx = threadIdx.x + (b0 + j) * NT;
+                    if (b0 + j < NG && idx < TR * 32 * (COT / 4)) {
+                        const int q = idx % (COT / 4), pix = idx / (COT / 4);
+                        *reinterpret_cast<float4*>(g_s + pix * COT + q * 4) = v[j];
+                    }
+                }
+            }
         }
         __syncthreads();
         for (int r = ps; r < TR; r += NPS) {

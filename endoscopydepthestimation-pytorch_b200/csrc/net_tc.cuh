@@ -26,6 +26,10 @@
 #include "tc_common.cuh"
 
 namespace endo {
+// clock64() trace of CTA 0 of the most recent traced launch (ENDO_TC_DEBUG bit 4): see tools/trace_fwd.py
+__device__ long long g_tc_trace[2048];
+#define ENDO_TRACE(slot) do { if ((A.dbg & 4) && blockIdx.x == 0 && blockIdx.z == 0) g_tc_trace[(slot)] = clock64(); } while (0)
+
 namespace tcconv {
 
 constexpr int TH = 32, TW = 32, PITCH = 34;
@@ -40,8 +44,9 @@ constexpr int B_BLOCK_BYTES = 2 * NB * 16;             // one (ky, k8) weight bl
 constexpr int B_STAGE_BYTES = 3 * (KCH / 8) * B_BLOCK_BYTES;
 constexpr int NUNITS = MBLK * 4;                       // (M-block, lane quadrant) epilogue units
 constexpr int EDGE_FLOATS = NUNITS * 2 * 16;
-constexpr int SMEM_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES + EDGE_FLOATS * 4 + 8 * 16 * 2 * 4 + 128;
-constexpr int NTHREADS = 288;
+constexpr int NPROD = 512;                              // 16 producer / epilogue warps + 1 MMA warp
+constexpr int SMEM_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES + EDGE_FLOATS * 4 + 16 * 16 * 2 * 4 + 128;
+constexpr int NTHREADS = NPROD + 32;
 
 // Weight images: the exact shared-memory layout of one pipeline stage, built once per layer call by a tiny kernel so
 // that the producers copy them with coalesced 128-bit loads (staging OIHW weights with scalar, serialised loads cost
@@ -86,8 +91,8 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     unsigned char* a_st0 = smem;
     unsigned char* b_st0 = smem + 2 * A_STAGE_BYTES;
     float* edge = reinterpret_cast<float*>(smem + 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES);   // [NUNITS][2][16]
-    float* red = edge + EDGE_FLOATS;                                                        // [8][16][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * 16 * 2);                         // full[2], empty[2], accum
+    float* red = edge + EDGE_FLOATS;                                                        // [16][16][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16 * 16 * 2);                         // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -98,9 +103,10 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     const int g = b / (A.B / A.G);
     const int nchunks = (A.K + KCH - 1) / KCH;
 
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) ENDO_TRACE(1);
+    if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        tc::mbar_init(bars + 0, 256); tc::mbar_init(bars + 1, 256);
+        tc::mbar_init(bars + 0, NPROD); tc::mbar_init(bars + 1, NPROD);
         tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
         tc::mbar_init(bars + 4, 1);
         tc::fence_mbar_init();
@@ -110,12 +116,14 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < 16) {
         // ======================================================================== producers
         const int grp = tid & 3;                                  // this thread always stages the same 4-channel group
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1;
+            if (tid == 0) ENDO_TRACE(16 + c * 8 + 0);
             if (c >= 2) tc::mbar_wait(bars + 2 + s, ((c >> 1) - 1) & 1);
+            if (tid == 0) ENDO_TRACE(16 + c * 8 + 1);
             unsigned char* a_s = a_st0 + s * A_STAGE_BYTES + grp * PLANE_BYTES;
             const int ch = c * KCH + grp * 4;
             float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
@@ -128,15 +136,14 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             const int sh = A.up ? 1 : 0;                              // source = (y >> sh, x >> sh) of a (H >> sh) x (W >> sh) buffer
             const int sW = A.W >> sh;
             const float* in_b = A.in + (size_t)b * (A.H >> sh) * sW * A.in_C + A.in_off + ch;
-            // 19 pixels per thread, issued as two batches of 10 independent 16-byte loads (memory-level parallelism:
-            // the kernel is bound by how many bytes each SM keeps in flight, not by the tensor core)
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            // 10 pixels per thread (512 producer threads, 4 per pixel): ONE batch of independent 16-byte loads, i.e. one
+            // memory round trip per stage with 80 KB per SM in flight (the kernel is bound by bytes in flight)
+            {
                 float4 q[10];
                 unsigned okmask = 0u;
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
-                    const int px = (tid >> 2) + 64 * (half * 10 + j);
+                    const int px = (tid >> 2) + 128 * j;
                     const int r = px / PITCH, cc = px - r * PITCH;
                     const int y = y0 + r - 1, x = x0 + cc - 1;
                     const bool ok = ch_ok && (px < REAL_ROWS) && y >= 0 && y < A.H && x >= 0 && x < A.W && !(A.dbg & 2);
@@ -148,7 +155,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 }
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
-                    const int px = (tid >> 2) + 64 * (half * 10 + j);
+                    const int px = (tid >> 2) + 128 * j;
                     if (px < REAL_ROWS) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (okmask & (1u << j)) {
@@ -162,58 +169,65 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     }
                 }
             }
+            if (tid == 0) ENDO_TRACE(16 + c * 8 + 2);
             // weights of this channel chunk: 9,216-byte image copied verbatim
             {
                 unsigned char* b_s = b_st0 + s * B_STAGE_BYTES;
                 const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 2304);
-                float4 wq[3];
+                float4 wq[2];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int i = tid + 256 * j;
+                for (int j = 0; j < 2; ++j) {
+                    const int i = tid + NPROD * j;
                     wq[j] = (i < 576) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int i = tid + 256 * j;
+                for (int j = 0; j < 2; ++j) {
+                    const int i = tid + NPROD * j;
                     if (i < 576) *reinterpret_cast<float4*>(b_s + (size_t)i * 16) = wq[j];
                 }
             }
+            if (tid == 0) ENDO_TRACE(16 + c * 8 + 3);
             tc::fence_proxy_async();
             tc::mbar_arrive(bars + s);
+            if (tid == 0) ENDO_TRACE(16 + c * 8 + 4);
         }
         // ======================================================================== epilogue
+        if (tid == 0) ENDO_TRACE(2);
         tc::mbar_wait(bars + 4, 0);
         tc::tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;
+        if (tid == 0) ENDO_TRACE(3);
+        const int q = warp & 3, part = warp >> 2;             // TMEM lane quadrant, and which M-blocks this warp drains
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         // pass 1: publish the values the neighbouring 32-lane units need
-        for (int mb = half; mb < MBLK; mb += 2) {
+        for (int mb = part; mb < MBLK; mb += 4) {
             const int u = mb * 4 + q;
-            float v0[16], v2[16];
-            tc::tmem_ld16(tmem + lane_base + mb * NB + 0, v0);
-            tc::tmem_ld16(tmem + lane_base + mb * NB + 32, v2);
+            uint32_t r0[16], r2[16];
+            tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 0, r0);
+            tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 32, r2);
+            tc::tmem_ld_wait();
             if (lane == 31) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) edge[(u * 2 + 1) * 16 + j] = v0[j];    // kx = 0 part of my last pixel
+                for (int j = 0; j < 16; ++j) edge[(u * 2 + 1) * 16 + j] = __uint_as_float(r0[j]);    // kx = 0 part of my last pixel
             }
             if (lane == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) edge[(u * 2 + 0) * 16 + j] = v2[j];    // kx = 2 part of my first pixel
+                for (int j = 0; j < 16; ++j) edge[(u * 2 + 0) * 16 + j] = __uint_as_float(r2[j]);    // kx = 2 part of my first pixel
             }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
         float bias[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) bias[j] = (j < A.N) ? __ldg(A.bias + j) : 0.f;
-        for (int mb = half; mb < MBLK; mb += 2) {
+        for (int mb = part; mb < MBLK; mb += 4) {
             const int u = mb * 4 + q;
-            float v0[16], v1[16], v2[16];
-            tc::tmem_ld16(tmem + lane_base + mb * NB + 0, v0);
-            tc::tmem_ld16(tmem + lane_base + mb * NB + 16, v1);
-            tc::tmem_ld16(tmem + lane_base + mb * NB + 32, v2);
+            uint32_t v0[16], v1[16], v2[16];
+            tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 0, v0);
+            tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 16, v1);
+            tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 32, v2);
+            tc::tmem_ld_wait();
             const int L = PITCH + mb * 128 + q * 32 + lane;           // linear index in the halo tile
             const int r = L / PITCH, cc = L - r * PITCH;
             const int y = y0 + r - 1, x = x0 + cc - 1;
@@ -221,11 +235,11 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             float o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                float left = __shfl_up_sync(0xffffffffu, v0[j], 1);
-                float right = __shfl_down_sync(0xffffffffu, v2[j], 1);
+                float left = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
+                float right = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
                 if (lane == 0) left = (u > 0) ? edge[((u - 1) * 2 + 1) * 16 + j] : 0.f;
                 if (lane == 31) right = (u < NUNITS - 1) ? edge[((u + 1) * 2 + 0) * 16 + j] : 0.f;
-                o[j] = (left + v1[j]) + right + bias[j];
+                o[j] = (left + __uint_as_float(v1[j])) + right + bias[j];
             }
             if (ok) {
                 float* op = A.out + ((size_t)(b * A.H + y) * A.W + x) * A.out_C + A.out_off;
@@ -250,12 +264,12 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             }
             if (lane == 0) { red[(warp * 16 + j) * 2] = a; red[(warp * 16 + j) * 2 + 1] = c2; }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         if (tid < 2 * A.N) {
             const int j = tid >> 1, which = tid & 1;
             double sum = 0.0;
 #pragma unroll
-            for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * 16 + j) * 2 + which];
+            for (int wq = 0; wq < 16; ++wq) sum += (double)red[(wq * 16 + j) * 2 + which];
             atomicAdd(A.stats + ((size_t)g * A.stats_C + A.out_off + j) * 2 + which, sum);
         }
     } else if (lane == 0) {
@@ -263,8 +277,10 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NB);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1;
+            ENDO_TRACE(16 + c * 8 + 5);
             tc::mbar_wait(bars + s, (c >> 1) & 1);
             tc::tc_fence_after();
+            ENDO_TRACE(16 + c * 8 + 6);
             const uint32_t a_base = tc::smem_u32(a_st0 + s * A_STAGE_BYTES);
             const uint32_t b_base = tc::smem_u32(b_st0 + s * B_STAGE_BYTES);
             const int nk8 = (A.K - c * KCH > 8) ? 2 : 1;           // skip an all-zero K half on the last chunk
@@ -285,15 +301,18 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 }
             }
             tc::tc_commit(bars + 2 + s);
+            ENDO_TRACE(16 + c * 8 + 7);
         }
         tc::tc_commit(bars + 4);
     }
+    if (tid == 0) ENDO_TRACE(4);
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         __syncwarp();
         tc::tmem_dealloc(tmem, 512);
     }
+    if (tid == 0) { ENDO_TRACE(5); if ((A.dbg & 4) && blockIdx.x == 0 && blockIdx.z == 0) g_tc_trace[0] = nchunks; }
 }
 
 }  // namespace tcconv
@@ -632,6 +651,9 @@ struct Args {
     int tiles_per_cta, n_tiles;
     const float* xa; int xa_C, up;                       // activation source: buffer + channel stride; up = 1: half-resolution buffer,
                                                          // nearest-upsampled x2, no BatchNorm (TransitionUp)
+    // 1x1 mode (TransitionDown, models.py:56-67): no taps, N = 48 output channels [out_off, out_off + 48) per launch; the
+    // output gradient is the max-pool-routed gradient of the NEXT level's buffer (gc, xc, abc: stride cC, first channel c_off)
+    int one; const unsigned char* argmax; const float* gc; const float* xc; const float* abc; int cC, c_off, cH, cW;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -742,6 +764,54 @@ dense_wgrad_bf16_kernel(const Args A) {
             // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile
             //      interior.  One thread per interior pixel: all of its loads are issued before any use, then the 16
             //      corrected channels are written into the three kx-shifted planes.
+            if (A.one) {
+                // one thread per pixel of the 8x32 tile; 48 channels in three rounds of 16 (argmax word + g + x loads first)
+                const int r = 1 + (tid >> 5), cc = 1 + (tid & 31);
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                const bool ok = (y < A.H) && (x < A.W);
+                const unsigned pos = (unsigned)(((y & 1) << 1) | (x & 1));
+                const size_t pp = ok ? ((size_t)(b * A.cH + (y >> 1)) * A.cW + (x >> 1)) : 0;
+                const int q = r * PITCH + cc;
+                // halo rows / columns of the six planes must read as zero: clear the few rows the interior never writes
+                for (int i = tid; i < 6 * (A_ROWS + 2); i += 256) {
+                    const int pl = i % 6, row = i / 6, src = row - 1;
+                    const int rr = src / PITCH, c2 = src - rr * PITCH;
+                    if (src < 0 || src >= A_ROWS || rr < 1 || rr > TR || c2 < 1 || c2 > TW)
+                        *reinterpret_cast<uint4*>(g_s + pl * PLANE_BYTES + (size_t)row * 16) = make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll 1
+                for (int sub = 0; sub < 3; ++sub) {
+                    const int cbase = A.out_off + sub * 16;                 // channel inside the conv's output
+                    unsigned am[4];
+                    float4 gq[4], xq[4];
+#pragma unroll
+                    for (int h4 = 0; h4 < 4; ++h4) {
+                        am[h4] = 0xffffffffu; gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4];
+                        if (ok && cbase + h4 * 4 < A.Cout) {
+                            am[h4] = __ldg(reinterpret_cast<const unsigned*>(A.argmax + pp * A.Cout + cbase + h4 * 4));
+                            gq[h4] = __ldg(reinterpret_cast<const float4*>(A.gc + pp * A.cC + A.c_off + cbase + h4 * 4));
+                            xq[h4] = __ldg(reinterpret_cast<const float4*>(A.xc + pp * A.cC + A.c_off + cbase + h4 * 4));
+                        }
+                    }
+                    float v[16];
+#pragma unroll
+                    for (int h4 = 0; h4 < 4; ++h4) {
+                        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                        if (cbase + h4 * 4 < A.Cout) {
+                            const float* abp = A.abc + ((size_t)g * A.cC + A.c_off + cbase + h4 * 4) * 2;
+                            c0 = __ldg(reinterpret_cast<const float4*>(abp)); c1 = __ldg(reinterpret_cast<const float4*>(abp + 4));
+                        }
+                        v[h4 * 4 + 0] = ((am[h4] & 0xffu) == pos) ? gq[h4].x + fmaf(c0.y, xq[h4].x, c0.x) : 0.f;
+                        v[h4 * 4 + 1] = (((am[h4] >> 8) & 0xffu) == pos) ? gq[h4].y + fmaf(c0.w, xq[h4].y, c0.z) : 0.f;
+                        v[h4 * 4 + 2] = (((am[h4] >> 16) & 0xffu) == pos) ? gq[h4].z + fmaf(c1.y, xq[h4].z, c1.x) : 0.f;
+                        v[h4 * 4 + 3] = ((am[h4] >> 24) == pos) ? gq[h4].w + fmaf(c1.w, xq[h4].w, c1.z) : 0.f;
+                    }
+                    const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    *reinterpret_cast<uint4*>(g_s + (sub * 2 + 0) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? lo : make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(g_s + (sub * 2 + 1) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? hi : make_uint4(0u, 0u, 0u, 0u);
+                }
+            } else
             {
                 uint4* gz = reinterpret_cast<uint4*>(g_s);
                 for (int i = tid; i < G_STAGE / 16; i += 256) gz[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -792,7 +862,29 @@ dense_wgrad_bf16_kernel(const Args A) {
         // ---- epilogue: D_ky[ci][kx*16 + co] -> atomicAdd into OIHW
         tc::mbar_wait(bars + 4, 0);
         tc::tc_fence_after();
-        if (warp < 2 && ntiles > 0) {
+        if (warp < 2 && ntiles > 0 && A.one) {
+            const int ci = ci0 + warp * 32 + lane;
+#pragma unroll 1
+            for (int grp16 = 0; grp16 < 3; ++grp16) {
+                float acc16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc16[j] = 0.f;
+#pragma unroll 1
+                for (int set = 0; set < 9; ++set) {
+                    float v[16];
+                    tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + set * NB + grp16 * 16, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc16[j] += v[j];
+                }
+                if (ci < A.Cin) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = A.out_off + grp16 * 16 + j;
+                        if (co < A.Cout) atomicAdd(A.dw + (size_t)co * A.Cin + ci, acc16[j]);
+                    }
+                }
+            }
+        } else if (warp < 2 && ntiles > 0) {
             const int ci = ci0 + warp * 32 + lane;
 #pragma unroll 1
             for (int ky = 0; ky < 3; ++ky) {
@@ -824,6 +916,13 @@ dense_wgrad_bf16_kernel(const Args A) {
             // into the tile its predecessor wrote waits ~266 cycles for it
             const uint64_t d_hi = tc::smem_desc(0, 128, PLANE_BYTES);   // MN-major: LBO = 8-pixel groups (128 B), SBO = 8-channel groups (planes)
             const uint64_t a_d0 = d_hi | (uint64_t)(a_base >> 4), b_d0 = d_hi | (uint64_t)((g_base + 16u) >> 4);
+            if (A.one) {
+                // 1x1: one MMA per 16 pixels, rotating over 9 accumulator tiles
+#pragma unroll 1
+                for (int k16 = 0; k16 < KPX / 16; ++k16)
+                    tc::mma_f16(tmem + (k16 % 9) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16), b_d0 + (uint64_t)(PITCH + k16 * 16), idesc,
+                                (uint32_t)(it != 0 || k16 >= 9));
+            } else {
 #pragma unroll 1
             for (int k16 = 0; k16 < KPX / 16; ++k16) {
                 const int set = k16 % 3;
@@ -832,6 +931,7 @@ dense_wgrad_bf16_kernel(const Args A) {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
                     tc::mma_f16(tmem + (set * 3 + ky) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16 + (ky - 1) * PITCH), bd, idesc, acc);
+            }
             }
             tc::tc_commit(bars + 2 + s);
         }

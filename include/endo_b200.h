@@ -184,6 +184,10 @@ int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long lo
                        float momentum, float max_norm, int first_step, const float* finite_flag,
                        float* grad_norm_out, void* ws, size_t ws_bytes, endo_stream_t stream);
 
+/* Development aid: copies the clock64() trace that CTA 0 of the last tensor-core forward launch recorded when
+ * ENDO_TC_DEBUG has bit 4 set (tools/trace_fwd.py decodes it).  Synchronises the device. */
+int endo_debug_trace_read(long long* host_out, int n);
+
 /* ------------------------------------------------------------------------------------------------
  * tcgen05 bring-up probe (tests only): D[128][N] = A[shift..shift+128][K] * B[N][K]^T computed with
  * tcgen05.mma from operands staged in the shared-memory layouts the convolution kernels use.

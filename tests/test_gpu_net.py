@@ -240,10 +240,11 @@ def test_tensor_core_backward_kernels_match_ffma_backward(monkeypatch):
         torch.cuda.synchronize()
         return {k: p.grad.clone() for k, p in model.named_parameters()}, y.detach().clone()
 
-    # bits: 2 = dense dgrad, 4 = dense wgrad, 16 = TransitionUp wgrad fall back to FFMA (1 / 8 would change the forward)
-    ref, y_ref = grads(22)
+    # bits: 2 = dense dgrad, 4 = dense wgrad, 16 = TransitionUp wgrad, 32 = TransitionDown wgrad fall back to FFMA
+    # (1 / 8 would change the forward)
+    ref, y_ref = grads(54)
     gmax = max(float(v.abs().max()) for v in ref.values())
-    for mask, what in ((20, "dense dgrad"), (18, "dense wgrad"), (6, "TransitionUp wgrad"), (0, "all")):
+    for mask, what in ((52, "dense dgrad"), (50, "dense wgrad"), (38, "TransitionUp wgrad"), (22, "TransitionDown wgrad"), (0, "all")):
         got, y = grads(mask)
         assert rel_err(y, y_ref) < 1e-6
         errs = []
