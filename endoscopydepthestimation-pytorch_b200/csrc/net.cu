@@ -265,11 +265,11 @@ static int trans_down_bwd(const Ctx& c, int l) {
                                            tcwgrad::SMEM_BYTES));
             configured = true;
         }
-        for (int co0 = 0; co0 < cs; co0 += 16) {
-            const int nco = (cs - co0) < 16 ? (cs - co0) : 16;
+        {
             ProfScope prof(PC_WGRAD, c.s);
-            bias_grad_kernel<<<kNumSMs / 2, 256, 0, c.s>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b + co0, P.Ctot[l + 1],
-                                                          P.offIn[l + 1] + co0, nco, (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
+            bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.s>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
+                                                                             P.Ctot[l + 1], P.offIn[l + 1], cs,
+                                                                             (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
             ENDO_CHECK_LAUNCH();
         }
         for (int co0 = 0; co0 < cs; co0 += 48) {
@@ -369,14 +369,14 @@ static int trans_up_bwd(const Ctx& c, int i) {
                                            tcwgrad::SMEM_BYTES));
             configured = true;
         }
+        {
+            ProfScope prof(PC_WGRAD, c.s);
+            bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
+                                                                                       t.conv.cout, (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
+            ENDO_CHECK_LAUNCH();
+        }
         for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
             const int nco = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
-            {
-                ProfScope prof(PC_WGRAD, c.s);
-                bias_grad_kernel<<<kNumSMs, 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b + co0, P.Ctot[l], co0, nco,
-                                                          (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
-                ENDO_CHECK_LAUNCH();
-            }
             tcwgrad::Args q;
             q.x = c.X(l); q.coef = nullptr; q.g = c.GX(l); q.ab = c.AB(l); q.dw = c.gparams + t.conv.w + (size_t)co0 * t.cin * 9;
             q.xa = c.X(ls); q.xa_C = P.Ctot[ls]; q.up = 1; q.one = 0;

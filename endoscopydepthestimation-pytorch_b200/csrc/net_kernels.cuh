@@ -622,6 +622,9 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ ab, float* __restrict__ db,
                  int C, int off, int Cout, long long npix_per_group, int G) {
+    // blockIdx.y selects a group of 16 output channels
+    off += 16 * blockIdx.y; db += 16 * blockIdx.y; Cout -= 16 * blockIdx.y;
+    if (Cout > 16) Cout = 16;
     __shared__ float red[8][16];
     const int grp = threadIdx.x & 3, ch = grp * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);

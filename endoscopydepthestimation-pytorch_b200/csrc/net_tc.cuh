@@ -94,6 +94,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     float* red = edge + EDGE_FLOATS;                                                        // [16][16][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16 * 16 * 2);                         // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    __shared__ float s_bias[16];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_x = (A.W + TW - 1) / TW;
@@ -117,6 +118,9 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 16) {
+        // bias is needed only in the epilogue, but a global load issued there would pay the loaded-DRAM latency
+        // (~4 us while every SM streams operands): fetch it now
+        if (tid < 16) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;     // visible after the named barrier below
         // ======================================================================== producers
         const int grp = tid & 3;                                  // this thread always stages the same 4-channel group
         for (int c = 0; c < nchunks; ++c) {
@@ -218,9 +222,6 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-        float bias[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) bias[j] = (j < A.N) ? __ldg(A.bias + j) : 0.f;
         for (int mb = part; mb < MBLK; mb += 4) {
             const int u = mb * 4 + q;
             uint32_t v0[16], v1[16], v2[16];
@@ -239,7 +240,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 float right = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
                 if (lane == 0) left = (u > 0) ? edge[((u - 1) * 2 + 1) * 16 + j] : 0.f;
                 if (lane == 31) right = (u < NUNITS - 1) ? edge[((u + 1) * 2 + 0) * 16 + j] : 0.f;
-                o[j] = (left + __uint_as_float(v1[j])) + right + bias[j];
+                o[j] = (left + __uint_as_float(v1[j])) + right + s_bias[j];
             }
             if (ok) {
                 float* op = A.out + ((size_t)(b * A.H + y) * A.W + x) * A.out_C + A.out_off;
