@@ -141,6 +141,48 @@ def pick_cpu_threads(h, w):
     return best, avail
 
 
+def warp_layer_bench(dev, peaks, sizes=(("C2", 8, 256, 320), ("C5", 16, 512, 640)), iters=10):
+    """DepthWarpingLayer forward / backward alone (BASELINE.json: 'warp-layer HBM GB/s'): algorithmic bytes
+    (fwd 20*P, bwd 24*P) over the CUDA-event duration of the library call, with a 512 MB write
+    between iterations so the inputs come from HBM, not from the 126 MB L2."""
+    import endo_b200
+    from endo_b200 import _lib
+    out = {}
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    layer = endo_b200.models.DepthWarpingLayer(epsilon=1.0e-8)
+    for name, b, h, w in sizes:
+        batch = endo_b200.synthetic.make_batch(b, h, w, seed=7)
+        d1, d2 = endo_b200.synthetic.jitter_depths(batch, seed=8)
+        args = [batch[k].to(dev) for k in ("boundaries", "translations_1_wrt_2", "rotations_1_wrt_2", "intrinsics")]
+        x1, x2 = d1.to(dev).requires_grad_(True), d2.to(dev).requires_grad_(True)
+        gw = torch.randn(b, 1, h, w, device=dev)
+        for _ in range(2):
+            wd, _ = layer([x1, x2] + args)
+            torch.autograd.grad(wd, [x1, x2], gw)
+        torch.cuda.synchronize()
+        res = {}
+        for phase in ("fwd", "bwd"):
+            total = 0.0
+            for _ in range(iters):
+                flush.zero_()
+                if phase == "fwd":
+                    with _lib.profile() as prof:
+                        wd, _ = layer([x1, x2] + args)
+                else:
+                    wd, _ = layer([x1, x2] + args)
+                    flush.zero_()
+                    with _lib.profile() as prof:
+                        torch.autograd.grad(wd, [x1, x2], gw)
+                total += prof.ms["depth_warp"]
+            ms = total / iters
+            nbytes = (20.0 if phase == "fwd" else 24.0) * b * h * w
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res[phase] = {"ms": round(ms, 4), "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)}
+        out[name] = dict(pixels=b * h * w, **res)
+    del flush
+    return out
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of train.py:272-325 (reference semantics, torch CPU ops) on all host threads."""
     if rank != 0:
@@ -198,6 +240,74 @@ def cpu_baseline_sample(h, w, budget_s=20.0):
                       f"{cores} torch threads (best of several pool sizes; {avail} logical CPUs available)"}
 
 
+def resident_arm(model, h, w, bsz, resident, steps, warmup, world, dev, pg, barrier, max_over_ranks, sampler=None):
+    """Device-resident step (inputs in HBM, fused pair forward, fused optimiser tail): returns timing + launch count."""
+    from endo_b200 import _lib, train_step
+    fused = train_step.TrainStep(model, h, w, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0, sfl_weight=20.0,
+                                 pair=True, process_group=pg)
+    for _ in range(warmup):
+        fused.step(resident)
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _, _ = fused.step(resident)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - launches0
+    if sampler is not None:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    return fused, dict(ms_per_step=ms_total / steps, value=world * bsz * steps / (ms_total / 1e3), launches=int(launches),
+                       loss=float(loss))
+
+
+def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof_steps=3):
+    """Per-kernel-class CUDA-event timing inside the library (endo_prof_*) -> roofline of the dominant class."""
+    from endo_b200 import _lib
+    with _lib.profile() as prof:
+        for _ in range(prof_steps):
+            fused.step(resident)
+    barrier()
+    dense_f, trans_f, final_f = conv_flops_per_image(h, w)
+    imgs = 2 * bsz                                                             # both images of every pair
+    P = bsz * h * w
+    cat_ms = {k: v / prof_steps for k, v in prof.ms.items()}
+    cat_n = {k: v // prof_steps for k, v in prof.counts.items()}
+    # algorithmic work per step for each class (fwd FLOPs of the convs; dgrad and wgrad redo the same MACs)
+    work_flops = {"conv_dense_fwd": dense_f * imgs, "conv_trans_fwd": trans_f * imgs,
+                  "conv_dgrad": (dense_f + trans_f - 2.0 * 3 * 48 * 9 * h * w) * imgs,
+                  "conv_wgrad": (dense_f + trans_f) * imgs}
+    work_bytes = {"depth_warp": 2 * 44.0 * P, "flow_from_depth": 2 * 36.0 * P, "depth_scale": 2 * 48.0 * P}
+    dominant = max(("conv_dense_fwd", "conv_dgrad", "conv_wgrad", "conv_trans_fwd"), key=lambda k: cat_ms.get(k, 0.0))
+    dom_ms = cat_ms[dominant]
+    dom_launches = max(cat_n[dominant], 1)
+    achieved_tf = work_flops[dominant] / (dom_ms * 1e-3) / 1e12
+    peak_tf = peaks["bf16_tflops_sustained"]
+    note = ("fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe); fraction is of the measured bf16 tensor peak; "
+            "fp32 FFMA nominal peak on B200 is ~75 TFLOP/s") if math_mode == "fp32" else \
+           ("tcgen05 kernels (tf32 forward / data gradient, bf16 weight gradient, fp32 accumulate); these layers read "
+            "Cin*4 B/pixel for 216*Cin flop/pixel (54 flop/B, ridge ~220): the operand stream, not the tensor pipe, bounds them")
+    roofline = {"kernel": dominant, "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
+                "launches_per_step": dom_launches, "avg_launch_ms": dom_ms / dom_launches,
+                "flops_per_launch": work_flops[dominant] / dom_launches, "note": note,
+                "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
+    kernels = {k: {"ms_per_step": round(v, 4), "launch_sites": cat_n[k]} for k, v in cat_ms.items()}
+    for k, byts in work_bytes.items():
+        if cat_ms.get(k, 0.0) > 0:
+            gbs = byts / (cat_ms[k] * 1e-3) / 1e9
+            kernels[k].update({"algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
+    for k, fl in work_flops.items():
+        if cat_ms.get(k, 0.0) > 0:
+            kernels[k].update({"TFLOPps": round(fl / (cat_ms[k] * 1e-3) / 1e12, 2)})
+    return roofline, kernels
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,9 +316,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "bf16"],
-                    help="override the arithmetic of the conv path (default: the config's, fp32)")
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32"],
+                    help="arithmetic of the conv path for the headline arm (default: the config's, fp32)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel development runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the tensor-core arm and the warp-layer microbenchmark")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -234,10 +345,12 @@ def main():
         math_mode = args.math
     peaks = measured_peaks()
 
-    torch.manual_seed(10085 + rank)
-    model = endo_b200.models.FCDenseNet57(n_classes=1, math=math_mode)
-    endo_b200.engine.kaiming_init_(model, seed=10085)           # identical weights on every rank
-    model.to(dev).train()
+    def new_model(mode):
+        torch.manual_seed(10085 + rank)
+        m = endo_b200.models.FCDenseNet57(n_classes=1, math=mode)
+        endo_b200.engine.kaiming_init_(m, seed=10085)           # identical weights on every rank
+        return m.to(dev).train()
+
     host = endo_b200.synthetic.make_batch(bsz, h, w, seed=10085 + rank)
     keys = endo_b200.synthetic.BATCH_KEYS_H2D
     host = {k: host[k].pin_memory() for k in keys}
@@ -256,120 +369,83 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ------------------------------------------------------------------ device-resident arm (value)
     pg = dist.group.WORLD if world > 1 else None
-    fused = train_step.TrainStep(model, h, w, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0, sfl_weight=20.0,
-                                 pair=True, process_group=pg)
-    for _ in range(args.warmup):
-        fused.step(resident)
-    barrier()
+
+    # ------------------------------------------------------------------ device-resident arm (value)
     sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss, _, _ = fused.step(resident)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - launches0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    final_loss = float(loss)
-    ms_per_step = ms_total / args.steps
-    value = world * bsz * args.steps / (ms_total / 1e3)
+    model = new_model(math_mode)
+    fused, res = resident_arm(model, h, w, bsz, resident, args.steps, args.warmup, world, dev, pg, barrier, max_over_ranks, sampler)
 
     # ------------------------------------------------------------------ end-to-end arm (e2e)
-    model2 = endo_b200.models.FCDenseNet57(n_classes=1, math=math_mode)
-    endo_b200.engine.kaiming_init_(model2, seed=10085)
-    model2.to(dev).train()
-    stack = train_step.LossStack(h, w, dcl_weight=5.0, sfl_weight=20.0)
-    opt = torch.optim.SGD(model2.parameters(), lr=1e-4, momentum=0.9)          # train.py:202
+    e2e = None
+    if not args.no_e2e:
+        model2 = new_model(math_mode)
+        stack = train_step.LossStack(h, w, dcl_weight=5.0, sfl_weight=20.0)
+        opt = torch.optim.SGD(model2.parameters(), lr=1e-4, momentum=0.9)          # train.py:202
 
-    def e2e_step():
-        cb = {k: host[k].to(dev, non_blocking=True) for k in keys}             # train.py:254-270
-        lv, _, _, _ = stack.loss(model2, cb)                                   # :272-315 (two separate net() calls)
-        val = lv.item()                                                        # :317 device->host read
-        if train_step.is_bad(val):
+        def e2e_step():
+            cb = {k: host[k].to(dev, non_blocking=True) for k in keys}             # train.py:254-270
+            lv, _, _, _ = stack.loss(model2, cb)                                   # :272-315 (two separate net() calls)
+            val = lv.item()                                                        # :317 device->host read
+            if train_step.is_bad(val):
+                opt.zero_grad()
+                return val
             opt.zero_grad()
+            lv.backward()
+            if world > 1:
+                ddp.allreduce_gradients(model2)
+            torch.nn.utils.clip_grad_norm_(model2.parameters(), 10.0)              # :327
+            opt.step()                                                             # :328
             return val
-        opt.zero_grad()
-        lv.backward()
-        if world > 1:
-            ddp.allreduce_gradients(model2)
-        torch.nn.utils.clip_grad_norm_(model2.parameters(), 10.0)              # :327
-        opt.step()                                                             # :328
-        return val
 
-    e2e_steps = 0 if args.no_e2e else args.steps
-    for _ in range(args.warmup if e2e_steps else 0):
-        e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(max(e2e_steps, 1)):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) * (args.steps / max(e2e_steps, 1))
-    e2e_value = world * bsz * args.steps / (e2e_ms / 1e3)
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": world * bsz * args.steps / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+               "path": "reference-facing nn.Modules as train.py:254-328 drives them, pinned host buffers"}
+        del model2, opt, stack
 
     # ------------------------------------------------------------------ per-kernel-class timing (roofline)
-    prof_steps = 3
-    with _lib.profile() as prof:
-        for _ in range(prof_steps):
-            fused.step(resident)
-    barrier()
-    dense_f, trans_f, final_f = conv_flops_per_image(h, w)
-    imgs = 2 * bsz                                                             # both images of every pair
-    P = bsz * h * w
-    cat_ms = {k: v / prof_steps for k, v in prof.ms.items()}
-    cat_n = {k: v // prof_steps for k, v in prof.counts.items()}
-    # algorithmic work per step for each class (fwd FLOPs of the convs; dgrad and wgrad redo the same MACs)
-    work_flops = {"conv_dense_fwd": dense_f * imgs, "conv_trans_fwd": trans_f * imgs,
-                  "conv_dgrad": (dense_f + trans_f - 2.0 * 3 * 48 * 9 * h * w) * imgs,
-                  "conv_wgrad": (dense_f + trans_f) * imgs}
-    work_bytes = {"depth_warp": 2 * 44.0 * P, "flow_from_depth": 2 * 36.0 * P, "depth_scale": 2 * 48.0 * P}
-    dominant = max(("conv_dense_fwd", "conv_dgrad", "conv_wgrad", "conv_trans_fwd"), key=lambda k: cat_ms.get(k, 0.0))
-    dom_ms = cat_ms[dominant]
-    dom_launches = max(cat_n[dominant], 1)
-    achieved_tf = work_flops[dominant] / (dom_ms * 1e-3) / 1e12
-    peak_tf = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": dominant, "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
-                "launches_per_step": dom_launches, "avg_launch_ms": dom_ms / dom_launches,
-                "flops_per_launch": work_flops[dominant] / dom_launches,
-                "note": "fp32 FFMA implicit-GEMM path (no tensor pipe yet); fraction is of the measured bf16 tensor peak; "
-                        "fp32 FFMA nominal peak on B200 is ~75 TFLOP/s",
-                "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
-    warp_ms = cat_ms.get("depth_warp", 0.0)
-    kernels = {k: {"ms_per_step": round(v, 4), "launch_sites": cat_n[k]} for k, v in cat_ms.items()}
-    for k, byts in work_bytes.items():
-        if cat_ms.get(k, 0.0) > 0:
-            gbs = byts / (cat_ms[k] * 1e-3) / 1e9
-            kernels[k].update({"algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
-    for k, fl in work_flops.items():
-        if cat_ms.get(k, 0.0) > 0:
-            kernels[k].update({"TFLOPps": round(fl / (cat_ms[k] * 1e-3) / 1e12, 2)})
+    roofline, kernels = kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode)
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_sample(h, w)
+    # ------------------------------------------------------------------ extra arms (single GPU only)
+    tensor_core, warp_layer, cpu = None, None, None
+    if world == 1 and not args.no_extra:
+        if math_mode == "fp32":
+            del fused, model
+            torch.cuda.empty_cache()
+            model_tc = new_model("tf32")
+            fused_tc, res_tc = resident_arm(model_tc, h, w, bsz, resident, max(args.steps // 2, 3), 3, world, dev, pg, barrier,
+                                            max_over_ranks)
+            roof_tc, kern_tc = kernel_breakdown(fused_tc, resident, h, w, bsz, peaks, barrier, "tf32")
+            tensor_core = {"dtype": "tf32 operands (DenseLayer forward / data gradient), bf16 operands (weight gradients), fp32 accumulate "
+                                    "in TMEM; transition layers partly fp32 FFMA",
+                           "value": res_tc["value"], "unit": "pairs/s", "ms_per_step": res_tc["ms_per_step"],
+                           "gpu_launches": res_tc["launches"], "loss": res_tc["loss"], "roofline": roof_tc, "kernels": kern_tc,
+                           "parity": "depth maps within 2e-2 of the fp64 oracle (measured 1.3e-3), tests/test_gpu_net.py"}
+            del fused_tc, model_tc
+        warp_layer = warp_layer_bench(dev, peaks)
+        if rank == 0 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(h, w)
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": METRIC, "value": res["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": math_mode, "data": "synthetic",
                 "config": {"workload": desc, "batch_per_gpu": bsz, "global_batch": bsz * world, "height": h, "width": w,
                            "model": "FCDenseNet57 (random Kaiming init)", "parallelism": f"dp{world}",
                            "l2": "per-step working set (~3 GB of activations and gradients) >> 126 MB L2: no explicit flush",
-                           "loss": final_loss},
-                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                        "ms_per_step": e2e_ms / args.steps,
-                        "path": "reference-facing nn.Modules as train.py:254-328 drives them, pinned host buffers"},
-                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-                "kernels": kernels, "cpu_baseline": cpu}
+                           "loss": res["loss"]},
+                "e2e": e2e, "gpu_launches": res["launches"], "clocks": sampler.summary(), "roofline": roofline,
+                "kernels": kernels, "tensor_core": tensor_core, "warp_layer": warp_layer, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
