@@ -9,11 +9,11 @@
 namespace endo {
 
 // ------------------------------------------------------------------------------------------------ launchers
-template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP>
+template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP, int KCT = KC, int MINB = 1>
 static int launch_conv(const ConvArgs& a, cudaStream_t s) {
-    constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW>();
+    constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW, KCT>();
     static bool configured = false;
-    auto kern = conv_kernel<KS, PX, CO, NW, LM, EM, WM, UP>;
+    auto kern = conv_kernel<KS, PX, CO, NW, LM, EM, WM, UP, KCT, MINB>;
     if (!configured) {
         ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
@@ -21,6 +21,22 @@ static int launch_conv(const ConvArgs& a, cudaStream_t s) {
     const int tiles = cdiv(a.ow, 32) * cdiv(a.oh, NW * PX);
     dim3 grid(tiles, cdiv(a.N, CO), a.B);
     ProfScope prof(WM == WM_DGRAD ? PC_DGRAD : ((LM == LM_BNRELU && EM == EM_STORE) ? PC_CONV_DENSE_FWD : PC_CONV_TRANS_FWD), s);
+    kern<<<grid, NW * 32, smem, s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+template <int KS, int PX, int CO, int NW, int LM>
+static int launch_conv_splitk(const ConvArgs& a, cudaStream_t s) {
+    constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW>();
+    static bool configured = false;
+    auto kern = conv_kernel<KS, PX, CO, NW, LM, EM_PARTIAL, WM_FWD, false>;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(cdiv(a.ow, 32) * cdiv(a.oh, NW * PX), a.ksplit, a.B);
+    ProfScope prof(PC_CONV_DENSE_FWD, s);
     kern<<<grid, NW * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -49,7 +65,8 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
 }
 
 // ENDO_TC_DISABLE (bit mask, debugging / A-B tests only): 1 = forward, 2 = data gradient, 4 = weight gradient fall back
-// to the FFMA kernels even when the math mode asks for tensor cores.
+// to the FFMA kernels even when the math mode asks for tensor cores (8/16/32/64: transition layers); 128 = no split-K
+// in the FFMA DenseLayer forward.
 static int tc_debug_mask() {
     const char* e = getenv("ENDO_TC_DEBUG");
     return e ? atoi(e) : 0;
@@ -117,7 +134,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         tcconv::FwdArgs t;
         t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
         t.in_C = a.in_C; t.in_off = a.in_off; t.K = a.K; t.out_C = a.out_C; t.out_off = a.out_off; t.N = a.N;
-        t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask();
+        t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask(); t.one = 0;
         t.wpack = c.WPACK();
         {
             ProfScope prof(PC_BN, c.s);
@@ -135,6 +152,36 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(t);
         ENDO_CHECK_LAUNCH();
         return ENDO_OK;
+    }
+    // Low-resolution levels: 32x32 tiles over all input channels would occupy a handful of SMs for hundreds of
+    // microseconds.  Use 8x32 tiles and split the input channels over blockIdx.y; a second tiny kernel adds the slices.
+    const int big_tiles = cdiv(a.ow, 32) * cdiv(a.oh, 32) * a.B;
+    if (big_tiles < 2 * kNumSMs && a.K >= 32 && !(tc_disable_mask() & 128)) {
+        const int tiles = cdiv(a.ow, 32) * cdiv(a.oh, 8) * a.B;
+        int ksplit = cdiv(3 * kNumSMs, tiles);
+        if (ksplit > a.K / 16) ksplit = a.K / 16;
+        if (ksplit < 1) ksplit = 1;
+        const long long pixels = (long long)a.B * a.oh * a.ow;
+        if (4ll * ksplit * pixels * 16 <= P.tdtmp_bytes) {
+            a.partial = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
+            a.ksplit = ksplit;
+            const int per_group = (int)(pixels / a.G);
+            int fblocks = cdiv(per_group, 64);
+            if (fblocks > 4 * kNumSMs) fblocks = 4 * kNumSMs;
+            if (d.conv.cout == 12) {
+                ENDO_TRY((launch_conv_splitk<3, 2, 12, 4, LM_BNRELU>(a, c.s)));
+                ProfScope prof(PC_CONV_DENSE_FWD, c.s);
+                splitk_finish_kernel<12><<<dim3(fblocks, a.G), 256, 0, c.s>>>(a.partial, a.bias, a.out, a.stats, ksplit, pixels, per_group,
+                                                                            a.N, a.out_C, a.out_off, a.stats_C);
+            } else {
+                ENDO_TRY((launch_conv_splitk<3, 2, 16, 4, LM_BNRELU>(a, c.s)));
+                ProfScope prof(PC_CONV_DENSE_FWD, c.s);
+                splitk_finish_kernel<16><<<dim3(fblocks, a.G), 256, 0, c.s>>>(a.partial, a.bias, a.out, a.stats, ksplit, pixels, per_group,
+                                                                            a.N, a.out_C, a.out_off, a.stats_C);
+            }
+            ENDO_CHECK_LAUNCH();
+            return ENDO_OK;
+        }
     }
     if (d.conv.cout == 12) return launch_conv<3, 8, 12, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
     return launch_conv<3, 6, 16, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
@@ -219,7 +266,10 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(t);
         ENDO_CHECK_LAUNCH();
     } else {
-        ENDO_TRY((launch_conv<3, 2, 48, 8, LM_GRAD, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+        // all 12 (16) output-gradient channels in ONE staging step (no padded K), 32 input channels per CTA so that two
+        // CTAs fit an SM (<= 128 registers): their staging / epilogue phases overlap each other's FMA phase
+        if (d.conv.cout == 12) ENDO_TRY((launch_conv<3, 2, 32, 8, LM_GRAD, EM_DGRAD_BN, WM_DGRAD, false, 12, 2>(a, c.s)));
+        else ENDO_TRY((launch_conv<3, 2, 32, 8, LM_GRAD, EM_DGRAD_BN, WM_DGRAD, false, 16, 2>(a, c.s)));
     }
     BnBwdArgs b;
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(d.bn); b.mi = c.MI(l); b.ab = c.AB(l);
@@ -242,6 +292,42 @@ static int trans_down_fwd(const Ctx& c, int l) {
     a.out = c.X(l + 1); a.out_C = P.Ctot[l + 1]; a.out_off = P.offIn[l + 1]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l + 1); a.stats_C = P.Ctot[l + 1];
     a.argmax_out = reinterpret_cast<unsigned char*>(c.acts + t.argmax);
+    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 64) && cs <= 128 * tcconv::POOL_MAXQ) {
+        // tcgen05: 1x1 convolution in passes of 48 output channels into a scratch tensor, then one HBM-bound pooling pass
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcconv::SMEM_BYTES));
+            configured = true;
+        }
+        float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
+        for (int co0 = 0; co0 < cs; co0 += 48) {
+            tcconv::FwdArgs f;
+            f.in = a.in; f.coef = a.coef; f.w = a.w; f.bias = a.bias + co0; f.out = tmp; f.stats = nullptr;
+            f.in_C = a.in_C; f.in_off = a.in_off; f.K = cs; f.out_C = cs; f.out_off = co0; f.N = (cs - co0) < 48 ? (cs - co0) : 48;
+            f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = 0; f.up = 0; f.dbg = 0; f.one = 1; f.wpack = c.WPACK();
+            {
+                ProfScope prof(PC_BN, c.s);
+                tcconv::pack_w_1x1_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
+                ENDO_CHECK_LAUNCH();
+            }
+            dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
+            ProfScope prof(PC_CONV_TRANS_FWD, c.s);
+            tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(f);
+            ENDO_CHECK_LAUNCH();
+        }
+        {
+            const long long pixels = (long long)(P.B / P.G) * (a.oh / 2) * (a.ow / 2);
+            int blocks = (int)((pixels + 7) / 8);
+            if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+            if (blocks < 1) blocks = 1;
+            ProfScope prof(PC_CONV_TRANS_FWD, c.s);
+            tcconv::td_pool_kernel<<<dim3(blocks, P.G), 256, sizeof(float) * 16 * cs, c.s>>>(tmp, a.out, a.argmax_out, a.stats, P.B, a.oh, a.ow, cs,
+                                                                                          a.out_C, a.out_off, P.G, a.stats_C);
+            ENDO_CHECK_LAUNCH();
+        }
+        return ENDO_OK;
+    }
     return launch_conv<1, 2, 48, 8, LM_BNRELU, EM_POOL, WM_FWD, false>(a, c.s);
 }
 
@@ -334,7 +420,7 @@ static int trans_up_fwd(const Ctx& c, int i) {
             f.in = a.in; f.coef = nullptr; f.w = a.w + (size_t)co0 * t.cin * 9; f.bias = a.bias + co0; f.out = a.out; f.stats = a.stats;
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = a.K; f.out_C = a.out_C; f.out_off = a.out_off + co0;
             f.N = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
-            f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.up = 1; f.dbg = 0;
+            f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.up = 1; f.dbg = 0; f.one = 0;
             f.wpack = c.WPACK();
             {
                 ProfScope prof(PC_BN, c.s);

@@ -13,6 +13,9 @@
 //       EM_POOL       + bias, 2x2 max-pool (first-max-wins like ATen), store, argmax byte, statistics
 //       EM_DGRAD_BN   ReLU mask, BN-backward sums, scaled accumulate into the gradient buffer
 //       EM_DGRAD_UP   2x2 sum (backward of nearest upsampling), accumulate
+//       EM_PARTIAL    split-K: blockIdx.y owns a slice of the input channels and stores its raw partial sums to a
+//                     scratch tensor; splitk_finish_kernel adds the slices in a fixed order (low-resolution levels,
+//                     where a CTA per 32x32 tile over ALL input channels would leave most SMs idle)
 //   * the weight view: forward (k = ci, n = co) or data-gradient (k = co, n = ci, taps flipped).
 // Thread mapping: a warp owns PX output rows x 32 consecutive columns (lane = column, so every shared
 // memory access is either conflict-free or a broadcast), a CTA stacks NW warps vertically; each
@@ -23,7 +26,7 @@
 namespace endo {
 
 enum { LM_PLAIN = 0, LM_BNRELU = 1, LM_NCHW = 2, LM_GRAD = 3, LM_GRADPOOL = 4 };
-enum { EM_STORE = 0, EM_POOL = 1, EM_DGRAD_BN = 2, EM_DGRAD_UP = 3 };
+enum { EM_STORE = 0, EM_POOL = 1, EM_DGRAD_BN = 2, EM_DGRAD_UP = 3, EM_PARTIAL = 4 };
 enum { WM_FWD = 0, WM_DGRAD = 1 };
 
 constexpr int KC = 8;   // input channels staged per main-loop step
@@ -52,6 +55,9 @@ struct ConvArgs {
     // ---- EM_DGRAD_BN
     const float* x;           // activation buffer (same geometry as `out`)
     const float* ep_coef;     // [G][N][4] (a, beta, mean, invstd) of the BatchNorm being differentiated
+    // ---- EM_PARTIAL
+    float* partial;           // [ksplit][B][oh][ow][CO]
+    int ksplit;
 };
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -112,20 +118,20 @@ struct ConvTile {
     static constexpr int PLANE = TRP * TWP + ((TRP * TWP) % 32 == 4 ? 0 : ((36 - (TRP * TWP) % 32) % 32));   // plane % 32 == 4
 };
 
-template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP>
-__global__ void __launch_bounds__(NW * 32)
+template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP, int KCT = KC, int MINB = 1>
+__global__ void __launch_bounds__(NW * 32, MINB)
 conv_kernel(const ConvArgs A) {
     using T = ConvTile<KS, PX, NW>;
     constexpr int PAD = T::PAD, TR = T::TR, TRP = T::TRP, TWP = T::TWP, PLANE = T::PLANE, TAPS = KS * KS;
     constexpr int NT = NW * 32;
     extern __shared__ __align__(16) float smem[];
-    float* a_s = smem;                          // [KC][PLANE]
-    float* w_s = smem + KC * PLANE;             // [KC][TAPS][CO]
+    float* a_s = smem;                          // [KCT][PLANE]
+    float* w_s = smem + KCT * PLANE;             // [KCT][TAPS][CO]
 
     const int tiles_x = (A.ow + 31) / 32;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int y0 = ty * TR, x0 = tx * 32;
-    const int n0 = blockIdx.y * CO;
+    const int n0 = (EM == EM_PARTIAL) ? 0 : blockIdx.y * CO;
     const int b = blockIdx.z;
     const int g = b / (A.B / A.G);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -137,11 +143,17 @@ conv_kernel(const ConvArgs A) {
 #pragma unroll
         for (int j = 0; j < CO; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < A.K; k0 += KC) {
+    int k_lo = 0, k_hi = A.K;
+    if constexpr (EM == EM_PARTIAL) {
+        const int kper = ((A.K + A.ksplit - 1) / A.ksplit + KCT - 1) / KCT * KCT;
+        k_lo = blockIdx.y * kper;
+        k_hi = (k_lo + kper < A.K) ? (k_lo + kper) : A.K;
+    }
+    for (int k0 = k_lo; k0 < k_hi; k0 += KCT) {
         __syncthreads();
         // ---- stage operand A: global (NHWC, transformed on the fly) -> shared [k][row][col]
         if constexpr (LM == LM_NCHW) {
-            for (int idx = threadIdx.x; idx < KC * TRP * TWP; idx += NT) {
+            for (int idx = threadIdx.x; idx < KCT * TRP * TWP; idx += NT) {
                 const int kk = idx / (TRP * TWP), pix = idx - kk * (TRP * TWP);
                 const int r = pix / TWP, c = pix - r * TWP;
                 const int y = y0 + r - PAD, x = x0 + c - PAD, ch = k0 + kk;
@@ -153,7 +165,7 @@ conv_kernel(const ConvArgs A) {
         } else {
             // loads first, stores second (batches of 6): every thread keeps several 16-byte loads in flight instead
             // of one load -> transform -> store round trip per iteration
-            constexpr int NA = (TRP * TWP * (KC / 4) + NT - 1) / NT;
+            constexpr int NA = (TRP * TWP * (KCT / 4) + NT - 1) / NT;
 #pragma unroll
             for (int b0 = 0; b0 < NA; b0 += 6) {
                 float4 v[6];
@@ -161,8 +173,8 @@ conv_kernel(const ConvArgs A) {
                 for (int j = 0; j < 6; ++j) {
                     const int idx = threadIdx.x + (b0 + j) * NT;
                     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b0 + j < NA && idx < TRP * TWP * (KC / 4)) {
-                        const int q = idx % (KC / 4), pix = idx / (KC / 4);
+                    if (b0 + j < NA && idx < TRP * TWP * (KCT / 4)) {
+                        const int q = idx % (KCT / 4), pix = idx / (KCT / 4);
                         const int r = pix / TWP, c = pix - r * TWP;
                         v[j] = load_a4<LM, UP>(A, b, g, y0 + r - PAD, x0 + c - PAD, k0 + q * 4);
                     }
@@ -170,8 +182,8 @@ conv_kernel(const ConvArgs A) {
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     const int idx = threadIdx.x + (b0 + j) * NT;
-                    if (b0 + j < NA && idx < TRP * TWP * (KC / 4)) {
-                        const int q = idx % (KC / 4), pix = idx / (KC / 4);
+                    if (b0 + j < NA && idx < TRP * TWP * (KCT / 4)) {
+                        const int q = idx % (KCT / 4), pix = idx / (KCT / 4);
                         float* d = a_s + (q * 4) * PLANE + pix;
                         d[0] = v[j].x; d[PLANE] = v[j].y; d[2 * PLANE] = v[j].z; d[3 * PLANE] = v[j].w;
                     }
@@ -180,14 +192,14 @@ conv_kernel(const ConvArgs A) {
         }
         // ---- stage weights: w_s[kk][tap][n]  (all loads of this chunk issued before the first store)
         {
-            constexpr int NWV = (CO * KC * TAPS + NT - 1) / NT;
+            constexpr int NWV = (CO * KCT * TAPS + NT - 1) / NT;
             float wv[NWV];
 #pragma unroll
             for (int j = 0; j < NWV; ++j) {
                 const int idx = threadIdx.x + j * NT;
                 wv[j] = 0.f;
-                if (idx < CO * KC * TAPS) {
-                    const int tap = idx % TAPS, kk = (idx / TAPS) % KC, n = idx / (TAPS * KC);
+                if (idx < CO * KCT * TAPS) {
+                    const int tap = idx % TAPS, kk = (idx / TAPS) % KCT, n = idx / (TAPS * KCT);
                     const int k = k0 + kk, nn = n0 + n;
                     if (k < A.K && nn < A.N) {
                         if constexpr (WM == WM_FWD) wv[j] = __ldg(A.w + ((size_t)nn * A.w_cin + k) * TAPS + tap);
@@ -198,8 +210,8 @@ conv_kernel(const ConvArgs A) {
 #pragma unroll
             for (int j = 0; j < NWV; ++j) {
                 const int idx = threadIdx.x + j * NT;
-                if (idx < CO * KC * TAPS) {
-                    const int tap = idx % TAPS, kk = (idx / TAPS) % KC, n = idx / (TAPS * KC);
+                if (idx < CO * KCT * TAPS) {
+                    const int tap = idx % TAPS, kk = (idx / TAPS) % KCT, n = idx / (TAPS * KCT);
                     w_s[(kk * TAPS + tap) * CO + n] = wv[j];
                 }
             }
@@ -207,7 +219,7 @@ conv_kernel(const ConvArgs A) {
         __syncthreads();
         // ---- main loop: PX x CO register tile per thread
 #pragma unroll 1
-        for (int kk = 0; kk < KC; ++kk) {
+        for (int kk = 0; kk < KCT; ++kk) {
             const float* ap = a_s + kk * PLANE + r0 * TWP + lane;
             const float* wp = w_s + kk * TAPS * CO;
 #pragma unroll
@@ -240,7 +252,19 @@ conv_kernel(const ConvArgs A) {
 #pragma unroll
     for (int j = 0; j < CO; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
 
-    if constexpr (EM == EM_STORE) {
+    if constexpr (EM == EM_PARTIAL) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i) {
+            const int y = y0 + r0 + i;
+            if (y < A.oh && x < A.ow) {
+                float* pp = A.partial + ((((size_t)blockIdx.y * A.B + b) * A.oh + y) * A.ow + x) * CO;
+#pragma unroll
+                for (int j = 0; j < CO; j += 4)
+                    *reinterpret_cast<float4*>(pp + j) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+            }
+        }
+        return;
+    } else if constexpr (EM == EM_STORE) {
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             const int y = y0 + r0 + i;
@@ -291,33 +315,45 @@ conv_kernel(const ConvArgs A) {
             }
         }
     } else if constexpr (EM == EM_DGRAD_BN) {
+        // channel quad outermost: the BN-backward sums of 4 channels are complete after PX pixels and are reduced across
+        // the warp right away, so only 8 of them are live next to the accumulators (2 CTAs / SM need <= 128 registers)
 #pragma unroll
-        for (int i = 0; i < PX; ++i) {
-            const int y = y0 + r0 + i;
-            const bool ok = (y < A.oh) && (x < A.ow);
-            if (ok) {
-                const size_t o = ((size_t)(b * A.oh + y) * A.ow + x) * A.out_C + A.out_off + n0;
+        for (int j = 0; j < CO; j += 4) {
+            float t1[4] = {0.f, 0.f, 0.f, 0.f}, t2[4] = {0.f, 0.f, 0.f, 0.f};
+            if (n0 + j < A.N) {
+                const float* cf = A.ep_coef + ((size_t)g * A.N + n0 + j) * 4;
+                const float4 c0 = ldg4(cf), c1 = ldg4(cf + 4), c2 = ldg4(cf + 8), c3 = ldg4(cf + 12);
 #pragma unroll
-                for (int j = 0; j < CO; j += 4) {
-                    if (n0 + j < A.N) {
+                for (int i = 0; i < PX; ++i) {
+                    const int y = y0 + r0 + i;
+                    if ((y < A.oh) && (x < A.ow)) {
+                        const size_t o = ((size_t)(b * A.oh + y) * A.ow + x) * A.out_C + A.out_off + n0;
                         const float4 xq = ldg4(A.x + o + j);
-                        const float* cf = A.ep_coef + ((size_t)g * A.N + n0 + j) * 4;
-                        const float4 c0 = ldg4(cf), c1 = ldg4(cf + 4), c2 = ldg4(cf + 8), c3 = ldg4(cf + 12);
                         float4 gq = *reinterpret_cast<const float4*>(A.out + o + j);
                         const float d0 = xq.x - c0.z, d1 = xq.y - c1.z, d2 = xq.z - c2.z, d3 = xq.w - c3.z;
                         const float g0 = fmaf(c0.x, d0, c0.y) > 0.f ? acc[i][j] : 0.f;
                         const float g1 = fmaf(c1.x, d1, c1.y) > 0.f ? acc[i][j + 1] : 0.f;
                         const float g2 = fmaf(c2.x, d2, c2.y) > 0.f ? acc[i][j + 2] : 0.f;
                         const float g3 = fmaf(c3.x, d3, c3.y) > 0.f ? acc[i][j + 3] : 0.f;
-                        s1[j] += g0; s2[j] += g0 * (d0 * c0.w);
-                        s1[j + 1] += g1; s2[j + 1] += g1 * (d1 * c1.w);
-                        s1[j + 2] += g2; s2[j + 2] += g2 * (d2 * c2.w);
-                        s1[j + 3] += g3; s2[j + 3] += g3 * (d3 * c3.w);
+                        t1[0] += g0; t2[0] += g0 * (d0 * c0.w);
+                        t1[1] += g1; t2[1] += g1 * (d1 * c1.w);
+                        t1[2] += g2; t2[2] += g2 * (d2 * c2.w);
+                        t1[3] += g3; t2[3] += g3 * (d3 * c3.w);
                         gq.x = fmaf(c0.x, g0, gq.x); gq.y = fmaf(c1.x, g1, gq.y);
                         gq.z = fmaf(c2.x, g2, gq.z); gq.w = fmaf(c3.x, g3, gq.w);
                         *reinterpret_cast<float4*>(A.out + o + j) = gq;
                     }
                 }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float a = t1[e], c = t2[e];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    c += __shfl_xor_sync(0xffffffffu, c, o);
+                }
+                if (lane == 0) { red[(warp * CO + j + e) * 2] = a; red[(warp * CO + j + e) * 2 + 1] = c; }
             }
         }
     } else if constexpr (EM == EM_DGRAD_UP) {
@@ -349,7 +385,7 @@ conv_kernel(const ConvArgs A) {
     if constexpr (EM != EM_DGRAD_UP) {
         // per-channel sums: warp shuffle tree -> shared -> one fp64 atomic per channel per CTA
 #pragma unroll
-        for (int j = 0; j < CO; ++j) {
+        for (int j = 0; j < (EM == EM_DGRAD_BN ? 0 : CO); ++j) {
             float a = s1[j], c = s2[j];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -372,12 +408,63 @@ conv_kernel(const ConvArgs A) {
     }
 }
 
-template <int KS, int PX, int CO, int NW>
+template <int KS, int PX, int CO, int NW, int KCT = KC>
 constexpr size_t conv_smem_bytes() {
     using T = ConvTile<KS, PX, NW>;
-    size_t main = sizeof(float) * (size_t)(KC * T::PLANE + KC * KS * KS * CO);
+    size_t main = sizeof(float) * (size_t)(KCT * T::PLANE + KCT * KS * KS * CO);
     size_t red = sizeof(float) * (size_t)(NW * CO * 2);
     return main > red ? main : red;
+}
+
+// Split-K finish: out[p][n] = bias[n] + sum_s partial[s][p][n] (fixed order), per-channel statistics of the result.
+// thread = (pixel, channel quad); a block owns a contiguous pixel range of one statistic group.
+template <int CO>
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ partial, const float* __restrict__ bias, float* __restrict__ out,
+                     double* __restrict__ stats, int ksplit, long long pixels, int per_group, int N, int out_C, int out_off,
+                     int stats_C) {
+    constexpr int NQ = CO / 4;
+    __shared__ float red[8][CO][2];
+    const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const int q = threadIdx.x & 3;
+    float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < NQ && q * 4 < N) bq = ldg4(bias + q * 4);
+    for (int i = blockIdx.x * 64 + (threadIdx.x >> 2); i < per_group; i += gridDim.x * 64) {
+        if (q < NQ && q * 4 < N) {
+            const long long p = (long long)g * per_group + i;
+            float4 v = bq;
+            for (int sidx = 0; sidx < ksplit; ++sidx) {
+                const float4 t = ldg4(partial + ((size_t)sidx * pixels + p) * CO + q * 4);
+                v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            }
+            *reinterpret_cast<float4*>(out + (size_t)p * out_C + out_off + q * 4) = v;
+            s1[0] += v.x; s2[0] += v.x * v.x; s1[1] += v.y; s2[1] += v.y * v.y;
+            s1[2] += v.z; s2[2] += v.z * v.z; s1[3] += v.w; s2[3] += v.w * v.w;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+        }
+    }
+    if (lane < 4 && lane < NQ) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { red[warp][lane * 4 + e][0] = s1[e]; red[warp][lane * 4 + e][1] = s2[e]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < CO * 2; t += 256) {
+        const int j = t >> 1, which = t & 1;
+        if (j < N) {
+            double sum = 0.0;
+#pragma unroll
+            for (int wq = 0; wq < 8; ++wq) sum += (double)red[wq][j][which];
+            atomicAdd(stats + ((size_t)g * stats_C + out_off + j) * 2 + which, sum);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

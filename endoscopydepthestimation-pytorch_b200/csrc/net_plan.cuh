@@ -44,6 +44,8 @@ struct NetPlan {
     long long mi_off[kMaxLevels];               // float  [G][Ctot][2]  (mean, invstd)
     long long pre_off;                          // float  [B*H*W] finalConv output before abs
     long long wpack_off;                        // 256 KB: tensor-core weight image of the layer being run (forward)
+    long long tdtmp_off, tdtmp_bytes;           // forward scratch: float [B,h,w,Cs] TransitionDown conv output before pooling (tensor-core
+                                                // path, largest level); split-K partial sums of low-resolution DenseLayers
     long long acts_bytes;
     // byte offsets inside the backward scratch block
     long long gx_off[kMaxLevels];               // float [B,h,w,Ctot] gradient buffers
@@ -173,6 +175,14 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
     }
     P.pre_off = off; off = align_up(off + 4ll * B * H * W, 256);
     P.wpack_off = off; off += 256 * 1024;
+    {
+        long long mx = 0;
+        for (int l = 0; l < nd; ++l) {
+            const long long v = 4ll * B * P.h[l] * P.w[l] * (P.C0[l] + P.Dn[l]);
+            if (v > mx) mx = v;
+        }
+        P.tdtmp_off = off; P.tdtmp_bytes = mx; off = align_up(off + mx, 256);
+    }
     P.acts_bytes = off;
     // ---- backward scratch block
     off = 0;

@@ -76,6 +76,86 @@ pack_w_dgrad_kernel(const float* __restrict__ w, int Cin, int Cout, float* __res
     }
 }
 
+// 1x1 convolution (TransitionDown): only blocks k8 = 0, 1 of the stage image are used, n = output channel co0 + n
+__global__ void __launch_bounds__(256)
+pack_w_1x1_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 2304; d += 256) {
+        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int cin = c * 16 + blk * 8 + kc * 4 + e, co = co0 + n;
+        float v = 0.f;
+        if (blk < 2 && co < Ntot && cin < K) v = __ldg(w + (size_t)co * K + cin);
+        out[(size_t)c * 2304 + d] = v;
+    }
+}
+
+// 2x2 max-pool of the TransitionDown conv output (tensor-core path): pooled value -> next level buffer, argmax byte,
+// per-channel statistics.  HBM-bound elementwise pass (reads 16 B/px/channel-quad, writes 4).  A warp walks coarse
+// pixels, lane = channel quad (q = lane, lane + 32, ...), so a pixel is read as one contiguous run and the statistics
+// of a channel are accumulated by ONE lane in a fixed order (bit-reproducible forward, like the FFMA epilogue).
+constexpr int POOL_MAXQ = 6;                               // channel quads per lane: Cs <= 768
+__global__ void __launch_bounds__(256)
+td_pool_kernel(const float* __restrict__ tmp, float* __restrict__ out, unsigned char* __restrict__ argmax, double* __restrict__ stats,
+               int B, int h, int w, int Cs, int out_C, int out_off, int G, int stats_C) {
+    extern __shared__ float sm[];                          // [8 warps][Cs][2]
+    const int nq = Cs >> 2, oh = h >> 1, ow = w >> 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long per_group = (long long)(B / G) * oh * ow;
+    const int g = blockIdx.y;
+    float s1[POOL_MAXQ][4], s2[POOL_MAXQ][4];
+#pragma unroll
+    for (int qi = 0; qi < POOL_MAXQ; ++qi)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s1[qi][e] = 0.f; s2[qi][e] = 0.f; }
+    for (long long i = (long long)blockIdx.x * 8 + warp; i < per_group; i += (long long)gridDim.x * 8) {
+        const long long pp = (long long)g * per_group + i;               // coarse pixel (b, y2, x2) flattened
+        const int x2 = (int)(pp % ow), y2 = (int)((pp / ow) % oh), b = (int)(pp / ((long long)ow * oh));
+        const float* p00 = tmp + (((size_t)b * h + 2 * y2) * w + 2 * x2) * Cs;
+#pragma unroll
+        for (int qi = 0; qi < POOL_MAXQ; ++qi) {
+            const int q = lane + 32 * qi;
+            if (q < nq) {
+                const float* pq = p00 + q * 4;
+                const float4 v00 = __ldg(reinterpret_cast<const float4*>(pq)), v01 = __ldg(reinterpret_cast<const float4*>(pq + Cs));
+                const float4 v10 = __ldg(reinterpret_cast<const float4*>(pq + (size_t)w * Cs));
+                const float4 v11 = __ldg(reinterpret_cast<const float4*>(pq + (size_t)w * Cs + Cs));
+                const float a0[4] = {v00.x, v00.y, v00.z, v00.w}, a1[4] = {v01.x, v01.y, v01.z, v01.w};
+                const float a2[4] = {v10.x, v10.y, v10.z, v10.w}, a3[4] = {v11.x, v11.y, v11.z, v11.w};
+                float m[4]; unsigned am4 = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float mm = a0[e]; unsigned am = 0;                  // ATen max_pool2d: (val > max) || isnan(val)
+                    if (a1[e] > mm || a1[e] != a1[e]) { mm = a1[e]; am = 1; }
+                    if (a2[e] > mm || a2[e] != a2[e]) { mm = a2[e]; am = 2; }
+                    if (a3[e] > mm || a3[e] != a3[e]) { mm = a3[e]; am = 3; }
+                    m[e] = mm; am4 |= am << (8 * e);
+                    s1[qi][e] += mm; s2[qi][e] += mm * mm;
+                }
+                *reinterpret_cast<float4*>(out + (size_t)pp * out_C + out_off + q * 4) = make_float4(m[0], m[1], m[2], m[3]);
+                *reinterpret_cast<unsigned*>(argmax + (size_t)pp * Cs + q * 4) = am4;
+            }
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < POOL_MAXQ; ++qi) {
+        const int q = lane + 32 * qi;
+        if (q < nq) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sm[((size_t)warp * Cs + q * 4 + e) * 2] = s1[qi][e];
+                sm[((size_t)warp * Cs + q * 4 + e) * 2 + 1] = s2[qi][e];
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cs * 2; i += 256) {
+        double sum = 0.0;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) sum += (double)sm[(size_t)wq * Cs * 2 + i];
+        atomicAdd(stats + ((size_t)g * stats_C + out_off + (i >> 1)) * 2 + (i & 1), sum);
+    }
+}
+
 struct FwdArgs {
     const float* in; const float* coef; const float* w; const float* bias; float* out; double* stats;
     int in_C, in_off, K, out_C, out_off, N, H, W, B, G, stats_C;
@@ -83,6 +163,7 @@ struct FwdArgs {
                  //    buffer, nearest-upsampled x2, no BatchNorm (TransitionUp, models.py:73-74)
     int dbg;     // performance experiments only (ENDO_TC_DEBUG): 1 = skip the MMAs, 2 = skip the activation loads
     const float* wpack;   // weight image built by pack_w_fwd_kernel (2304 floats per 16-channel chunk)
+    int one;              // 1: 1x1 convolution, N <= 48 plain output channels, epilogue = + bias, store (no taps, no statistics)
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -94,7 +175,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     float* red = edge + EDGE_FLOATS;                                                        // [16][16][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16 * 16 * 2);                         // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
-    __shared__ float s_bias[16];
+    __shared__ float s_bias[48];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_x = (A.W + TW - 1) / TW;
@@ -120,7 +201,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     if (warp < 16) {
         // bias is needed only in the epilogue, but a global load issued there would pay the loaded-DRAM latency
         // (~4 us while every SM streams operands): fetch it now
-        if (tid < 16) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;     // visible after the named barrier below
+        if (tid < 48) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;     // visible after the named barrier below
         // ======================================================================== producers
         const int grp = tid & 3;                                  // this thread always stages the same 4-channel group
         for (int c = 0; c < nchunks; ++c) {
@@ -202,6 +283,30 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
         if (tid == 0) ENDO_TRACE(3);
         const int q = warp & 3, part = warp >> 2;             // TMEM lane quadrant, and which M-blocks this warp drains
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        if (A.one) {
+            asm volatile("bar.sync 1, 512;" ::: "memory");       // s_bias visible
+            for (int mb = part; mb < MBLK; mb += 4) {
+                const int L = PITCH + mb * 128 + q * 32 + lane;
+                const int r = L / PITCH, cc = L - r * PITCH;
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                const bool ok = (r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W);
+                float* op = A.out + ((size_t)(b * A.H + y) * A.W + x) * A.out_C + A.out_off;
+#pragma unroll 1
+                for (int c16 = 0; c16 < 3; ++c16) {
+                    float v[16];
+                    tc::tmem_ld16(tmem + lane_base + mb * NB + c16 * 16, v);
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            if (c16 * 16 + j < A.N)
+                                *reinterpret_cast<float4*>(op + c16 * 16 + j) =
+                                    make_float4(v[j] + s_bias[c16 * 16 + j], v[j + 1] + s_bias[c16 * 16 + j + 1],
+                                                v[j + 2] + s_bias[c16 * 16 + j + 2], v[j + 3] + s_bias[c16 * 16 + j + 3]);
+                        }
+                    }
+                }
+            }
+        } else {
         // pass 1: publish the values the neighbouring 32-lane units need
         for (int mb = part; mb < MBLK; mb += 4) {
             const int u = mb * 4 + q;
@@ -273,6 +378,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             for (int wq = 0; wq < 16; ++wq) sum += (double)red[(wq * 16 + j) * 2 + which];
             atomicAdd(A.stats + ((size_t)g * A.stats_C + A.out_off + j) * 2 + which, sum);
         }
+        }   // !A.one
     } else if (lane == 0) {
         // ======================================================================== MMA issuer (one thread)
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NB);
@@ -289,6 +395,15 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             // (measured, tests/test_gpu_tc_probe.py::test_mma_cost_by_operand_layout), whatever its size.  Consecutive
             // MMAs therefore target different M-blocks: 9 independent accumulator chains keep the pipe busy.
             const uint64_t a_hi = tc::smem_desc(0, PLANE_BYTES, 128), b_hi = tc::smem_desc(0, NB * 16, 128);
+            if (A.one) {
+                for (int k8 = 0; k8 < nk8; ++k8) {
+                    const uint64_t bd = b_hi | (uint64_t)((b_base + (uint32_t)k8 * B_BLOCK_BYTES) >> 4);
+                    const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)PITCH * 16u) >> 4);
+#pragma unroll
+                    for (int mb = 0; mb < MBLK; ++mb)
+                        tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, (uint32_t)((c | k8) != 0));
+                }
+            } else
 #pragma unroll 1
             for (int ky = 0; ky < 3; ++ky) {
                 for (int k8 = 0; k8 < nk8; ++k8) {

@@ -134,8 +134,9 @@ def test_pair_forward_equals_two_calls():
 
 def test_growth16_variant_fcdensenet67():
     cfg = onet.FCDENSENET67
-    state, x, model = _setup(cfg, lambda: endo_b200.models.FCDenseNet67(n_classes=1), 1, 32, 64, 21)
-    gy = torch.randn(1, 1, 32, 64, generator=torch.Generator().manual_seed(4))
+    state, x, model = _setup(cfg, lambda: endo_b200.models.FCDenseNet67(n_classes=1), 2, 64, 64, 21)
+    # (batch 1 at 32x64 leaves 2 samples per channel in the bottleneck BatchNorms: gradients there are pure cancellation)
+    gy = torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(4))
     y64, g64, _ = _oracle_fwd_bwd(state, x, cfg, gy, torch.float64)
     y32, g32, _ = _oracle_fwd_bwd(state, x, cfg, gy, torch.float32)
     y = model(x.cuda())
@@ -255,3 +256,59 @@ def test_tensor_core_backward_kernels_match_ffma_backward(monkeypatch):
         print(f"tensor-core {what}: median {np.median(errs):.2e}  p90 {np.percentile(errs, 90):.2e}  max {errs.max():.2e}")
         assert np.median(errs) < 5e-3, (what, np.median(errs))
         assert errs.max() < 1e-1, (what, errs.max(), list(ref)[int(errs.argmax())])
+
+
+def test_tensor_core_transition_down_forward_matches_ffma(monkeypatch):
+    """math="tf32" with the TransitionDown 1x1 convolution on tcgen05 (+ pooling pass) against the same forward
+    with that one layer type on the fp32 FFMA kernel (ENDO_TC_DISABLE=64): tf32 operand rounding only.  The
+    gradients of the two runs differentiate forwards that differ by ~1e-3, which this network amplifies ~100x
+    (ReLU / arg-max flips feeding BatchNorms with few samples per channel, see _check_grads): they are compared
+    loosely, as a guard against routing errors (a wrong arg-max byte or statistic gives O(1) differences)."""
+    state, x, _ = _setup(onet.FCDENSENET57, lambda: endo_b200.models.FCDenseNet57(n_classes=1), 2, 128, 160, 78)
+    gy = torch.randn(2, 1, 128, 160, generator=torch.Generator().manual_seed(4)).cuda()
+
+    def run(mask):
+        monkeypatch.setenv("ENDO_TC_DISABLE", str(mask))
+        model = endo_b200.models.FCDenseNet57(n_classes=1, math="tf32")
+        model.load_state_dict(state)
+        model.cuda().train()
+        y = model(x.cuda())
+        (y * gy).sum().backward()
+        torch.cuda.synchronize()
+        return y.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()}
+
+    y_ref, g_ref = run(64)
+    y, g = run(0)
+    assert rel_err(y, y_ref) < 5e-3, rel_err(y, y_ref)
+    gmax = max(float(v.abs().max()) for v in g_ref.values())
+    errs = np.array([float((g[k] - v).abs().max()) / max(float(v.abs().max()), 1e-4 * gmax) for k, v in g_ref.items()])
+    print(f"TransitionDown tcgen05 forward: y {rel_err(y, y_ref):.2e}  grads median {np.median(errs):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 0.25, np.median(errs)
+
+
+def test_splitk_forward_matches_single_pass(monkeypatch):
+    """fp32 FFMA DenseLayer forward at low resolution: input channels split over CTAs + fixed-order finish kernel
+    against the single-pass kernel (ENDO_TC_DISABLE=128).  Same products, different fp32 summation order."""
+    state, x, _ = _setup(onet.FCDENSENET57, lambda: endo_b200.models.FCDenseNet57(n_classes=1), 2, 64, 64, 404)
+    gy = torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(6)).cuda()
+
+    def run(mask):
+        monkeypatch.setenv("ENDO_TC_DISABLE", str(mask))
+        model = endo_b200.models.FCDenseNet57(n_classes=1)
+        model.load_state_dict(state)
+        model.cuda().train()
+        y = model(x.cuda())
+        (y * gy).sum().backward()
+        torch.cuda.synchronize()
+        bufs = {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
+        return y.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters()}, bufs
+
+    y_ref, g_ref, b_ref = run(128)
+    y, g, b = run(0)
+    assert rel_err(y, y_ref) < 1e-5, rel_err(y, y_ref)
+    for k in b_ref:
+        assert rel_err(b[k], b_ref[k]) < 1e-5, k
+    gmax = max(float(v.abs().max()) for v in g_ref.values())
+    errs = np.array([float((g[k] - v).abs().max()) / max(float(v.abs().max()), 1e-4 * gmax) for k, v in g_ref.items()])
+    print(f"split-K forward: y {rel_err(y, y_ref):.2e}  grads median {np.median(errs):.2e} p90 {np.percentile(errs, 90):.2e} max {errs.max():.2e}")
+    assert np.median(errs) < 1e-3, np.median(errs)

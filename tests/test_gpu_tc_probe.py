@@ -84,3 +84,39 @@ def test_mma_cost_independent_accumulators():
             n_mma = reps * (k // (8 if fmt == TF32 else 16))
             print(f"{name} N={n:3d} rotate={rot}: {_run.cycles / n_mma:7.1f} cycles per MMA, err {err:.1e}")
             assert err < 5e-3
+
+
+def _probe(a, b, n, k):
+    d = torch.full((128, n), float("nan"), device="cuda")
+    cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().endo_tc_probe(a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[0], n, k, 0, TF32, 0, 0,
+                                        0, 1, cyc.data_ptr(), 1, _lib.stream_ptr(a.device)), "tc_probe")
+    torch.cuda.synchronize()
+    return d
+
+
+def _trunc_tf32(x):
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def test_tf32_operand_conversion_and_split_accuracy():
+    """Facts the 3xTF32 (fp32-accurate) convolution mode relies on: (1) how kind::tf32 converts fp32 operands
+    (truncation of the low 13 mantissa bits vs rounding), (2) that hi/lo operand splitting
+    a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo recovers fp32-level accuracy from tf32 MMAs with fp32 accumulation."""
+    n, k = 48, 128
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(128, k, generator=g).cuda()
+    b = torch.randn(n, k, generator=g).cuda()
+    d = _probe(a, b, n, k).double()
+    ref_trunc = _trunc_tf32(a).double() @ _trunc_tf32(b).double().t()
+    ref_full = a.double() @ b.double().t()
+    e_trunc = float((d - ref_trunc).abs().max() / ref_full.abs().max())
+    e_full = float((d - ref_full).abs().max() / ref_full.abs().max())
+    print(f"tf32 MMA vs truncated-operand product: {e_trunc:.2e}; vs exact product: {e_full:.2e}")
+    a_hi, b_hi = _trunc_tf32(a), _trunc_tf32(b)
+    a_lo, b_lo = a - a_hi, b - b_hi
+    d3 = _probe(a_hi, b_hi, n, k) + (_probe(a_lo, b_hi, n, k) + _probe(a_hi, b_lo, n, k))
+    e3 = float((d3.double() - ref_full).abs().max() / ref_full.abs().max())
+    e32 = float(((a @ b.t()).double() - ref_full).abs().max() / ref_full.abs().max())
+    print(f"3xTF32 split: {e3:.2e}   (fp32 FFMA matmul: {e32:.2e})")
+    assert e3 < 2e-6, e3

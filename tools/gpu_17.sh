@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25
+timeout 600 python bench.py --no-cpu-baseline --steps 10 --warmup 3 > gpurun_out/bench_17.json 2> gpurun_out/bench_17.err; echo "bench exit $?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_17.json')); print(d['value'], d['ms_per_step'], d['e2e']['value']); print('tc', d['tensor_core']['value'], d['tensor_core']['loss'], d['config']['loss']); print(d['warp_layer'])"
