@@ -26,6 +26,25 @@ static int launch_conv(const ConvArgs& a, cudaStream_t s) {
     return ENDO_OK;
 }
 
+// DenseLayer forward, software-pipelined variant (4-channel chunks, register prefetch, coefficient table in shared memory)
+template <int PX, int CO>
+static int launch_conv_pf(const ConvArgs& a, cudaStream_t s) {
+    constexpr size_t base = conv_smem_bytes<3, PX, CO, 4, 4>();
+    constexpr int kMaxK = 1536;
+    static bool configured = false;
+    auto kern = conv_kernel<3, PX, CO, 4, LM_BNRELU, EM_STORE, WM_FWD, false, 4, 3, true>;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + 16 * kMaxK)));
+        configured = true;
+    }
+    if (a.K > kMaxK) return ENDO_ERR_BAD_SHAPE;
+    dim3 grid(cdiv(a.ow, 32) * cdiv(a.oh, 4 * PX), cdiv(a.N, CO), a.B);
+    ProfScope prof(PC_CONV_DENSE_FWD, s);
+    kern<<<grid, 128, base + 16 * (size_t)a.K, s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
 template <int KS, int PX, int CO, int NW, int LM>
 static int launch_conv_splitk(const ConvArgs& a, cudaStream_t s) {
     constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW>();
@@ -54,6 +73,29 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
     const int ychunks = cdiv(a.a_K, 32), zchunks = cdiv(a.g_K, CW * NCG);
     a.n_tiles = a.B * cdiv(a.oh, 8) * cdiv(a.ow, 32);
     int want = (3 * kNumSMs) / (ychunks * zchunks);
+    if (want < 1) want = 1;
+    if (want > a.n_tiles) want = a.n_tiles;
+    a.tiles_per_cta = cdiv(a.n_tiles, want);
+    dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
+    ProfScope prof(PC_WGRAD, s);
+    kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
+template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
+static int launch_wgrad2(WgradArgs a, cudaStream_t s) {
+    if (a.G > 2) return launch_wgrad<KS, CW, NCG, NPS, LMA, LMG, UP>(a, s);     // coefficient cache holds two statistic groups
+    constexpr size_t smem = wgrad2_smem_bytes<KS, CW, NCG>();
+    static bool configured = false;
+    auto kern = wgrad2_kernel<KS, CW, NCG, NPS, LMA, LMG, UP>;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int ychunks = cdiv(a.a_K, 32), zchunks = cdiv(a.g_K, CW * NCG);
+    a.n_tiles = a.B * cdiv(a.oh, 8) * cdiv(a.ow, 32);
+    int want = (2 * kNumSMs) / (ychunks * zchunks);
     if (want < 1) want = 1;
     if (want > a.n_tiles) want = a.n_tiles;
     a.tiles_per_cta = cdiv(a.n_tiles, want);
@@ -183,6 +225,10 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
             return ENDO_OK;
         }
     }
+    if (a.K <= 1536 && !(tc_disable_mask() & 256)) {
+        if (d.conv.cout == 12) return launch_conv_pf<8, 12>(a, c.s);
+        return launch_conv_pf<6, 16>(a, c.s);
+    }
     if (d.conv.cout == 12) return launch_conv<3, 8, 12, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
     return launch_conv<3, 6, 16, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
 }
@@ -231,9 +277,9 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(t);
         ENDO_CHECK_LAUNCH();
     } else if (d.conv.cout == 12) {
-        ENDO_TRY((launch_wgrad<3, 12, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+        ENDO_TRY((launch_wgrad2<3, 12, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.s)));
     } else {
-        ENDO_TRY((launch_wgrad<3, 16, 1, 2, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+        ENDO_TRY((launch_wgrad2<3, 16, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.s)));
     }
     // data gradient through conv, ReLU and BatchNorm (first term; the mean terms are applied lazily)
     ConvArgs a = base_args(c);
@@ -378,7 +424,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
             ENDO_CHECK_LAUNCH();
         }
     } else {
-        ENDO_TRY((launch_wgrad<1, 48, 1, 4, LM_BNRELU, LM_GRADPOOL, false>(w, c.s)));
+        ENDO_TRY((launch_wgrad2<1, 48, 1, 8, LM_BNRELU, LM_GRADPOOL, false>(w, c.s)));
     }
     ConvArgs a = base_args(c);
     a.in = c.GX(l + 1); a.in2 = c.X(l + 1); a.in_ab = c.AB(l + 1); a.argmax = am; a.in_C = P.Ctot[l + 1];

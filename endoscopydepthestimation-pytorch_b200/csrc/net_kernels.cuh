@@ -118,7 +118,7 @@ struct ConvTile {
     static constexpr int PLANE = TRP * TWP + ((TRP * TWP) % 32 == 4 ? 0 : ((36 - (TRP * TWP) % 32) % 32));   // plane % 32 == 4
 };
 
-template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP, int KCT = KC, int MINB = 1>
+template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP, int KCT = KC, int MINB = 1, bool PF = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 conv_kernel(const ConvArgs A) {
     using T = ConvTile<KS, PX, NW>;
@@ -149,6 +149,102 @@ conv_kernel(const ConvArgs A) {
         k_lo = blockIdx.y * kper;
         k_hi = (k_lo + kper < A.K) ? (k_lo + kper) : A.K;
     }
+    auto compute_chunk = [&]() {
+        // ---- main loop: PX x CO register tile per thread
+#pragma unroll 1
+        for (int kk = 0; kk < KCT; ++kk) {
+            const float* ap = a_s + kk * PLANE + r0 * TWP + lane;
+            const float* wp = w_s + kk * TAPS * CO;
+#pragma unroll
+            for (int kx = 0; kx < KS; ++kx) {
+                float av[PX + KS - 1];
+#pragma unroll
+                for (int i = 0; i < PX + KS - 1; ++i) av[i] = ap[i * TWP + kx];
+#pragma unroll
+                for (int ky = 0; ky < KS; ++ky) {
+                    float wv[CO];
+#pragma unroll
+                    for (int j = 0; j < CO / 4; ++j) {
+                        const float4 q = *reinterpret_cast<const float4*>(wp + (ky * KS + kx) * CO + j * 4);
+                        wv[j * 4] = q.x; wv[j * 4 + 1] = q.y; wv[j * 4 + 2] = q.z; wv[j * 4 + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < PX; ++i)
+#pragma unroll
+                        for (int j = 0; j < CO; ++j) acc[i][j] = fmaf(av[i + ky], wv[j], acc[i][j]);
+                }
+            }
+        }
+    };
+    if constexpr (PF) {
+        // Software pipeline (DenseLayer forward at the large levels): the raw activations and weights of chunk k+1 are
+        // requested into registers before the FMA loop of chunk k and transformed / stored after it, so the memory
+        // latency of a chunk is paid behind a full FMA phase.  BatchNorm coefficients of all K channels sit in shared memory.
+        static_assert(!PF || (LM == LM_BNRELU && !UP && KCT == 4 && WM == WM_FWD), "prefetch variant: DenseLayer forward, 4-channel chunks");
+        constexpr int NAP = (TRP * TWP + NT - 1) / NT, NWP = (CO * KCT * TAPS + NT - 1) / NT;
+        float4* coef_s = reinterpret_cast<float4*>(w_s + KCT * TAPS * CO);           // [K] (a, beta, mean, invstd)
+        for (int i = threadIdx.x; i < A.K; i += NT) coef_s[i] = ldg4(A.coef + ((size_t)g * A.K + i) * 4);
+        float4 pa[NAP];
+        float pw[NWP];
+        unsigned okm = 0u;
+        auto issue = [&](int k0) {
+            okm = 0u;
+#pragma unroll
+            for (int j = 0; j < NAP; ++j) {
+                const int pix = threadIdx.x + j * NT;
+                const int r = pix / TWP, c = pix - r * TWP;
+                const int y = y0 + r - PAD, x = x0 + c - PAD;
+                pa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pix < TRP * TWP && y >= 0 && y < A.oh && x >= 0 && x < A.ow && k0 < A.K) {
+                    pa[j] = ldg4(A.in + ((size_t)(b * A.ih + y) * A.iw + x) * A.in_C + A.in_off + k0);
+                    okm |= 1u << j;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NWP; ++j) {
+                const int idx = threadIdx.x + j * NT;
+                pw[j] = 0.f;
+                if (idx < CO * KCT * TAPS) {
+                    const int tap = idx % TAPS, kk = (idx / TAPS) % KCT, n = idx / (TAPS * KCT);
+                    const int k = k0 + kk, nn = n0 + n;
+                    if (k < A.K && nn < A.N) pw[j] = __ldg(A.w + ((size_t)nn * A.w_cin + k) * TAPS + tap);
+                }
+            }
+        };
+        auto commit = [&](int k0) {
+            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
+            if (k0 + 3 < A.K) { c0 = coef_s[k0]; c1 = coef_s[k0 + 1]; c2 = coef_s[k0 + 2]; c3 = coef_s[k0 + 3]; }
+#pragma unroll
+            for (int j = 0; j < NAP; ++j) {
+                const int pix = threadIdx.x + j * NT;
+                if (pix < TRP * TWP) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (okm & (1u << j)) {
+                        v.x = fmaxf(fmaf(c0.x, pa[j].x - c0.z, c0.y), 0.f); v.y = fmaxf(fmaf(c1.x, pa[j].y - c1.z, c1.y), 0.f);
+                        v.z = fmaxf(fmaf(c2.x, pa[j].z - c2.z, c2.y), 0.f); v.w = fmaxf(fmaf(c3.x, pa[j].w - c3.z, c3.y), 0.f);
+                    }
+                    float* d = a_s + pix;
+                    d[0] = v.x; d[PLANE] = v.y; d[2 * PLANE] = v.z; d[3 * PLANE] = v.w;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NWP; ++j) {
+                const int idx = threadIdx.x + j * NT;
+                if (idx < CO * KCT * TAPS) {
+                    const int tap = idx % TAPS, kk = (idx / TAPS) % KCT, n = idx / (TAPS * KCT);
+                    w_s[(kk * TAPS + tap) * CO + n] = pw[j];
+                }
+            }
+        };
+        if (k_lo < k_hi) issue(k_lo);
+        for (int k0 = k_lo; k0 < k_hi; k0 += KCT) {
+            __syncthreads();                 // FMA loop of the previous chunk is done with a_s / w_s (first pass: coef_s is written)
+            commit(k0);
+            __syncthreads();
+            if (k0 + KCT < k_hi) issue(k0 + KCT);
+            compute_chunk();
+        }
+    } else
     for (int k0 = k_lo; k0 < k_hi; k0 += KCT) {
         __syncthreads();
         // ---- stage operand A: global (NHWC, transformed on the fly) -> shared [k][row][col]
@@ -217,31 +313,7 @@ conv_kernel(const ConvArgs A) {
             }
         }
         __syncthreads();
-        // ---- main loop: PX x CO register tile per thread
-#pragma unroll 1
-        for (int kk = 0; kk < KCT; ++kk) {
-            const float* ap = a_s + kk * PLANE + r0 * TWP + lane;
-            const float* wp = w_s + kk * TAPS * CO;
-#pragma unroll
-            for (int kx = 0; kx < KS; ++kx) {
-                float av[PX + KS - 1];
-#pragma unroll
-                for (int i = 0; i < PX + KS - 1; ++i) av[i] = ap[i * TWP + kx];
-#pragma unroll
-                for (int ky = 0; ky < KS; ++ky) {
-                    float wv[CO];
-#pragma unroll
-                    for (int j = 0; j < CO / 4; ++j) {
-                        const float4 q = *reinterpret_cast<const float4*>(wp + (ky * KS + kx) * CO + j * 4);
-                        wv[j * 4] = q.x; wv[j * 4 + 1] = q.y; wv[j * 4 + 2] = q.z; wv[j * 4 + 3] = q.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < PX; ++i)
-#pragma unroll
-                        for (int j = 0; j < CO; ++j) acc[i][j] = fmaf(av[i + ky], wv[j], acc[i][j]);
-                }
-            }
-        }
+        compute_chunk();
     }
 
     // =================================================================================== epilogue
@@ -616,6 +688,199 @@ wgrad_kernel(const WgradArgs A) {
         }
     }
     if (do_bias && A.db && co0 + cg * CW + lane < A.g_K) atomicAdd(A.db + co0 + cg * CW + lane, bsum);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight gradient, software-pipelined version (same thread mapping and arithmetic as wgrad_kernel): the global
+// loads of tile t+1 are issued into registers before the FMA loop of tile t and transformed / stored to shared
+// memory after it, so a CTA pays the memory latency once instead of once per tile.  The BatchNorm coefficients
+// and lazy-correction pairs of the CTA's channel chunk live in shared memory (loaded once).
+// ---------------------------------------------------------------------------------------------------
+template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
+__global__ void __launch_bounds__(KS * NCG * NPS * 32)
+wgrad2_kernel(const WgradArgs A) {
+    static_assert(LMA == LM_BNRELU || LMA == LM_PLAIN, "activation loader");
+    static_assert(LMG == LM_GRAD || LMG == LM_GRADPOOL, "gradient loader");
+    constexpr int PAD = KS / 2, TR = 8, TRP = TR + 2 * PAD, TWP = 32 + 2 * PAD, COT = CW * NCG;
+    constexpr int NT = KS * NCG * NPS * 32;
+    constexpr int NA_ITEMS = TRP * TWP * 8, NG_ITEMS = TR * 32 * (COT / 4);
+    constexpr int NA = (NA_ITEMS + NT - 1) / NT, NG = (NG_ITEMS + NT - 1) / NT;
+    static_assert(NT % 8 == 0, "a thread must own one activation channel quad");
+    extern __shared__ __align__(16) float smem[];
+    float* a_s = smem;                                  // [TRP][TWP][32]   (ci fastest)
+    float* g_s = smem + TRP * TWP * 32;                 // [TR][32][COT]
+    float* coef_s = g_s + TR * 32 * COT;                // [2][32][4]  (a, beta, mean, invstd)
+    float* ab_s = coef_s + 2 * 32 * 4;                  // [2][COT][2]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ky = warp % KS, cg = (warp / KS) % NCG, ps = warp / (KS * NCG);
+    const int c0 = blockIdx.y * 32, co0 = blockIdx.z * COT;
+    const int tiles_x = (A.ow + 31) / 32, tiles_y = (A.oh + TR - 1) / TR;
+    const int per_img = tiles_x * tiles_y;
+
+    for (int i = threadIdx.x; i < 2 * 32 * 4; i += NT) {
+        const int gg = i / 128, ch = (i >> 2) & 31;
+        float v = 0.f;
+        if (LMA == LM_BNRELU && gg < A.G && c0 + ch < A.a_K) v = __ldg(A.a_coef + ((size_t)gg * A.a_K + c0 + ch) * 4 + (i & 3));
+        coef_s[i] = v;
+    }
+    for (int i = threadIdx.x; i < 2 * COT * 2; i += NT) {
+        const int gg = i / (COT * 2), ch = (i >> 1) % COT;
+        float v = 0.f;
+        if (gg < A.G && co0 + ch < A.g_K) v = __ldg(A.g_ab + ((size_t)gg * A.g_C + A.g_off + co0 + ch) * 2 + (i & 1));
+        ab_s[i] = v;
+    }
+
+    const int qa = threadIdx.x & 7;                                         // this thread's activation channel quad
+    float4 pa[NA], pg[NG], px[NG];
+    unsigned pam[NG];
+    unsigned ok_a = 0u, ok_g = 0u;
+
+    auto issue = [&](int t) {
+        const int b = t / per_img, rem = t - b * per_img;
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const int y0 = ty * TR, x0 = tx * 32;
+        ok_a = 0u; ok_g = 0u;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const int idx = threadIdx.x + j * NT, pix = idx >> 3;
+            const int r = pix / TWP, c = pix - r * TWP;
+            const int y = y0 + r - PAD, x = x0 + c - PAD, ch = c0 + qa * 4;
+            pa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < NA_ITEMS && y >= 0 && y < A.oh && x >= 0 && x < A.ow && ch < A.a_K) {
+                const int sy = UP ? (y >> 1) : y, sx = UP ? (x >> 1) : x;
+                pa[j] = ldg4(A.a_in + ((size_t)(b * A.a_h + sy) * A.a_w + sx) * A.a_C + A.a_off + ch);
+                ok_a |= 1u << j;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            const int idx = threadIdx.x + j * NT, pix = idx / (COT / 4), qg = idx - pix * (COT / 4);
+            const int y = y0 + (pix >> 5), x = x0 + (pix & 31), ch = co0 + qg * 4;
+            pg[j] = make_float4(0.f, 0.f, 0.f, 0.f); px[j] = pg[j]; pam[j] = 0xffffffffu;
+            if (idx < NG_ITEMS && y < A.oh && x < A.ow && ch < A.g_K) {
+                size_t pp;
+                if constexpr (LMG == LM_GRADPOOL) {
+                    pp = (size_t)(b * A.g_h + (y >> 1)) * A.g_w + (x >> 1);
+                    pam[j] = __ldg(reinterpret_cast<const unsigned*>(A.g_argmax + pp * A.g_K + ch));
+                } else {
+                    pp = (size_t)(b * A.g_h + y) * A.g_w + x;
+                }
+                const size_t o = pp * A.g_C + A.g_off + ch;
+                pg[j] = ldg4(A.g_in + o); px[j] = ldg4(A.g_x + o);
+                ok_g |= 1u << j;
+            }
+        }
+    };
+    auto commit = [&](int t) {
+        const int b = t / per_img, rem = t - b * per_img;
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const int y0 = ty * TR, x0 = tx * 32;
+        const int g = b / (A.B / A.G);
+        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;
+        if constexpr (LMA == LM_BNRELU) {
+            const float4* cf = reinterpret_cast<const float4*>(coef_s + (g * 32 + qa * 4) * 4);
+            k0 = cf[0]; k1 = cf[1]; k2 = cf[2]; k3 = cf[3];
+        }
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const int idx = threadIdx.x + j * NT;
+            if (idx < NA_ITEMS) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok_a & (1u << j)) {
+                    if constexpr (LMA == LM_BNRELU) {
+                        v.x = fmaxf(fmaf(k0.x, pa[j].x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, pa[j].y - k1.z, k1.y), 0.f);
+                        v.z = fmaxf(fmaf(k2.x, pa[j].z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, pa[j].w - k3.z, k3.y), 0.f);
+                    } else {
+                        v = pa[j];
+                    }
+                }
+                *reinterpret_cast<float4*>(a_s + (idx >> 3) * 32 + qa * 4) = v;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            const int idx = threadIdx.x + j * NT;
+            if (idx < NG_ITEMS) {
+                const int pix = idx / (COT / 4), qg = idx - pix * (COT / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok_g & (1u << j)) {
+                    const float4* abp = reinterpret_cast<const float4*>(ab_s + (g * COT + qg * 4) * 2);
+                    const float4 c0q = abp[0], c1q = abp[1];
+                    v.x = pg[j].x + fmaf(c0q.y, px[j].x, c0q.x); v.y = pg[j].y + fmaf(c0q.w, px[j].y, c0q.z);
+                    v.z = pg[j].z + fmaf(c1q.y, px[j].z, c1q.x); v.w = pg[j].w + fmaf(c1q.w, px[j].w, c1q.z);
+                    if constexpr (LMG == LM_GRADPOOL) {
+                        const unsigned pos = (unsigned)((((y0 + (pix >> 5)) & 1) << 1) | ((x0 + (pix & 31)) & 1));
+                        const unsigned am = pam[j];
+                        if ((am & 0xffu) != pos) v.x = 0.f;
+                        if (((am >> 8) & 0xffu) != pos) v.y = 0.f;
+                        if (((am >> 16) & 0xffu) != pos) v.z = 0.f;
+                        if ((am >> 24) != pos) v.w = 0.f;
+                    }
+                }
+                *reinterpret_cast<float4*>(g_s + pix * COT + qg * 4) = v;
+            }
+        }
+    };
+
+    float acc[KS][CW];
+#pragma unroll
+    for (int i = 0; i < KS; ++i)
+#pragma unroll
+        for (int j = 0; j < CW; ++j) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    const bool do_bias = (blockIdx.y == 0) && (ky == 0) && (lane < CW);
+
+    const int t_begin = blockIdx.x * A.tiles_per_cta;
+    const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
+    if (t_begin < t_end) issue(t_begin);
+    for (int t = t_begin; t < t_end; ++t) {
+        __syncthreads();                     // previous tile's FMA loop is done with the shared tiles (and coef_s / ab_s are written)
+        commit(t);
+        __syncthreads();
+        if (t + 1 < t_end) issue(t + 1);
+        for (int r = ps; r < TR; r += NPS) {
+            const float* ar = a_s + ((r + ky) * TWP) * 32 + lane;
+            const float* gr = g_s + (r * 32) * COT + cg * CW;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+            if constexpr (KS == 3) { a1 = ar[0]; a2 = ar[32]; }
+#pragma unroll 4
+            for (int xx = 0; xx < 32; ++xx) {
+                if constexpr (KS == 3) { a0 = a1; a1 = a2; a2 = ar[(xx + 2) * 32]; }
+                else a0 = ar[xx * 32];
+                float gv[CW];
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                    const float4 q = *reinterpret_cast<const float4*>(gr + xx * COT + j * 4);
+                    gv[j * 4] = q.x; gv[j * 4 + 1] = q.y; gv[j * 4 + 2] = q.z; gv[j * 4 + 3] = q.w;
+                }
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    acc[0][j] = fmaf(a0, gv[j], acc[0][j]);
+                    if constexpr (KS == 3) { acc[1][j] = fmaf(a1, gv[j], acc[1][j]); acc[2][j] = fmaf(a2, gv[j], acc[2][j]); }
+                }
+                if (do_bias) bsum += gr[xx * COT + lane];
+            }
+        }
+    }
+    const int ci = c0 + lane;
+    if (ci < A.a_K) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const int co = co0 + cg * CW + j;
+            if (co < A.g_K) {
+#pragma unroll
+                for (int kx = 0; kx < KS; ++kx)
+                    atomicAdd(A.dw + ((size_t)co * A.w_cin + ci) * (KS * KS) + ky * KS + kx, acc[kx][j]);
+            }
+        }
+    }
+    if (do_bias && A.db && co0 + cg * CW + lane < A.g_K) atomicAdd(A.db + co0 + cg * CW + lane, bsum);
+}
+
+template <int KS, int CW, int NCG>
+constexpr size_t wgrad2_smem_bytes() {
+    constexpr int PAD = KS / 2;
+    return sizeof(float) * (size_t)((8 + 2 * PAD) * (32 + 2 * PAD) * 32 + 8 * 32 * CW * NCG + 2 * 32 * 4 + 2 * CW * NCG * 2);
 }
 
 template <int KS, int CW, int NCG>

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_22.log 2>&1; tail -3 gpurun_out/pytest_22.log
+grep -n "^FAILED\|^E  " gpurun_out/pytest_22.log | head -20
+timeout 600 python bench.py --no-cpu-baseline --no-extra --no-e2e --steps 10 --warmup 3 > gpurun_out/bench_22.json 2> gpurun_out/bench_22.err; echo "bench exit $?"
+python -c "
+import json; d=json.load(open('gpurun_out/bench_22.json')); print(d['value'], d['ms_per_step']); print({k:v['ms_per_step'] for k,v in d['kernels'].items()}); print(d['config']['loss'])"
