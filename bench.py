@@ -8,7 +8,10 @@ A "step" is one optimisation step of /root/reference/train.py:272-328 on one syn
 FCDenseNet57 forward on both images of every pair, DepthScalingLayer x2, FlowfromDepthLayer x2 +
 SparseMaskedL1Loss x2, DepthWarpingLayer x2 + NormalizedDistanceLoss x2 (dcl_weight 5, sfl_weight 20),
 backward, clip_grad_norm_(10) and SGD(momentum 0.9); with N > 1 one gradient all-reduce per step.
-Metric: image-pairs/sec (whole job).  Default workload = BASELINE.json configs[1]: bs8/GPU, 256x320, fp32.
+Metric: image-pairs/sec (whole job).  Default workload = BASELINE.json configs[1]: bs8/GPU, 256x320, fp32 results:
+the headline arm runs every convolution on tcgen05 in math="tf32x3" (error-compensated 3xTF32 forward: depth maps and
+losses within 1e-4 of the fp32 reference, tests/test_gpu_net.py); `other_math_modes` adds the fp32 FFMA strict-parity
+path and the plain tf32 path for comparison.
 
 Prints ONE JSON line (rank 0):
   value     device-resident throughput: inputs already in HBM, fused pair forward + fused optimiser tail,
@@ -16,7 +19,8 @@ Prints ONE JSON line (rank 0):
   e2e       the same step through the reference-facing modules exactly as train.py drives them
             (net(colors_1); net(colors_2); torch.optim.SGD; clip_grad_norm_; loss.item()), host buffers in
             pinned memory, 16 H2D copies + 1 D2H read per step inside the timed region
-  roofline  dominant kernel class (per-category CUDA-event timing inside this process, endo_prof_*)
+  roofline  dominant kernel class (per-category CUDA-event timing inside this process, endo_prof_*): HBM bound, algorithmic
+            layer-by-layer operand bytes of the class / its time; the tensor-pipe throughput of the same launches beside it
   cpu_baseline  the oracle port (CPU restatement of the reference path) on the host cores, bounded sample
 `--impl reference` times that CPU path alone (the reference is pure PyTorch-on-CPU for this tier).
 """
@@ -35,10 +39,14 @@ if ROOT not in sys.path:
 
 CONFIGS = {
     # name: (batch per GPU, H, W, math, description)
-    "c2": (8, 256, 320, "fp32", "1xB200 bs8 256x320 synthetic pairs, FCDenseNet57, full loss stack (dcl 5, sfl 20), fp32"),
-    "c5": (16, 512, 640, "fp32", "bs16/GPU 512x640 (downsampling 2.0), warp-gather stress"),
+    "c2": (8, 256, 320, "tf32x3", "1xB200 bs8 256x320 synthetic pairs, FCDenseNet57, full loss stack (dcl 5, sfl 20), fp32"),
+    "c5": (16, 512, 640, "tf32x3", "bs16/GPU 512x640 (downsampling 2.0), warp-gather stress"),
 }
 METRIC = "image-pairs/sec fwd+bwd @256x320 bs8"
+DTYPE = {"fp32": "fp32 (FFMA convolutions, no tensor cores: strict-parity path)",
+         "tf32": "tf32 operands on tcgen05 (forward, data gradient), bf16 operands (weight gradient), fp32 accumulate",
+         "tf32x3": "fp32 (forward: error-compensated 3xTF32 on tcgen05, fp32-grade depth maps and losses; gradients: tf32 / bf16 "
+                   "operands on tcgen05; fp32 accumulate in TMEM; geometric layers, losses, BatchNorm statistics, optimiser fp32)"}
 
 
 def measured_peaks():
@@ -113,6 +121,47 @@ def conv_flops_per_image(h, w):
             dense += 2.0 * (48 + cs + j * g) * g * 9 * (h // res) * (w // res)
     final = 2.0 * 192 * h * w
     return dense, trans, final
+
+
+def conv_bytes_per_image(h, w):
+    """Layer-by-layer ALGORITHMIC HBM bytes (fp32) of the convolution classes: every layer reads each of its input maps once
+    and writes its output once.  forward: (Cin + Cout) * 4 B/px; data gradient: output gradient in
+    (Cout), activations in for the ReLU mask (Cin), input gradient accumulated in place (2 * Cin); weight gradient:
+    activations (Cin) + output gradient (Cout).  Pooled / upsampled sides are counted at their own resolution."""
+    g, first = 12, 48
+    by = {k: 0.0 for k in ("conv_dense_fwd", "conv_dense_dgrad", "conv_dense_wgrad", "conv_trans_fwd", "conv_trans_dgrad",
+                           "conv_trans_wgrad")}
+
+    def dense(cin, px):
+        by["conv_dense_fwd"] += 4.0 * (cin + g) * px
+        by["conv_dense_dgrad"] += 4.0 * (3 * cin + g) * px
+        by["conv_dense_wgrad"] += 4.0 * (cin + g) * px
+
+    by["conv_trans_fwd"] += 4.0 * (3 + first) * h * w                       # firstconv (no data gradient: images need none)
+    by["conv_trans_wgrad"] += 4.0 * (3 + first) * h * w
+    cur, res, skips = first, 1, []
+    for _ in range(5):
+        px = (h // res) * (w // res)
+        for j in range(4):
+            dense(cur + j * g, px)
+        cur += 4 * g
+        skips.append((cur, res))
+        by["conv_trans_fwd"] += 4.0 * (cur * px + cur * px / 4)              # TransitionDown: read at px, write pooled
+        by["conv_trans_dgrad"] += 4.0 * (3 * cur * px + cur * px / 4)
+        by["conv_trans_wgrad"] += 4.0 * (cur * px + cur * px / 4)
+        res *= 2
+    px = (h // res) * (w // res)
+    for j in range(4):
+        dense(cur + j * g, px)
+    for _ in range(5):
+        cs, res = skips.pop()
+        px = (h // res) * (w // res)
+        by["conv_trans_fwd"] += 4.0 * (48 * px / 4 + 48 * px)                # TransitionUp: read low res, write high res
+        by["conv_trans_dgrad"] += 4.0 * (48 * px + 2 * 48 * px / 4)
+        by["conv_trans_wgrad"] += 4.0 * (48 * px / 4 + 48 * px)
+        for j in range(4):
+            dense(48 + cs + j * g, px)
+    return by
 
 
 def pick_cpu_threads(h, w):
@@ -267,35 +316,44 @@ def resident_arm(model, h, w, bsz, resident, steps, warmup, world, dev, pg, barr
 
 
 def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof_steps=3):
-    """Per-kernel-class CUDA-event timing inside the library (endo_prof_*) -> roofline of the dominant class."""
+    """Per-kernel-class CUDA-event timing inside the library (endo_prof_*, events on the launching stream) -> roofline of the
+    dominant class.  The convolution classes are bounded by their operand stream (a DenseLayer moves
+    Cin*4 B/pixel for 216*Cin flop/pixel = 54 flop/B against a ridge of ~210), so the bound is HBM; the tensor-pipe
+    throughput of the same launches is reported next to it."""
     from endo_b200 import _lib
     with _lib.profile() as prof:
         for _ in range(prof_steps):
             fused.step(resident)
     barrier()
     dense_f, trans_f, final_f = conv_flops_per_image(h, w)
+    conv_b = conv_bytes_per_image(h, w)
     imgs = 2 * bsz                                                             # both images of every pair
     P = bsz * h * w
     cat_ms = {k: v / prof_steps for k, v in prof.ms.items()}
     cat_n = {k: v // prof_steps for k, v in prof.counts.items()}
-    # algorithmic work per step for each class (fwd FLOPs of the convs; dgrad and wgrad redo the same MACs)
+    first_f = 2.0 * 3 * 48 * 9 * h * w
     work_flops = {"conv_dense_fwd": dense_f * imgs, "conv_trans_fwd": trans_f * imgs,
-                  "conv_dgrad": (dense_f + trans_f - 2.0 * 3 * 48 * 9 * h * w) * imgs,
-                  "conv_wgrad": (dense_f + trans_f) * imgs}
-    work_bytes = {"depth_warp": 2 * 44.0 * P, "flow_from_depth": 2 * 36.0 * P, "depth_scale": 2 * 48.0 * P}
-    dominant = max(("conv_dense_fwd", "conv_dgrad", "conv_wgrad", "conv_trans_fwd"), key=lambda k: cat_ms.get(k, 0.0))
+                  "conv_dense_dgrad": dense_f * imgs, "conv_trans_dgrad": (trans_f - first_f) * imgs,
+                  "conv_dense_wgrad": dense_f * imgs, "conv_trans_wgrad": trans_f * imgs}
+    work_bytes = {k: v * imgs for k, v in conv_b.items()}
+    work_bytes.update({"depth_warp": 2 * 44.0 * P, "flow_from_depth": 2 * 36.0 * P, "depth_scale": 2 * 48.0 * P})
+    dominant = max(work_flops, key=lambda k: cat_ms.get(k, 0.0))
     dom_ms = cat_ms[dominant]
     dom_launches = max(cat_n[dominant], 1)
+    achieved_gbs = work_bytes[dominant] / (dom_ms * 1e-3) / 1e9
     achieved_tf = work_flops[dominant] / (dom_ms * 1e-3) / 1e12
-    peak_tf = peaks["bf16_tflops_sustained"]
-    note = ("fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe); fraction is of the measured bf16 tensor peak; "
-            "fp32 FFMA nominal peak on B200 is ~75 TFLOP/s") if math_mode == "fp32" else \
-           ("tcgen05 kernels (tf32 forward / data gradient, bf16 weight gradient, fp32 accumulate); these layers read "
-            "Cin*4 B/pixel for 216*Cin flop/pixel (54 flop/B, ridge ~220): the operand stream, not the tensor pipe, bounds them")
-    roofline = {"kernel": dominant, "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peaks["source"] + " (bf16 sustained)",
+    kind = {"fp32": "fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe)",
+            "tf32": "tcgen05 kernels, tf32 / bf16 operands, fp32 accumulate in TMEM",
+            "tf32x3": "tcgen05 kernels: 3xTF32 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM"}[math_mode]
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
                 "launches_per_step": dom_launches, "avg_launch_ms": dom_ms / dom_launches,
-                "flops_per_launch": work_flops[dominant] / dom_launches, "note": note,
+                "algorithmic_bytes_per_launch": work_bytes[dominant] / dom_launches,
+                "tensor": {"achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                           "frac": achieved_tf / peaks["bf16_tflops_sustained"],
+                           "note": "algorithmic conv FLOPs of the class over the same time, against the measured dense bf16 peak"},
+                "note": kind + "; algorithmic bytes = layer-by-layer operand stream (conv_bytes_per_image), time = sum of the "
+                        "class's launches in one step (CUDA events on the launching stream)",
                 "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
     kernels = {k: {"ms_per_step": round(v, 4), "launch_sites": cat_n[k]} for k, v in cat_ms.items()}
     for k, byts in work_bytes.items():
@@ -316,10 +374,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default=None, choices=["fp32", "tf32"],
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3"],
                     help="arithmetic of the conv path for the headline arm (default: the config's, fp32)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel development runs)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the tensor-core arm and the warp-layer microbenchmark")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other math modes and the warp-layer microbenchmark")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -417,21 +475,25 @@ def main():
     roofline, kernels = kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode)
 
     # ------------------------------------------------------------------ extra arms (single GPU only)
-    tensor_core, warp_layer, cpu = None, None, None
+    other_arms, warp_layer, cpu = {}, None, None
     if world == 1 and not args.no_extra:
-        if math_mode == "fp32":
-            del fused, model
+        del fused, model
+        torch.cuda.empty_cache()
+        notes = {"fp32": "strict-parity path: every convolution in fp32 FFMA (no tensor cores); gradients at CPU-fp32 level",
+                 "tf32": "every DenseLayer / transition convolution with plain tf32 operands (what cuDNN runs the reference's "
+                         "convolutions in by default): depth maps within 2e-2 of the fp64 oracle (measured 1.3e-3)",
+                 "tf32x3": "3xTF32 forward (fp32-grade), tf32 / bf16-operand gradients"}
+        for mode in ("fp32", "tf32", "tf32x3"):
+            if mode == math_mode:
+                continue
+            m2 = new_model(mode)
+            f2, r2 = resident_arm(m2, h, w, bsz, resident, max(args.steps // 2, 3), 3, world, dev, pg, barrier, max_over_ranks)
+            roof2, kern2 = kernel_breakdown(f2, resident, h, w, bsz, peaks, barrier, mode)
+            other_arms[mode] = {"dtype": DTYPE[mode], "value": r2["value"], "unit": "pairs/s", "ms_per_step": r2["ms_per_step"],
+                                "gpu_launches": r2["launches"], "loss": r2["loss"], "roofline": roof2, "kernels": kern2,
+                                "note": notes[mode]}
+            del f2, m2
             torch.cuda.empty_cache()
-            model_tc = new_model("tf32")
-            fused_tc, res_tc = resident_arm(model_tc, h, w, bsz, resident, max(args.steps // 2, 3), 3, world, dev, pg, barrier,
-                                            max_over_ranks)
-            roof_tc, kern_tc = kernel_breakdown(fused_tc, resident, h, w, bsz, peaks, barrier, "tf32")
-            tensor_core = {"dtype": "tf32 operands (DenseLayer forward / data gradient), bf16 operands (weight gradients), fp32 accumulate "
-                                    "in TMEM; transition layers partly fp32 FFMA",
-                           "value": res_tc["value"], "unit": "pairs/s", "ms_per_step": res_tc["ms_per_step"],
-                           "gpu_launches": res_tc["launches"], "loss": res_tc["loss"], "roofline": roof_tc, "kernels": kern_tc,
-                           "parity": "depth maps within 2e-2 of the fp64 oracle (measured 1.3e-3), tests/test_gpu_net.py"}
-            del fused_tc, model_tc
         warp_layer = warp_layer_bench(dev, peaks)
         if rank == 0 and not args.no_cpu_baseline:
             cpu = cpu_baseline_sample(h, w)
@@ -439,13 +501,13 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": res["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": math_mode, "data": "synthetic",
+                "vs_baseline": None, "dtype": DTYPE[math_mode], "data": "synthetic",
                 "config": {"workload": desc, "batch_per_gpu": bsz, "global_batch": bsz * world, "height": h, "width": w,
-                           "model": "FCDenseNet57 (random Kaiming init)", "parallelism": f"dp{world}",
+                           "model": "FCDenseNet57 (random Kaiming init)", "parallelism": f"dp{world}", "math": math_mode,
                            "l2": "per-step working set (~3 GB of activations and gradients) >> 126 MB L2: no explicit flush",
                            "loss": res["loss"]},
                 "e2e": e2e, "gpu_launches": res["launches"], "clocks": sampler.summary(), "roofline": roofline,
-                "kernels": kernels, "tensor_core": tensor_core, "warp_layer": warp_layer, "cpu_baseline": cpu}
+                "kernels": kernels, "other_math_modes": other_arms, "warp_layer": warp_layer, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

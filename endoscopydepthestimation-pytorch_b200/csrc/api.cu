@@ -31,8 +31,9 @@ void prof_end(cudaStream_t s) {
 extern "C" void endo_prof_enable(int on) { endo::g_prof_on = on; }
 extern "C" int endo_prof_categories(void) { return endo::PC_COUNT; }
 extern "C" const char* endo_prof_category_name(int c) {
-    static const char* names[] = {"conv_dense_fwd", "conv_trans_fwd", "conv_dgrad", "conv_wgrad", "bn_bookkeeping",
-                                  "final_conv", "depth_warp", "flow_from_depth", "depth_scale", "losses", "optimizer"};
+    static const char* names[] = {"conv_dense_fwd", "conv_trans_fwd", "conv_dense_dgrad", "conv_dense_wgrad", "bn_bookkeeping",
+                                  "final_conv", "depth_warp", "flow_from_depth", "depth_scale", "losses", "optimizer",
+                                  "conv_trans_dgrad", "conv_trans_wgrad"};
     return (c >= 0 && c < endo::PC_COUNT) ? names[c] : "?";
 }
 // Synchronises the device, adds every recorded launch's duration to ms[cat] / counts[cat] and clears the records.

@@ -11,7 +11,7 @@ extern unsigned long long g_launch_count;   // defined in api.cu
 // Optional per-category device timing (endo_prof_* in api.cu): when enabled, every launch site brackets
 // its kernel with two CUDA events on the launching stream.  Off by default (two predictable branches).
 enum ProfCat { PC_CONV_DENSE_FWD = 0, PC_CONV_TRANS_FWD, PC_DGRAD, PC_WGRAD, PC_BN, PC_FINAL, PC_WARP, PC_FLOW,
-               PC_SCALE, PC_LOSS, PC_OPT, PC_COUNT };
+               PC_SCALE, PC_LOSS, PC_OPT, PC_DGRAD_TRANS, PC_WGRAD_TRANS, PC_COUNT };   // PC_DGRAD / PC_WGRAD: DenseLayers only
 extern int g_prof_on;
 void prof_begin(int cat, cudaStream_t s);
 void prof_end(cudaStream_t s);

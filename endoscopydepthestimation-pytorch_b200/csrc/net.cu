@@ -20,7 +20,8 @@ static int launch_conv(const ConvArgs& a, cudaStream_t s) {
     }
     const int tiles = cdiv(a.ow, 32) * cdiv(a.oh, NW * PX);
     dim3 grid(tiles, cdiv(a.N, CO), a.B);
-    ProfScope prof(WM == WM_DGRAD ? PC_DGRAD : ((LM == LM_BNRELU && EM == EM_STORE) ? PC_CONV_DENSE_FWD : PC_CONV_TRANS_FWD), s);
+    ProfScope prof(WM == WM_DGRAD ? ((LM == LM_GRADPOOL || EM == EM_DGRAD_UP) ? PC_DGRAD_TRANS : PC_DGRAD)
+                                  : ((LM == LM_BNRELU && EM == EM_STORE) ? PC_CONV_DENSE_FWD : PC_CONV_TRANS_FWD), s);
     kern<<<grid, NW * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -77,7 +78,7 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
     if (want > a.n_tiles) want = a.n_tiles;
     a.tiles_per_cta = cdiv(a.n_tiles, want);
     dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
-    ProfScope prof(PC_WGRAD, s);
+    ProfScope prof((KS == 3 && LMA == LM_BNRELU) ? PC_WGRAD : PC_WGRAD_TRANS, s);
     kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -100,7 +101,7 @@ static int launch_wgrad2(WgradArgs a, cudaStream_t s) {
     if (want > a.n_tiles) want = a.n_tiles;
     a.tiles_per_cta = cdiv(a.n_tiles, want);
     dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
-    ProfScope prof(PC_WGRAD, s);
+    ProfScope prof((KS == 3 && LMA == LM_BNRELU) ? PC_WGRAD : PC_WGRAD_TRANS, s);
     kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
@@ -117,6 +118,8 @@ static int tc_disable_mask() {
     const char* e = getenv("ENDO_TC_DISABLE");
     return e ? atoi(e) : 0;
 }
+
+static inline bool is_tc(int math) { return math == ENDO_MATH_TF32 || math == ENDO_MATH_TF32X3; }
 
 struct Ctx {
     const NetPlan& P;
@@ -171,16 +174,17 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
     a.w = c.params + d.conv.w; a.bias = c.params + d.conv.b; a.w_cin = d.cin;
     a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = d.out_off; a.N = d.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l); a.stats_C = P.Ctot[l];
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 1)) {
+    if (is_tc(c.math) && !(tc_disable_mask() & 1)) {
         // tcgen05 path: tf32 operands (what cuDNN runs the reference's convs in by default), fp32 accumulate in TMEM
         tcconv::FwdArgs t;
         t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
         t.in_C = a.in_C; t.in_off = a.in_off; t.K = a.K; t.out_C = a.out_C; t.out_off = a.out_off; t.N = a.N;
         t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask(); t.one = 0;
-        t.wpack = c.WPACK();
+        t.wpack = c.WPACK(); t.x3 = c.math == ENDO_MATH_TF32X3;
         {
             ProfScope prof(PC_BN, c.s);
-            tcconv::pack_w_fwd_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
+            if (t.x3) tcconv::pack_w_fwd_x3_kernel<<<cdiv(t.K, 8), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
+            else tcconv::pack_w_fwd_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
             ENDO_CHECK_LAUNCH();
         }
         static bool configured = false;
@@ -242,8 +246,8 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = d.out_off; w.g_K = d.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + d.conv.w; w.db = c.gparams + d.conv.b; w.w_cin = d.cin;
-    const bool tc_w = c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 4);
-    const bool tc_d = c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 2);
+    const bool tc_w = is_tc(c.math) && !(tc_disable_mask() & 4);
+    const bool tc_d = is_tc(c.math) && !(tc_disable_mask() & 2);
     // the conv bias gradient is produced by exactly one kernel: the tcgen05 dgrad if it runs, else the FFMA wgrad if it
     // runs, else a tiny dedicated reduction
     if (tc_d) w.db = nullptr;
@@ -338,7 +342,7 @@ static int trans_down_fwd(const Ctx& c, int l) {
     a.out = c.X(l + 1); a.out_C = P.Ctot[l + 1]; a.out_off = P.offIn[l + 1]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l + 1); a.stats_C = P.Ctot[l + 1];
     a.argmax_out = reinterpret_cast<unsigned char*>(c.acts + t.argmax);
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 64) && cs <= 128 * tcconv::POOL_MAXQ) {
+    if (is_tc(c.math) && !(tc_disable_mask() & 64) && cs <= 128 * tcconv::POOL_MAXQ) {
         // tcgen05: 1x1 convolution in passes of 48 output channels into a scratch tensor, then one HBM-bound pooling pass
         static bool configured = false;
         if (!configured) {
@@ -352,9 +356,11 @@ static int trans_down_fwd(const Ctx& c, int l) {
             f.in = a.in; f.coef = a.coef; f.w = a.w; f.bias = a.bias + co0; f.out = tmp; f.stats = nullptr;
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = cs; f.out_C = cs; f.out_off = co0; f.N = (cs - co0) < 48 ? (cs - co0) : 48;
             f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = 0; f.up = 0; f.dbg = 0; f.one = 1; f.wpack = c.WPACK();
+            f.x3 = c.math == ENDO_MATH_TF32X3;
             {
                 ProfScope prof(PC_BN, c.s);
-                tcconv::pack_w_1x1_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
+                if (f.x3) tcconv::pack_w_1x1_x3_kernel<<<cdiv(cs, 8), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
+                else tcconv::pack_w_1x1_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }
             dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
@@ -388,7 +394,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
     w.g_off = P.offIn[l + 1]; w.g_K = cs; w.g_h = P.h[l + 1]; w.g_w = P.w[l + 1];
     w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = cs;
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 32)) {
+    if (is_tc(c.math) && !(tc_disable_mask() & 32)) {
         // tcgen05 (bf16): the weight-gradient kernel in 1x1 mode, 48 output channels per launch; bias gradient = sum of the
         // routed (= of the pooled) gradient, reduced over the coarse buffer
         static bool configured = false;
@@ -398,7 +404,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
             configured = true;
         }
         {
-            ProfScope prof(PC_WGRAD, c.s);
+            ProfScope prof(PC_WGRAD_TRANS, c.s);
             bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.s>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
                                                                              P.Ctot[l + 1], P.offIn[l + 1], cs,
                                                                              (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
@@ -419,7 +425,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
             if (want < 1) want = 1;
             q.tiles_per_cta = cdiv(q.n_tiles, want);
             dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
-            ProfScope prof(PC_WGRAD, c.s);
+            ProfScope prof(PC_WGRAD_TRANS, c.s);
             tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(q);
             ENDO_CHECK_LAUNCH();
         }
@@ -453,7 +459,7 @@ static int trans_up_fwd(const Ctx& c, int i) {
     a.w = c.params + t.conv.w; a.bias = c.params + t.conv.b; a.w_cin = t.cin;
     a.out = c.X(l); a.out_C = P.Ctot[l]; a.out_off = 0; a.N = t.conv.cout; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.ST(l); a.stats_C = P.Ctot[l];
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 8)) {
+    if (is_tc(c.math) && !(tc_disable_mask() & 8)) {
         // tcgen05: the DenseLayer forward kernel with the upsampling loader, 16 output channels per pass
         static bool configured = false;
         if (!configured) {
@@ -467,10 +473,11 @@ static int trans_up_fwd(const Ctx& c, int i) {
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = a.K; f.out_C = a.out_C; f.out_off = a.out_off + co0;
             f.N = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
             f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.up = 1; f.dbg = 0; f.one = 0;
-            f.wpack = c.WPACK();
+            f.wpack = c.WPACK(); f.x3 = c.math == ENDO_MATH_TF32X3;
             {
                 ProfScope prof(PC_BN, c.s);
-                tcconv::pack_w_fwd_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
+                if (f.x3) tcconv::pack_w_fwd_x3_kernel<<<cdiv(f.K, 8), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
+                else tcconv::pack_w_fwd_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }
             dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
@@ -492,7 +499,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = 0; w.g_K = t.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = t.cin;
-    if (c.math == ENDO_MATH_TF32 && !(tc_disable_mask() & 16)) {
+    if (is_tc(c.math) && !(tc_disable_mask() & 16)) {
         // tcgen05 (bf16): the DenseLayer weight-gradient kernel with the upsampling loader, 16 output channels per pass;
         // the bias gradient comes from the small dedicated reduction
         static bool configured = false;
@@ -502,7 +509,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
             configured = true;
         }
         {
-            ProfScope prof(PC_WGRAD, c.s);
+            ProfScope prof(PC_WGRAD_TRANS, c.s);
             bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
                                                                                        t.conv.cout, (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
             ENDO_CHECK_LAUNCH();
@@ -521,7 +528,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
             if (want < 1) want = 1;
             q.tiles_per_cta = cdiv(q.n_tiles, want);
             dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
-            ProfScope prof(PC_WGRAD, c.s);
+            ProfScope prof(PC_WGRAD_TRANS, c.s);
             tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(q);
             ENDO_CHECK_LAUNCH();
         }
@@ -569,7 +576,7 @@ extern "C" size_t endo_net_backward_scratch_bytes(const endo_net_config* cfg, in
 extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const float* params, float* bn_buffers,
                             float* y, void* acts, size_t acts_bytes, int B, int H, int W, int groups, int training,
                             int math, endo_stream_t stream) {
-    if (math != ENDO_MATH_FP32 && math != ENDO_MATH_TF32) return ENDO_ERR_CONFIG;
+    if (math != ENDO_MATH_FP32 && !is_tc(math)) return ENDO_ERR_CONFIG;
     if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
     if (!x || !params || !bn_buffers || !y || !acts) return ENDO_ERR_BAD_POINTER;
     if (!aligned16(x) || !aligned16(params) || !aligned16(y) || (reinterpret_cast<uintptr_t>(acts) & 255u))
@@ -614,7 +621,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
                             float* g_params, float* g_x, void* acts, size_t acts_bytes, void* scratch,
                             size_t scratch_bytes, int B, int H, int W, int groups, int accumulate, int math,
                             endo_stream_t stream) {
-    if (math != ENDO_MATH_FP32 && math != ENDO_MATH_TF32) return ENDO_ERR_CONFIG;
+    if (math != ENDO_MATH_FP32 && !is_tc(math)) return ENDO_ERR_CONFIG;
     if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
     if (g_x != nullptr) return ENDO_ERR_CONFIG;              // train.py never differentiates w.r.t. the images
     if (!g_y || !x || !params || !g_params || !acts || !scratch) return ENDO_ERR_BAD_POINTER;

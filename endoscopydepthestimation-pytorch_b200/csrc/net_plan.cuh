@@ -43,7 +43,7 @@ struct NetPlan {
     long long stat_off[kMaxLevels];             // double [G][Ctot][2]  (sum, sumsq)
     long long mi_off[kMaxLevels];               // float  [G][Ctot][2]  (mean, invstd)
     long long pre_off;                          // float  [B*H*W] finalConv output before abs
-    long long wpack_off;                        // 256 KB: tensor-core weight image of the layer being run (forward)
+    long long wpack_off;                        // 512 KB: tensor-core weight image of the layer being run (forward)
     long long tdtmp_off, tdtmp_bytes;           // forward scratch: float [B,h,w,Cs] TransitionDown conv output before pooling (tensor-core
                                                 // path, largest level); split-K partial sums of low-resolution DenseLayers
     long long acts_bytes;
@@ -174,7 +174,7 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         off = align_up(off + 1ll * B * P.h[l + 1] * P.w[l + 1] * (P.C0[l] + P.Dn[l]), 256);
     }
     P.pre_off = off; off = align_up(off + 4ll * B * H * W, 256);
-    P.wpack_off = off; off += 256 * 1024;
+    P.wpack_off = off; off += 512 * 1024;
     {
         long long mx = 0;
         for (int l = 0; l < nd; ++l) {

@@ -48,6 +48,17 @@ constexpr int NPROD = 512;                              // 16 producer / epilogu
 constexpr int SMEM_BYTES = 2 * A_STAGE_BYTES + 2 * B_STAGE_BYTES + EDGE_FLOATS * 4 + 16 * 16 * 2 * 4 + 128;
 constexpr int NTHREADS = NPROD + 32;
 
+// kind::tf32 TRUNCATES the low 13 mantissa bits of its fp32 operands (tests/test_gpu_tc_probe.py).  Truncation is biased
+// (every magnitude shrinks by ~2^-11 on average) and the bias compounds through the 57 stacked layers, so every operand
+// is rounded to nearest tf32 while it is staged: the rounding error is then zero-mean and averages out over the GEMM K.
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+// hi part of the 3xTF32 split v = hi + lo (lo = v - hi is exact in fp32 and fits the 11 bits tf32 keeps up to 2^-23 |v|)
+__device__ __forceinline__ float tf32_hi(float v) { return tf32_rn(v); }
+
 // Weight images: the exact shared-memory layout of one pipeline stage, built once per layer call by a tiny kernel so
 // that the producers copy them with coalesced 128-bit loads (staging OIHW weights with scalar, serialised loads cost
 // more than the activation stream in the first version of these kernels).
@@ -61,7 +72,7 @@ pack_w_fwd_kernel(const float* __restrict__ w, int K, int N, float* __restrict__
         const int ky = blk >> 1, k8 = blk & 1, co = n & 15, kx = n >> 4, cin = c * 16 + k8 * 8 + kc * 4 + e;
         float v = 0.f;
         if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
-        out[(size_t)c * 2304 + d] = v;
+        out[(size_t)c * 2304 + d] = tf32_rn(v);
     }
 }
 __global__ void __launch_bounds__(256)
@@ -72,7 +83,34 @@ pack_w_dgrad_kernel(const float* __restrict__ w, int Cin, int Cout, float* __res
         const int tap = blk >> 1, k8 = blk & 1, co = k8 * 8 + kc * 4 + e, ci = c * 64 + n;
         float v = 0.f;
         if (co < Cout && ci < Cin) v = __ldg(w + ((size_t)co * Cin + ci) * 9 + (8 - tap));
-        out[(size_t)c * 9216 + d] = v;
+        out[(size_t)c * 9216 + d] = tf32_rn(v);
+    }
+}
+
+// 3xTF32 (error-compensated, fp32-grade) variants: a chunk holds 8 input channels; block (ky, part) carries the tf32-truncated
+// weights (part 0, "hi") and the remainders w - hi (part 1, "lo") of the same 8 channels.
+__global__ void __launch_bounds__(256)
+pack_w_fwd_x3_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 2304; d += 256) {
+        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int ky = blk >> 1, part = blk & 1, co = n & 15, kx = n >> 4, cin = c * 8 + kc * 4 + e;
+        float v = 0.f;
+        if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
+        const float hi = tf32_hi(v);
+        out[(size_t)c * 2304 + d] = part ? (v - hi) : hi;
+    }
+}
+__global__ void __launch_bounds__(256)
+pack_w_1x1_x3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 768; d += 256) {
+        const int part = d / 384, r = d - part * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int cin = c * 8 + kc * 4 + e, co = co0 + n;
+        float v = 0.f;
+        if (co < Ntot && cin < K) v = __ldg(w + (size_t)co * K + cin);
+        const float hi = tf32_hi(v);
+        out[(size_t)c * 2304 + d] = part ? (v - hi) : hi;
     }
 }
 
@@ -85,7 +123,7 @@ pack_w_1x1_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* 
         const int cin = c * 16 + blk * 8 + kc * 4 + e, co = co0 + n;
         float v = 0.f;
         if (blk < 2 && co < Ntot && cin < K) v = __ldg(w + (size_t)co * K + cin);
-        out[(size_t)c * 2304 + d] = v;
+        out[(size_t)c * 2304 + d] = tf32_rn(v);
     }
 }
 
@@ -164,6 +202,7 @@ struct FwdArgs {
     int dbg;     // performance experiments only (ENDO_TC_DEBUG): 1 = skip the MMAs, 2 = skip the activation loads
     const float* wpack;   // weight image built by pack_w_fwd_kernel (2304 floats per 16-channel chunk)
     int one;              // 1: 1x1 convolution, N <= 48 plain output channels, epilogue = + bias, store (no taps, no statistics)
+    int x3;               // 1: 3xTF32 -- a stage holds 8 channels as planes (hi0, hi1, lo0, lo1); D += Ahi*Whi + Alo*Whi + Ahi*Wlo
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -183,7 +222,8 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     const int y0 = ty * TH, x0 = tx * TW;
     const int b = blockIdx.z;
     const int g = b / (A.B / A.G);
-    const int nchunks = (A.K + KCH - 1) / KCH;
+    const int kch = A.x3 ? 8 : KCH;                            // input channels per pipeline stage
+    const int nchunks = (A.K + kch - 1) / kch;
 
     if (tid == 0) ENDO_TRACE(1);
     if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
@@ -203,14 +243,16 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
         // (~4 us while every SM streams operands): fetch it now
         if (tid < 48) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;     // visible after the named barrier below
         // ======================================================================== producers
-        const int grp = tid & 3;                                  // this thread always stages the same 4-channel group
+        const int grp = tid & 3;                                  // this thread always stages the same plane (4-channel group)
+        const int cgrp = A.x3 ? (grp & 1) : grp;                  // x3: planes 0,1 = hi, planes 2,3 = lo of channel groups 0,1
+        const bool lo_part = A.x3 && (grp >> 1);
         for (int c = 0; c < nchunks; ++c) {
             const int s = c & 1;
             if (tid == 0) ENDO_TRACE(16 + c * 8 + 0);
             if (c >= 2) tc::mbar_wait(bars + 2 + s, ((c >> 1) - 1) & 1);
             if (tid == 0) ENDO_TRACE(16 + c * 8 + 1);
             unsigned char* a_s = a_st0 + s * A_STAGE_BYTES + grp * PLANE_BYTES;
-            const int ch = c * KCH + grp * 4;
+            const int ch = c * kch + cgrp * 4;
             float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
             const bool ch_ok = ch < A.K;
             if (ch_ok && !A.up) {
@@ -248,6 +290,10 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                             else {
                                 v.x = fmaxf(fmaf(k0.x, q[j].x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q[j].y - k1.z, k1.y), 0.f);
                                 v.z = fmaxf(fmaf(k2.x, q[j].z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q[j].w - k3.z, k3.y), 0.f);
+                            }
+                            {                                            // exact split v = hi + lo (hi = v rounded to tf32)
+                                const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
+                                v = lo_part ? make_float4(v.x - hx, v.y - hy, v.z - hz, v.w - hw) : make_float4(hx, hy, hz, hw);
                             }
                         }
                         *reinterpret_cast<float4*>(a_s + (size_t)px * 16) = v;
@@ -390,12 +436,31 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             ENDO_TRACE(16 + c * 8 + 6);
             const uint32_t a_base = tc::smem_u32(a_st0 + s * A_STAGE_BYTES);
             const uint32_t b_base = tc::smem_u32(b_st0 + s * B_STAGE_BYTES);
-            const int nk8 = (A.K - c * KCH > 8) ? 2 : 1;           // skip an all-zero K half on the last chunk
+            const int nk8 = (A.x3 || A.K - c * KCH > 8) ? 2 : 1;   // skip an all-zero K half on the last chunk
             // A tcgen05.mma that accumulates into the SAME TMEM tile as its predecessor waits ~266 cycles for it
             // (measured, tests/test_gpu_tc_probe.py::test_mma_cost_by_operand_layout), whatever its size.  Consecutive
             // MMAs therefore target different M-blocks: 9 independent accumulator chains keep the pipe busy.
             const uint64_t a_hi = tc::smem_desc(0, PLANE_BYTES, 128), b_hi = tc::smem_desc(0, NB * 16, 128);
-            if (A.one) {
+            if (A.x3) {
+                // 3xTF32: planes (0,1) = A_hi, planes (2,3) = A_lo; weight block (ky, 0) = W_hi, (ky, 1) = W_lo.  The small
+                // cross terms are accumulated first, the hi*hi term last.
+                const int nky = A.one ? 1 : 3;
+#pragma unroll 1
+                for (int ky = 0; ky < nky; ++ky) {
+                    const uint32_t row0 = (uint32_t)(A.one ? PITCH : PITCH + (ky - 1) * PITCH) * 16u;
+                    const uint64_t ahi = a_hi | (uint64_t)((a_base + row0) >> 4);
+                    const uint64_t alo = a_hi | (uint64_t)((a_base + 2u * PLANE_BYTES + row0) >> 4);
+                    const uint64_t bhi = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + 0) * B_BLOCK_BYTES) >> 4);
+                    const uint64_t blo = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + 1) * B_BLOCK_BYTES) >> 4);
+                    const uint32_t acc = (uint32_t)((c | ky) != 0);
+#pragma unroll
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc, acc);
+#pragma unroll
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), blo, idesc, 1u);
+#pragma unroll
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
+                }
+            } else if (A.one) {
                 for (int k8 = 0; k8 < nk8; ++k8) {
                     const uint64_t bd = b_hi | (uint64_t)((b_base + (uint32_t)k8 * B_BLOCK_BYTES) >> 4);
                     const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)PITCH * 16u) >> 4);
@@ -548,6 +613,7 @@ dense_dgrad_tf32_kernel(const Args A) {
                             v.x = gq[j].x + fmaf(c0.y, xq[j].x, c0.x); v.y = gq[j].y + fmaf(c0.w, xq[j].y, c0.z);
                             v.z = gq[j].z + fmaf(c1.y, xq[j].z, c1.x); v.w = gq[j].w + fmaf(c1.w, xq[j].w, c1.z);
                             if (r >= 1 && r <= TH && cc >= 1 && cc <= TW) { bs.x += v.x; bs.y += v.y; bs.z += v.z; bs.w += v.w; }
+                            v.x = tcconv::tf32_rn(v.x); v.y = tcconv::tf32_rn(v.y); v.z = tcconv::tf32_rn(v.z); v.w = tcconv::tf32_rn(v.w);
                         }
                         *reinterpret_cast<float4*>(g_s + grp * PLANE_BYTES + (size_t)(px + 1) * 16) = v;   // row 0 is a margin row
                     }

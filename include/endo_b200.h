@@ -144,7 +144,10 @@ int endo_scale_inv_bwd(const float* g_loss, const float* pred, const float* goal
  * bwd: g_y[B,1,H,W] -> g_params (flat, same layout as params; ACCUMULATED into if accumulate != 0,
  *   else overwritten) and optionally g_x.  `scratch` (endo_net_backward_scratch_bytes) is transient.
  * math: ENDO_MATH_FP32 = fp32 FFMA (parity path, matches the reference's CPU fp32 results);
- *       ENDO_MATH_TF32 / ENDO_MATH_BF16 = tcgen05 tensor-core tiles with fp32 accumulation.
+ *       ENDO_MATH_TF32 = tcgen05 tensor-core tiles, tf32 operands (what cuDNN runs the reference's convolutions in
+ *       by default), fp32 accumulation in TMEM; ENDO_MATH_TF32X3 = tcgen05 with error-compensated operands in the
+ *       forward (x = hi + lo, three tf32 MMAs per product: fp32-grade depth maps and losses on the tensor cores);
+ *       gradients as in ENDO_MATH_TF32 (tf32 data gradient, bf16 weight gradient, fp32 accumulation).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
     int in_channels;
@@ -157,7 +160,7 @@ typedef struct {
     int n_classes;            /* only 1 is supported */
 } endo_net_config;
 
-enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2 };
+enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2 /* reserved */, ENDO_MATH_TF32X3 = 3 };
 
 long long endo_net_param_count(const endo_net_config* cfg);
 long long endo_net_buffer_count(const endo_net_config* cfg); /* running_mean + running_var floats */
