@@ -45,6 +45,8 @@ CONFIGS = {
 METRIC = "image-pairs/sec fwd+bwd @256x320 bs8"
 DTYPE = {"fp32": "fp32 (FFMA convolutions, no tensor cores: strict-parity path)",
          "tf32": "tf32 operands on tcgen05 (forward, data gradient), bf16 operands (weight gradient), fp32 accumulate",
+         "bf16x3": "fp32 (forward: error-compensated two-term bf16 operands on tcgen05, three kind::f16 MMAs per product, depth maps "
+                   "within ~2e-5 of fp32; gradients: tf32 / bf16 operands on tcgen05; fp32 accumulate in TMEM; everything else fp32)",
          "tf32x3": "fp32 (forward: error-compensated 3xTF32 on tcgen05, fp32-grade depth maps and losses; gradients: tf32 / bf16 "
                    "operands on tcgen05; fp32 accumulate in TMEM; geometric layers, losses, BatchNorm statistics, optimiser fp32)"}
 
@@ -344,7 +346,8 @@ def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof
     achieved_tf = work_flops[dominant] / (dom_ms * 1e-3) / 1e12
     kind = {"fp32": "fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe)",
             "tf32": "tcgen05 kernels, tf32 / bf16 operands, fp32 accumulate in TMEM",
-            "tf32x3": "tcgen05 kernels: 3xTF32 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM"}[math_mode]
+            "tf32x3": "tcgen05 kernels: 3xTF32 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM",
+            "bf16x3": "tcgen05 kernels: bf16x3 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM"}[math_mode]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
                 "launches_per_step": dom_launches, "avg_launch_ms": dom_ms / dom_launches,
@@ -374,7 +377,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3"],
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3", "bf16x3"],
                     help="arithmetic of the conv path for the headline arm (default: the config's, fp32)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel development runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other math modes and the warp-layer microbenchmark")
@@ -482,8 +485,9 @@ def main():
         notes = {"fp32": "strict-parity path: every convolution in fp32 FFMA (no tensor cores); gradients at CPU-fp32 level",
                  "tf32": "every DenseLayer / transition convolution with plain tf32 operands (what cuDNN runs the reference's "
                          "convolutions in by default): depth maps within 2e-2 of the fp64 oracle (measured 1.3e-3)",
-                 "tf32x3": "3xTF32 forward (fp32-grade), tf32 / bf16-operand gradients"}
-        for mode in ("fp32", "tf32", "tf32x3"):
+                 "tf32x3": "3xTF32 forward (fp32-grade: depth maps within 2e-6 of the fp64 oracle), tf32 / bf16-operand gradients",
+                 "bf16x3": "two-term bf16 forward (depth maps within 2e-5 of the fp64 oracle), tf32 / bf16-operand gradients"}
+        for mode in ("fp32", "tf32", "tf32x3", "bf16x3"):
             if mode == math_mode:
                 continue
             m2 = new_model(mode)

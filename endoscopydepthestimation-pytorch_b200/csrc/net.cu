@@ -5,6 +5,7 @@
 #include "net_kernels.cuh"
 #include "net_plan.cuh"
 #include "net_tc.cuh"
+#include "net_pw.cuh"
 
 namespace endo {
 
@@ -119,7 +120,9 @@ static int tc_disable_mask() {
     return e ? atoi(e) : 0;
 }
 
-static inline bool is_tc(int math) { return math == ENDO_MATH_TF32 || math == ENDO_MATH_TF32X3; }
+static inline bool is_tc(int math) { return math == ENDO_MATH_TF32 || math == ENDO_MATH_TF32X3 || math == ENDO_MATH_BF16X3; }
+// forward operand scheme of the tensor-core modes: 0 = plain tf32, 1 = 3xTF32, 2 = bf16x3
+static inline int x3_mode(int math) { return math == ENDO_MATH_TF32X3 ? 1 : (math == ENDO_MATH_BF16X3 ? 2 : 0); }
 
 struct Ctx {
     const NetPlan& P;
@@ -159,6 +162,21 @@ static ConvArgs base_args(const Ctx& c) {
     return a;
 }
 
+static int launch_pw(const tcpw::Args& a, int G, cudaStream_t s, int cat) {
+    static bool configured = false;
+    if (!configured) {
+        ENDO_CUDA(cudaFuncSetAttribute(tcpw::pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const size_t smem = tcpw::smem_bytes(a.Npad, a.K, a.mode);
+    if (smem > 227 * 1024) return ENDO_ERR_CONFIG;
+    dim3 grid(cdiv(a.per_group, tcpw::MT), G, 1);
+    ProfScope prof(cat, s);
+    tcpw::pw_gemm_kernel<<<grid, tcpw::NTHREADS, smem, s>>>(a);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
 #define ENDO_TRY(expr)                 \
     do {                               \
         int _e = (expr);               \
@@ -180,10 +198,11 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
         t.in_C = a.in_C; t.in_off = a.in_off; t.K = a.K; t.out_C = a.out_C; t.out_off = a.out_off; t.N = a.N;
         t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask(); t.one = 0;
-        t.wpack = c.WPACK(); t.x3 = c.math == ENDO_MATH_TF32X3;
+        t.wpack = c.WPACK(); t.x3 = x3_mode(c.math);
         {
             ProfScope prof(PC_BN, c.s);
-            if (t.x3) tcconv::pack_w_fwd_x3_kernel<<<cdiv(t.K, 8), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
+            if (t.x3 == 1) tcconv::pack_w_fwd_x3_kernel<<<cdiv(t.K, 8), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
+            else if (t.x3 == 2) tcconv::pack_w_fwd_b3_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, reinterpret_cast<uint32_t*>(c.WPACK()));
             else tcconv::pack_w_fwd_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
             ENDO_CHECK_LAUNCH();
         }
@@ -193,10 +212,36 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
                                            tcconv::SMEM_BYTES));
             configured = true;
         }
-        dim3 grid(cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH), 1, t.B);
+        // Low-resolution levels: a CTA per 32x32 tile over ALL input channels leaves most SMs idle behind a long serial
+        // channel loop.  Split the channel chunks over blockIdx.y (raw partial sums to scratch, splitk_finish_kernel adds
+        // the slices in a fixed order, then bias + statistics): pick the slice count that minimises waves x chunks.
+        const int tiles = cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH) * t.B;
+        const int nchunks = cdiv(t.K, t.x3 == 1 ? 8 : 16);
+        const long long pixels = (long long)t.B * t.H * t.W;
+        int ksplit = 1;
+        if (tiles < 2 * kNumSMs && !(tc_disable_mask() & 128)) {
+            long long best = -1;
+            for (int ks = 1; ks <= 16 && ks <= nchunks; ++ks) {
+                if (4ll * ks * pixels * 16 > P.tdtmp_bytes) break;
+                const long long cost = (long long)cdiv((long long)tiles * ks, kNumSMs) * (cdiv(nchunks, ks) + 2);
+                if (best < 0 || cost < best) { best = cost; ksplit = ks; }
+            }
+            ksplit = cdiv(nchunks, cdiv(nchunks, ksplit));          // no empty slice
+        }
+        t.partial = nullptr; t.ksplit = 1; t.pixels = pixels;
+        if (ksplit > 1) { t.partial = reinterpret_cast<float*>(c.acts + P.tdtmp_off); t.ksplit = ksplit; }
+        dim3 grid(cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH), ksplit, t.B);
         ProfScope prof(PC_CONV_DENSE_FWD, c.s);
         tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(t);
         ENDO_CHECK_LAUNCH();
+        if (ksplit > 1) {
+            const int per_group = (int)(pixels / t.G);
+            int fblocks = cdiv(per_group, 64);
+            if (fblocks > 4 * kNumSMs) fblocks = 4 * kNumSMs;
+            splitk_finish_kernel<16><<<dim3(fblocks, t.G), 256, 0, c.s>>>(t.partial, t.bias, t.out, t.stats, ksplit, pixels, per_group,
+                                                                        t.N, t.out_C, t.out_off, t.stats_C);
+            ENDO_CHECK_LAUNCH();
+        }
         return ENDO_OK;
     }
     // Low-resolution levels: 32x32 tiles over all input channels would occupy a handful of SMs for hundreds of
@@ -311,7 +356,9 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
                                            tcdgrad::SMEM_BYTES));
             configured = true;
         }
-        dim3 grid(cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH), 1, t.B);
+        const int tiles = cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH);
+        const int ysplit = (tiles * t.B < 4 * kNumSMs && !(tc_disable_mask() & 128)) ? cdiv(t.Cin, tcdgrad::NC) : 1;
+        dim3 grid(tiles, ysplit, t.B);
         ProfScope prof(PC_DGRAD, c.s);
         tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(t);
         ENDO_CHECK_LAUNCH();
@@ -351,15 +398,31 @@ static int trans_down_fwd(const Ctx& c, int l) {
             configured = true;
         }
         float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
-        for (int co0 = 0; co0 < cs; co0 += 48) {
+        const int npad = (cs + 15) / 16 * 16;
+        const bool pw = npad <= 512 && !(tc_disable_mask() & 512);
+        if (pw) {
+            // one GEMM over all output channels per 128-pixel tile (net_pw.cuh): the input is read once
+            tcpw::Args q{};
+            q.in = a.in; q.in_C = a.in_C; q.in_off = a.in_off; q.coef = a.coef; q.wpack = c.WPACK(); q.bias = a.bias;
+            q.out = tmp; q.out_C = cs; q.out_off = 0; q.K = cs; q.N = cs; q.Npad = npad;
+            q.per_group = (long long)(P.B / P.G) * a.oh * a.ow; q.mode = 0; q.x3 = x3_mode(c.math) != 0;
+            {
+                ProfScope prof(PC_BN, c.s);
+                tcpw::pack_w_pw_kernel<<<cdiv(cs, q.x3 ? 8 : 16), 256, 0, c.s>>>(a.w, cs, npad, q.x3, 0, c.WPACK());
+                ENDO_CHECK_LAUNCH();
+            }
+            ENDO_TRY(launch_pw(q, P.G, c.s, PC_CONV_TRANS_FWD));
+        }
+        for (int co0 = 0; co0 < (pw ? 0 : cs); co0 += 48) {
             tcconv::FwdArgs f;
             f.in = a.in; f.coef = a.coef; f.w = a.w; f.bias = a.bias + co0; f.out = tmp; f.stats = nullptr;
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = cs; f.out_C = cs; f.out_off = co0; f.N = (cs - co0) < 48 ? (cs - co0) : 48;
             f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = 0; f.up = 0; f.dbg = 0; f.one = 1; f.wpack = c.WPACK();
-            f.x3 = c.math == ENDO_MATH_TF32X3;
+            f.x3 = x3_mode(c.math); f.partial = nullptr; f.ksplit = 1; f.pixels = 0;
             {
                 ProfScope prof(PC_BN, c.s);
-                if (f.x3) tcconv::pack_w_1x1_x3_kernel<<<cdiv(cs, 8), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
+                if (f.x3 == 1) tcconv::pack_w_1x1_x3_kernel<<<cdiv(cs, 8), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
+                else if (f.x3 == 2) tcconv::pack_w_1x1_b3_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, reinterpret_cast<uint32_t*>(c.WPACK()));
                 else tcconv::pack_w_1x1_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }
@@ -439,7 +502,24 @@ static int trans_down_bwd(const Ctx& c, int l) {
     a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = P.offIn[l]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.BNRED(); a.stats_C = P.maxC;
     a.x = c.X(l); a.ep_coef = c.COEF(t.bn);
-    ENDO_TRY((launch_conv<1, 2, 48, 8, LM_GRADPOOL, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+    const int npad = (cs + 15) / 16 * 16;
+    if (is_tc(c.math) && npad <= 512 && !(tc_disable_mask() & 1024)) {
+        // tcgen05 (tf32): routed-gradient GEMM over all input channels per 128-pixel tile, BN-backward epilogue (net_pw.cuh)
+        tcpw::Args q{};
+        q.argmax = am; q.gc = c.GX(l + 1); q.xc = c.X(l + 1); q.abc = c.AB(l + 1); q.cC = P.Ctot[l + 1]; q.c_off = P.offIn[l + 1];
+        q.H = P.h[l]; q.W = P.w[l]; q.wpack = c.WPACK_BWD();
+        q.out = c.GX(l); q.out_C = P.Ctot[l]; q.out_off = P.offIn[l]; q.x = c.X(l); q.ep_coef = c.COEF(t.bn);
+        q.red = c.BNRED(); q.red_C = P.maxC; q.K = cs; q.N = cs; q.Npad = npad;
+        q.per_group = (long long)(P.B / P.G) * P.h[l] * P.w[l]; q.mode = 1; q.x3 = 0;
+        {
+            ProfScope prof(PC_BN, c.s);
+            tcpw::pack_w_pw_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(t.conv.w + c.params, cs, npad, 0, 1, c.WPACK_BWD());
+            ENDO_CHECK_LAUNCH();
+        }
+        ENDO_TRY(launch_pw(q, P.G, c.s, PC_DGRAD_TRANS));
+    } else {
+        ENDO_TRY((launch_conv<1, 2, 48, 8, LM_GRADPOOL, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
+    }
     BnBwdArgs b;
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(t.bn); b.mi = c.MI(l); b.ab = c.AB(l);
     b.dgamma = c.gparams + t.bn.gamma; b.dbeta = c.gparams + t.bn.beta;
@@ -473,10 +553,11 @@ static int trans_up_fwd(const Ctx& c, int i) {
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = a.K; f.out_C = a.out_C; f.out_off = a.out_off + co0;
             f.N = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
             f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.up = 1; f.dbg = 0; f.one = 0;
-            f.wpack = c.WPACK(); f.x3 = c.math == ENDO_MATH_TF32X3;
+            f.wpack = c.WPACK(); f.x3 = x3_mode(c.math); f.partial = nullptr; f.ksplit = 1; f.pixels = 0;
             {
                 ProfScope prof(PC_BN, c.s);
-                if (f.x3) tcconv::pack_w_fwd_x3_kernel<<<cdiv(f.K, 8), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
+                if (f.x3 == 1) tcconv::pack_w_fwd_x3_kernel<<<cdiv(f.K, 8), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
+                else if (f.x3 == 2) tcconv::pack_w_fwd_b3_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, reinterpret_cast<uint32_t*>(c.WPACK()));
                 else tcconv::pack_w_fwd_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }

@@ -43,7 +43,7 @@ struct NetPlan {
     long long stat_off[kMaxLevels];             // double [G][Ctot][2]  (sum, sumsq)
     long long mi_off[kMaxLevels];               // float  [G][Ctot][2]  (mean, invstd)
     long long pre_off;                          // float  [B*H*W] finalConv output before abs
-    long long wpack_off;                        // 512 KB: tensor-core weight image of the layer being run (forward)
+    long long wpack_off;                        // sized for the widest layer: tensor-core weight image of the layer being run (forward)
     long long tdtmp_off, tdtmp_bytes;           // forward scratch: float [B,h,w,Cs] TransitionDown conv output before pooling (tensor-core
                                                 // path, largest level); split-K partial sums of low-resolution DenseLayers
     long long acts_bytes;
@@ -51,7 +51,7 @@ struct NetPlan {
     long long gx_off[kMaxLevels];               // float [B,h,w,Ctot] gradient buffers
     long long ab_off[kMaxLevels];               // float [G][Ctot][2] lazy BN-backward correction (A, Bc)
     long long bnred_off;                        // double [G][maxC][2] per-layer BN backward sums
-    long long wpack_bwd_off;                    // 256 KB: tensor-core weight image of the layer being run (backward)
+    long long wpack_bwd_off;                    // sized for the widest layer: tensor-core weight image of the layer being run (backward)
     long long scratch_bytes;
     int maxC;
     ConvP first, final_;
@@ -174,7 +174,12 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         off = align_up(off + 1ll * B * P.h[l + 1] * P.w[l + 1] * (P.C0[l] + P.Dn[l]), 256);
     }
     P.pre_off = off; off = align_up(off + 4ll * B * H * W, 256);
-    P.wpack_off = off; off += 512 * 1024;
+    long long maxTD = 0;                                     // widest TransitionDown (1x1 conv C -> C), rounded to 16
+    for (int l = 0; l < nd; ++l) { const long long cs = (P.C0[l] + P.Dn[l] + 15) / 16 * 16; if (cs > maxTD) maxTD = cs; }
+    {   // 3x3 layers: one 9,216-byte image per 8-channel chunk (3xTF32); 1x1 layers: the whole matrix as hi + lo planes
+        long long a = 9216ll * ((P.maxC + 7) / 8) + 9216, b2 = 8ll * maxTD * maxTD + 4096;
+        P.wpack_off = off; off = align_up(off + (a > b2 ? a : b2), 256);
+    }
     {
         long long mx = 0;
         for (int l = 0; l < nd; ++l) {
@@ -189,7 +194,10 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
     for (int l = 0; l <= nd; ++l) { P.gx_off[l] = off; off = align_up(off + 4ll * B * P.h[l] * P.w[l] * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.ab_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }
     P.bnred_off = off; off = align_up(off + 16ll * P.G * P.maxC, 256);
-    P.wpack_bwd_off = off; off += 256 * 1024;
+    {   // 3x3 layers: one 36,864-byte image per 64-channel chunk; 1x1 layers: the transposed matrix, tf32
+        long long a = 36864ll * ((P.maxC + 63) / 64) + 36864, b2 = 4ll * maxTD * maxTD + 4096;
+        P.wpack_bwd_off = off; off = align_up(off + (a > b2 ? a : b2), 256);
+    }
     P.scratch_bytes = off;
     return ENDO_OK;
 }

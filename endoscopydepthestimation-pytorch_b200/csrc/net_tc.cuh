@@ -114,6 +114,49 @@ pack_w_1x1_x3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, floa
     }
 }
 
+// bf16x3 (error-compensated bf16: x = b1 + b2, two bf16 terms = 16 significant bits, three kind::f16 MMAs of K = 16 per
+// product -- half the MMA count of 3xTF32): a chunk holds 16 input channels, block (ky, term) = [kc (8 channels)][n][8 bf16].
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// returns the packed first terms; (rlo, rhi) receive the exact remainders
+__device__ __forceinline__ uint32_t bf16_split(float lo, float hi, float& rlo, float& rhi) {
+    const uint32_t p = bf16x2_rn(lo, hi);
+    rlo = lo - __uint_as_float(p << 16);
+    rhi = hi - __uint_as_float(p & 0xFFFF0000u);
+    return p;
+}
+__global__ void __launch_bounds__(256)
+pack_w_fwd_b3_kernel(const float* __restrict__ w, int K, int N, uint32_t* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 2304; d += 256) {
+        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int ky = blk >> 1, term = blk & 1, co = n & 15, kx = n >> 4, cin = c * 16 + kc * 8 + e * 2;
+        float v0 = 0.f, v1 = 0.f;
+        if (co < N && cin < K) v0 = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
+        if (co < N && cin + 1 < K) v1 = __ldg(w + (((size_t)co * K + cin + 1) * 3 + ky) * 3 + kx);
+        float r0, r1;
+        const uint32_t b1 = bf16_split(v0, v1, r0, r1);
+        out[(size_t)c * 2304 + d] = term ? bf16x2_rn(r0, r1) : b1;
+    }
+}
+__global__ void __launch_bounds__(256)
+pack_w_1x1_b3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, uint32_t* __restrict__ out) {
+    const int c = blockIdx.x;
+    for (int d = threadIdx.x; d < 768; d += 256) {
+        const int term = d / 384, r = d - term * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int cin = c * 16 + kc * 8 + e * 2, co = co0 + n;
+        float v0 = 0.f, v1 = 0.f;
+        if (co < Ntot && cin < K) v0 = __ldg(w + (size_t)co * K + cin);
+        if (co < Ntot && cin + 1 < K) v1 = __ldg(w + (size_t)co * K + cin + 1);
+        float r0, r1;
+        const uint32_t b1 = bf16_split(v0, v1, r0, r1);
+        out[(size_t)c * 2304 + d] = term ? bf16x2_rn(r0, r1) : b1;
+    }
+}
+
 // 1x1 convolution (TransitionDown): only blocks k8 = 0, 1 of the stage image are used, n = output channel co0 + n
 __global__ void __launch_bounds__(256)
 pack_w_1x1_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* __restrict__ out) {
@@ -202,7 +245,9 @@ struct FwdArgs {
     int dbg;     // performance experiments only (ENDO_TC_DEBUG): 1 = skip the MMAs, 2 = skip the activation loads
     const float* wpack;   // weight image built by pack_w_fwd_kernel (2304 floats per 16-channel chunk)
     int one;              // 1: 1x1 convolution, N <= 48 plain output channels, epilogue = + bias, store (no taps, no statistics)
-    int x3;               // 1: 3xTF32 -- a stage holds 8 channels as planes (hi0, hi1, lo0, lo1); D += Ahi*Whi + Alo*Whi + Ahi*Wlo
+    float* partial; int ksplit; long long pixels;   // split-K (not with `one`): [ksplit][B*H*W][16] raw partial sums, else nullptr
+    int x3;               // 1: 3xTF32 -- a stage holds 8 channels as planes (hi0, hi1, lo0, lo1); D += Alo*Whi + Ahi*Wlo + Ahi*Whi
+                          // 2: bf16x3 -- a stage holds 16 channels as bf16 planes (b1: ch 0-7, 8-15; b2: ch 0-7, 8-15), kind::f16
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -222,8 +267,13 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     const int y0 = ty * TH, x0 = tx * TW;
     const int b = blockIdx.z;
     const int g = b / (A.B / A.G);
-    const int kch = A.x3 ? 8 : KCH;                            // input channels per pipeline stage
+    const int kch = (A.x3 == 1) ? 8 : KCH;                            // input channels per pipeline stage
     const int nchunks = (A.K + kch - 1) / kch;
+    // split-K (low-resolution levels: few tiles, long channel loops): blockIdx.y owns a slice of the channel chunks and
+    // stores raw partial sums; splitk_finish_kernel adds the slices in a fixed order, then bias + statistics
+    const int per_slice = A.partial ? (nchunks + A.ksplit - 1) / A.ksplit : nchunks;
+    const int c_begin = A.partial ? (int)blockIdx.y * per_slice : 0;
+    const int c_end = min(nchunks, c_begin + per_slice);
 
     if (tid == 0) ENDO_TRACE(1);
     if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
@@ -243,14 +293,110 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
         // (~4 us while every SM streams operands): fetch it now
         if (tid < 48) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;     // visible after the named barrier below
         // ======================================================================== producers
+        if (A.x3 == 1) {
+            // ---- 3xTF32 producer: a stage = 8 channels as planes (hi0, hi1, lo0, lo1).  An item = (pixel, 4-channel group):
+            // ONE 16-byte load, BN+ReLU, exact split, TWO 16-byte shared stores.  Software-pipelined: the loads of chunk c+1
+            // are in flight (registers) while chunk c is transformed and stored, so the memory system never idles between
+            // stages; pixel offsets / validity are loop-invariant and computed once.
+            constexpr int NIT = 5;                                    // ceil(2 * 1156 / 512)
+            const int cg = tid & 1;
+            const int sh = A.up ? 1 : 0;
+            const int sW = A.W >> sh;
+            const float* in_img = A.in + (size_t)b * (A.H >> sh) * sW * A.in_C + A.in_off + cg * 4;
+            uint32_t poff[NIT];
+            unsigned pixok = 0u, rowok = 0u;
+#pragma unroll
+            for (int j = 0; j < NIT; ++j) {
+                const int px = (tid >> 1) + 256 * j;
+                const int r = px / PITCH, cc = px - r * PITCH;
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                poff[j] = 0u;
+                if (px < REAL_ROWS) {
+                    rowok |= 1u << j;
+                    if (y >= 0 && y < A.H && x >= 0 && x < A.W && !(A.dbg & 2)) {
+                        pixok |= 1u << j;
+                        poff[j] = (uint32_t)(((y >> sh) * sW + (x >> sh)) * A.in_C);
+                    }
+                }
+            }
+            float4 cur[NIT], nxt[NIT];
+#pragma unroll
+            for (int j = 0; j < NIT; ++j) {
+                cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((pixok & (1u << j)) && c_begin * 8 + cg * 4 < A.K)
+                    cur[j] = __ldg(reinterpret_cast<const float4*>(in_img + c_begin * 8 + poff[j]));
+            }
+            for (int c = c_begin; c < c_end; ++c) {
+                const int it = c - c_begin;
+                const int s = it & 1;
+                const int ch = c * 8 + cg * 4;
+                const bool ch_ok = ch < A.K;
+                const bool nxt_ok = ch + 8 < A.K && c + 1 < c_end;
+#pragma unroll
+                for (int j = 0; j < NIT; ++j) {                        // prefetch chunk c + 1
+                    nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((pixok & (1u << j)) && nxt_ok) nxt[j] = __ldg(reinterpret_cast<const float4*>(in_img + (c + 1) * 8 + poff[j]));
+                }
+                float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
+                if (ch_ok && !A.up) {
+                    const float* cf = A.coef + ((size_t)g * A.K + ch) * 4;
+                    k0 = __ldg(reinterpret_cast<const float4*>(cf)); k1 = __ldg(reinterpret_cast<const float4*>(cf + 4));
+                    k2 = __ldg(reinterpret_cast<const float4*>(cf + 8)); k3 = __ldg(reinterpret_cast<const float4*>(cf + 12));
+                }
+                float4 wq[2];
+                {
+                    const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 2304);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int i = tid + NPROD * j;
+                        wq[j] = (i < 576) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (tid == 0) ENDO_TRACE(16 + c * 8 + 0);
+                if (it >= 2) tc::mbar_wait(bars + 2 + s, ((it >> 1) - 1) & 1);
+                if (tid == 0) ENDO_TRACE(16 + c * 8 + 1);
+                unsigned char* a_hi_s = a_st0 + s * A_STAGE_BYTES + cg * PLANE_BYTES;
+#pragma unroll
+                for (int j = 0; j < NIT; ++j) {
+                    if (rowok & (1u << j)) {
+                        const int px = (tid >> 1) + 256 * j;
+                        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+                        if ((pixok & (1u << j)) && ch_ok) {
+                            float4 v = cur[j];
+                            if (!A.up) {
+                                v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
+                                v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
+                            }
+                            hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                            lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                        }
+                        *reinterpret_cast<float4*>(a_hi_s + (size_t)px * 16) = hi;
+                        *reinterpret_cast<float4*>(a_hi_s + 2 * PLANE_BYTES + (size_t)px * 16) = lo;
+                    }
+                }
+                if (tid == 0) ENDO_TRACE(16 + c * 8 + 2);
+                {
+                    unsigned char* b_s = b_st0 + s * B_STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int i = tid + NPROD * j;
+                        if (i < 576) *reinterpret_cast<float4*>(b_s + (size_t)i * 16) = wq[j];
+                    }
+                }
+                if (tid == 0) ENDO_TRACE(16 + c * 8 + 3);
+                tc::fence_proxy_async();
+                tc::mbar_arrive(bars + s);
+                if (tid == 0) ENDO_TRACE(16 + c * 8 + 4);
+#pragma unroll
+                for (int j = 0; j < NIT; ++j) cur[j] = nxt[j];
+            }
+        }
         const int grp = tid & 3;                                  // this thread always stages the same plane (4-channel group)
-        const int cgrp = A.x3 ? (grp & 1) : grp;                  // x3: planes 0,1 = hi, planes 2,3 = lo of channel groups 0,1
-        const bool lo_part = A.x3 && (grp >> 1);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c & 1;
+        const int cgrp = grp;
+        for (int c = c_begin; c < (A.x3 == 1 ? c_begin : c_end); ++c) {
+            const int it = c - c_begin;
+            const int s = it & 1;
             if (tid == 0) ENDO_TRACE(16 + c * 8 + 0);
-            if (c >= 2) tc::mbar_wait(bars + 2 + s, ((c >> 1) - 1) & 1);
-            if (tid == 0) ENDO_TRACE(16 + c * 8 + 1);
             unsigned char* a_s = a_st0 + s * A_STAGE_BYTES + grp * PLANE_BYTES;
             const int ch = c * kch + cgrp * 4;
             float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
@@ -280,6 +426,9 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                         okmask |= 1u << j;
                     }
                 }
+                // the loads above are in flight while this thread waits for the MMAs that still read the stage
+                if (it >= 2) tc::mbar_wait(bars + 2 + s, ((it >> 1) - 1) & 1);
+                if (tid == 0) ENDO_TRACE(16 + c * 8 + 1);
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
                     const int px = (tid >> 2) + 128 * j;
@@ -291,11 +440,17 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                                 v.x = fmaxf(fmaf(k0.x, q[j].x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, q[j].y - k1.z, k1.y), 0.f);
                                 v.z = fmaxf(fmaf(k2.x, q[j].z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, q[j].w - k3.z, k3.y), 0.f);
                             }
-                            {                                            // exact split v = hi + lo (hi = v rounded to tf32)
-                                const float hx = tf32_hi(v.x), hy = tf32_hi(v.y), hz = tf32_hi(v.z), hw = tf32_hi(v.w);
-                                v = lo_part ? make_float4(v.x - hx, v.y - hy, v.z - hz, v.w - hw) : make_float4(hx, hy, hz, hw);
-                            }
+                            if (A.x3 == 0) v = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
                         }
+                        if (A.x3 == 2) {
+                            // bf16x3: this thread's 4 channels are 8 bytes of the 16-byte (8-channel) row of plane grp / 2 (first
+                            // terms) and of plane 2 + grp / 2 (second terms = bf16 of the exact remainders)
+                            float r0, r1, r2, r3;
+                            const uint32_t p0 = bf16_split(v.x, v.y, r0, r1), p1 = bf16_split(v.z, v.w, r2, r3);
+                            unsigned char* row = a_st0 + s * A_STAGE_BYTES + (grp >> 1) * PLANE_BYTES + (size_t)px * 16 + (grp & 1) * 8;
+                            *reinterpret_cast<uint2*>(row) = make_uint2(p0, p1);
+                            *reinterpret_cast<uint2*>(row + 2 * PLANE_BYTES) = make_uint2(bf16x2_rn(r0, r1), bf16x2_rn(r2, r3));
+                        } else
                         *reinterpret_cast<float4*>(a_s + (size_t)px * 16) = v;
                     }
                 }
@@ -391,9 +546,13 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 float right = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
                 if (lane == 0) left = (u > 0) ? edge[((u - 1) * 2 + 1) * 16 + j] : 0.f;
                 if (lane == 31) right = (u < NUNITS - 1) ? edge[((u + 1) * 2 + 0) * 16 + j] : 0.f;
-                o[j] = (left + __uint_as_float(v1[j])) + right + s_bias[j];
+                o[j] = (left + __uint_as_float(v1[j])) + right + (A.partial ? 0.f : s_bias[j]);
             }
-            if (ok) {
+            if (ok && A.partial) {
+                float* pp = A.partial + ((size_t)blockIdx.y * A.pixels + ((size_t)(b * A.H + y) * A.W + x)) * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(pp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            } else if (ok) {
                 float* op = A.out + ((size_t)(b * A.H + y) * A.W + x) * A.out_C + A.out_off;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
@@ -417,7 +576,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             if (lane == 0) { red[(warp * 16 + j) * 2] = a; red[(warp * 16 + j) * 2 + 1] = c2; }
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid < 2 * A.N) {
+        if (tid < 2 * A.N && !A.partial) {
             const int j = tid >> 1, which = tid & 1;
             double sum = 0.0;
 #pragma unroll
@@ -428,15 +587,17 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     } else if (lane == 0) {
         // ======================================================================== MMA issuer (one thread)
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NB);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c & 1;
+        for (int c = c_begin; c < c_end; ++c) {
+            const int it = c - c_begin;
+            const int s = it & 1;
             ENDO_TRACE(16 + c * 8 + 5);
-            tc::mbar_wait(bars + s, (c >> 1) & 1);
+            tc::mbar_wait(bars + s, (it >> 1) & 1);
             tc::tc_fence_after();
             ENDO_TRACE(16 + c * 8 + 6);
             const uint32_t a_base = tc::smem_u32(a_st0 + s * A_STAGE_BYTES);
             const uint32_t b_base = tc::smem_u32(b_st0 + s * B_STAGE_BYTES);
             const int nk8 = (A.x3 || A.K - c * KCH > 8) ? 2 : 1;   // skip an all-zero K half on the last chunk
+            const uint32_t idesc_b = tc::instr_desc(tc::FMT_BF16, 128, NB);
             // A tcgen05.mma that accumulates into the SAME TMEM tile as its predecessor waits ~266 cycles for it
             // (measured, tests/test_gpu_tc_probe.py::test_mma_cost_by_operand_layout), whatever its size.  Consecutive
             // MMAs therefore target different M-blocks: 9 independent accumulator chains keep the pipe busy.
@@ -452,13 +613,22 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint64_t alo = a_hi | (uint64_t)((a_base + 2u * PLANE_BYTES + row0) >> 4);
                     const uint64_t bhi = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + 0) * B_BLOCK_BYTES) >> 4);
                     const uint64_t blo = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + 1) * B_BLOCK_BYTES) >> 4);
-                    const uint32_t acc = (uint32_t)((c | ky) != 0);
+                    const uint32_t acc = (uint32_t)((it | ky) != 0);
+                    if (A.x3 == 2) {                                  // bf16x3: same planes / blocks, kind::f16, K = 16 per MMA
+#pragma unroll
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc_b, acc);
+#pragma unroll
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, ahi + (uint64_t)(mb * 128), blo, idesc_b, 1u);
+#pragma unroll
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc_b, 1u);
+                    } else {
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc, acc);
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), blo, idesc, 1u);
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
+                    }
                 }
             } else if (A.one) {
                 for (int k8 = 0; k8 < nk8; ++k8) {
@@ -466,7 +636,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)PITCH * 16u) >> 4);
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb)
-                        tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, (uint32_t)((c | k8) != 0));
+                        tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, (uint32_t)((it | k8) != 0));
                 }
             } else
 #pragma unroll 1
@@ -476,7 +646,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint64_t bd = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + k8) * B_BLOCK_BYTES) >> 4);
                     // address field counts 16-byte units = pixel rows: +128 per M-block
                     const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)(PITCH + (ky - 1) * PITCH) * 16u) >> 4);
-                    const uint32_t acc = (uint32_t)((c | ky | k8) != 0);
+                    const uint32_t acc = (uint32_t)((it | ky | k8) != 0);
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, acc);
                 }
@@ -560,6 +730,10 @@ dense_dgrad_tf32_kernel(const Args A) {
     const int b = blockIdx.z;
     const int g = b / (A.B / A.G);
     const int nchunks = (A.Cin + NC - 1) / NC;
+    // gridDim.y > 1 (low-resolution levels: fewer tiles than SMs): one 64-channel chunk per CTA -- the chunks write disjoint
+    // gradient channels, only the small output-gradient tile is staged once per chunk instead of once per tile
+    const int c_begin = gridDim.y > 1 ? (int)blockIdx.y : 0;
+    const int c_end = gridDim.y > 1 ? c_begin + 1 : nchunks;
 
     if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
@@ -625,7 +799,7 @@ dense_dgrad_tf32_kernel(const Args A) {
                 bs.x += __shfl_xor_sync(0xffffffffu, bs.x, o2); bs.y += __shfl_xor_sync(0xffffffffu, bs.y, o2);
                 bs.z += __shfl_xor_sync(0xffffffffu, bs.z, o2); bs.w += __shfl_xor_sync(0xffffffffu, bs.w, o2);
             }
-            if (A.db && lane < 4 && ch_ok) {
+            if (A.db && lane < 4 && ch_ok && blockIdx.y == 0) {
                 atomicAdd(A.db + ch, bs.x); atomicAdd(A.db + ch + 1, bs.y);
                 atomicAdd(A.db + ch + 2, bs.z); atomicAdd(A.db + ch + 3, bs.w);
             }
@@ -633,7 +807,7 @@ dense_dgrad_tf32_kernel(const Args A) {
         const int q = warp & 3, chalf = warp >> 2;            // TMEM lane quadrant, column half (32 columns)
         const int quad = lane & 15, psub = lane >> 4;         // phase-2 mapping: channel quad, pixel parity
         int unit = 0;
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             const int ci0 = c * NC;
             // ------------------------------------------------------------ weights + BN table of this ci chunk
             {   // 36,864-byte weight image of this chunk, copied verbatim (9 x 16 B per thread, all loads first)
@@ -753,8 +927,8 @@ dense_dgrad_tf32_kernel(const Args A) {
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NC);
         const uint32_t g_base = tc::smem_u32(g_s), w_base = tc::smem_u32(w_s);
         int unit = 0;
-        for (int c = 0; c < nchunks; ++c) {
-            tc::mbar_wait(bars + 0, c & 1);
+        for (int c = c_begin; c < c_end; ++c) {
+            tc::mbar_wait(bars + 0, (c - c_begin) & 1);
             tc::tc_fence_after();
             // groups of up to 4 M-blocks are issued interleaved (independent accumulators: a dependent MMA waits
             // ~266 cycles for its predecessor); the other 4 TMEM buffers belong to the group the epilogue is draining

@@ -147,7 +147,9 @@ int endo_scale_inv_bwd(const float* g_loss, const float* pred, const float* goal
  *       ENDO_MATH_TF32 = tcgen05 tensor-core tiles, tf32 operands (what cuDNN runs the reference's convolutions in
  *       by default), fp32 accumulation in TMEM; ENDO_MATH_TF32X3 = tcgen05 with error-compensated operands in the
  *       forward (x = hi + lo, three tf32 MMAs per product: fp32-grade depth maps and losses on the tensor cores);
- *       gradients as in ENDO_MATH_TF32 (tf32 data gradient, bf16 weight gradient, fp32 accumulation).
+ *       gradients as in ENDO_MATH_TF32 (tf32 data gradient, bf16 weight gradient, fp32 accumulation);
+ *       ENDO_MATH_BF16X3 = the same with two-term bf16 operands (x = b1 + b2, 16 significant bits, three kind::f16 MMAs
+ *       of K = 16 per product: half the MMA count of 3xTF32, depth maps within ~2e-5 of fp32).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
     int in_channels;
@@ -160,7 +162,7 @@ typedef struct {
     int n_classes;            /* only 1 is supported */
 } endo_net_config;
 
-enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2 /* reserved */, ENDO_MATH_TF32X3 = 3 };
+enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2 /* reserved */, ENDO_MATH_TF32X3 = 3, ENDO_MATH_BF16X3 = 4 };
 
 long long endo_net_param_count(const endo_net_config* cfg);
 long long endo_net_buffer_count(const endo_net_config* cfg); /* running_mean + running_var floats */

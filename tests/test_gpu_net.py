@@ -147,7 +147,7 @@ def test_growth16_variant_fcdensenet67():
     _check_grads(model, g64, g32, [k for k in state if not onet.is_buffer(k)])
 
 
-@pytest.mark.parametrize("math_mode", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("math_mode", ["fp32", "tf32x3", "bf16x3"])
 def test_full_train_step_vs_reference_fixture(math_mode):
     """Two optimisation steps (train.py:272-328) against the trace recorded from the unmodified reference: loss terms,
     gradient norm and updated weights -- the same bounds for the fp32 FFMA path and the tensor-core tf32x3 path."""
@@ -164,14 +164,17 @@ def test_full_train_step_vs_reference_fixture(math_mode):
         step = endo_b200.train_step.TrainStep(model, h, w, lr=1e-3, momentum=0.9, max_norm=10.0, pair=pair)
         for it in range(2):
             loss, dcl, sfl = step.step(cb)
-            tol = 2e-3 if it == 0 else 3e-2
+            # bf16x3 keeps 16 significant operand bits (depth maps ~2e-5 from fp32); the composite loss at random init
+            # amplifies depth errors ~250x (tests/test_oracle_golden.py), hence the wider first-step bound for that mode
+            tol = (1e-2 if math_mode == "bf16x3" else 2e-3) if it == 0 else 3e-2
             assert abs(float(loss) - g["loss"][it]) / g["loss"][it] < tol, (pair, it, float(loss), g["loss"][it])
             assert abs(float(dcl) - g["dcl"][it]) / g["dcl"][it] < tol
             assert abs(float(sfl) - g["sfl"][it]) / g["sfl"][it] < tol
             # the second step's gradient norm is one realisation of fp32 rounding: an A/B of two summation orders of
             # the SAME forward (test_splitk_forward_matches_single_pass: y equal to 1e-6) moves individual gradient
             # tensors by up to 5e-2 at this size, and the norm after one update by ~10%
-            assert abs(float(step.opt.grad_norm) - g["gnorm"][it]) / g["gnorm"][it] < (2e-2 if it == 0 else 0.25)
+            assert abs(float(step.opt.grad_norm) - g["gnorm"][it]) / g["gnorm"][it] < \
+                ((1e-1 if math_mode == "bf16x3" else 2e-2) if it == 0 else 0.25)
         names = [k for k in state if not onet.is_buffer(k)]
         params = dict(model.named_parameters())
         l2 = np.array([params[k].double().norm().item() for k in names])
@@ -241,14 +244,16 @@ def _grad_errors(model, g64, names):
     return np.array(out)
 
 
-def test_tf32x3_tensor_core_forward_is_fp32_grade():
-    """math="tf32x3": every convolution of the forward on tcgen05 with error-compensated operands (x = hi + lo,
+@pytest.mark.parametrize("math_mode", ["tf32x3", "bf16x3"])
+def test_tf32x3_tensor_core_forward_is_fp32_grade(math_mode):
+    """math="tf32x3" / "bf16x3": every convolution of the forward on tcgen05 with error-compensated operands (x = hi + lo,
     D += lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM).  The depth map, the BatchNorm buffers and the eval-mode
     output must meet the SAME 1e-4 / 1e-5 bounds as the fp32 FFMA path (north_star: depth maps within 1e-4 rel fp32);
-    the gradients come from the tf32 / bf16-operand tensor-core kernels and are held to the tensor-core bound."""
+    the gradients come from the tf32 / bf16-operand tensor-core kernels and are held to the tensor-core bound.
+    bf16x3 splits every operand into two bf16 terms (16 significant bits) instead of two tf32 terms (21 bits)."""
     cfg = onet.FCDENSENET57
     state, x, _ = _setup(cfg, lambda: endo_b200.models.FCDenseNet57(n_classes=1), 2, 128, 160, 303)
-    model = endo_b200.models.FCDenseNet57(n_classes=1, math="tf32x3")
+    model = endo_b200.models.FCDenseNet57(n_classes=1, math=math_mode)
     model.load_state_dict(state)
     model.cuda().train()
     gy = torch.randn(2, 1, 128, 160, generator=torch.Generator().manual_seed(9))
@@ -256,7 +261,7 @@ def test_tf32x3_tensor_core_forward_is_fp32_grade():
     y32, g32, _ = _oracle_fwd_bwd(state, x, cfg, gy, torch.float32)
     y = model(x.cuda())
     err, err32 = rel_err(y, y64), rel_err(y32, y64)
-    print(f"tf32x3 forward rel err vs fp64 oracle {err:.3e} (fp32 CPU oracle: {err32:.3e})")
+    print(f"{math_mode} forward rel err vs fp64 oracle {err:.3e} (fp32 CPU oracle: {err32:.3e})")
     assert err < 1e-4, err
     (y * gy.cuda()).sum().backward()
     sd = model.state_dict()
@@ -264,14 +269,14 @@ def test_tf32x3_tensor_core_forward_is_fp32_grade():
         if k.endswith("num_batches_tracked"):
             assert int(sd[k]) == int(v)
         else:
-            assert rel_err(sd[k], v) < 1e-5, k
+            assert rel_err(sd[k], v) < (1e-5 if math_mode == "tf32x3" else 5e-5), k
     names = [k for k in state if not onet.is_buffer(k)]
     errs = _grad_errors(model, g64, names)
     gmax = max(float(g64[k].abs().max()) for k in names)
     e32 = np.array([float((g32[k].double() - g64[k]).abs().max()) / max(float(g64[k].abs().max()), 1e-5 * gmax) for k in names])
-    print(f"tf32x3 gradient error vs fp64 oracle: median {np.median(errs):.2e} p90 {np.percentile(errs, 90):.2e} max {errs.max():.2e}; "
+    print(f"{math_mode} gradient error vs fp64 oracle: median {np.median(errs):.2e} p90 {np.percentile(errs, 90):.2e} max {errs.max():.2e}; "
           f"fp32 CPU oracle median {np.median(e32):.2e} p90 {np.percentile(e32, 90):.2e} max {e32.max():.2e}")
-    assert np.median(errs) < 5e-3 and errs.max() < 1e-1, (np.median(errs), errs.max())
+    assert np.median(errs) < (5e-3 if math_mode == "tf32x3" else 1.5e-2) and errs.max() < 2e-1, (np.median(errs), errs.max())
     model.eval()
     with torch.no_grad():
         y_eval = model(x.cuda())
@@ -280,27 +285,31 @@ def test_tf32x3_tensor_core_forward_is_fp32_grade():
     assert rel_err(y_eval, y_eval64) < 1e-4
 
 
-def test_tf32x3_reference_fixture_and_growth16():
-    """tf32x3 forward against the fixture generated from the unmodified reference, and the 16-channel-growth variant."""
+@pytest.mark.parametrize("math_mode", ["tf32x3", "bf16x3"])
+def test_tf32x3_reference_fixture_and_growth16(math_mode):
+    """Error-compensated tensor-core forward against the fixture generated from the unmodified reference, and the 16-channel-growth variant."""
     g = load_golden("net_a")
     b, h, w, seed = [int(v) for v in g["meta"]]
     cfg = onet.FCDENSENET57
     state, x, _ = _setup(cfg, lambda: endo_b200.models.FCDenseNet57(n_classes=1), b, h, w, seed)
-    model = endo_b200.models.FCDenseNet57(n_classes=1, math="tf32x3")
+    model = endo_b200.models.FCDenseNet57(n_classes=1, math=math_mode)
     model.load_state_dict(state)
     model.cuda().train()
     y = model(x.cuda())
+    print(f"{math_mode} forward vs reference fixture: {rel_err(y, g['y']):.3e}")
     assert rel_err(y, g["y"]) < 1e-4, rel_err(y, g["y"])
     for k in g:
         if k.startswith("buf::"):
-            assert rel_err(model.state_dict()[k[5:]], g[k]) < 1e-5, k
+            assert rel_err(model.state_dict()[k[5:]], g[k]) < (1e-5 if math_mode == "tf32x3" else 5e-5), k
     cfg = onet.FCDENSENET67
     state, x, _ = _setup(cfg, lambda: endo_b200.models.FCDenseNet67(n_classes=1), 2, 64, 64, 21)
-    model = endo_b200.models.FCDenseNet67(n_classes=1, math="tf32x3")
+    model = endo_b200.models.FCDenseNet67(n_classes=1, math=math_mode)
     model.load_state_dict(state)
     model.cuda().train()
     y64 = onet.forward({k: (v if v.dtype == torch.long else v.double()) for k, v in state.items()}, x.double(), cfg, True, {})
-    assert rel_err(model(x.cuda()), y64) < 1e-4
+    e67 = rel_err(model(x.cuda()), y64)
+    print(f"{math_mode} FCDenseNet67 forward vs fp64 oracle: {e67:.3e}")
+    assert e67 < 1e-4
 
 
 def test_tensor_core_backward_kernels_match_ffma_backward(monkeypatch):
@@ -321,11 +330,13 @@ def test_tensor_core_backward_kernels_match_ffma_backward(monkeypatch):
         torch.cuda.synchronize()
         return {k: p.grad.clone() for k, p in model.named_parameters()}, y.detach().clone()
 
-    # bits: 2 = dense dgrad, 4 = dense wgrad, 16 = TransitionUp wgrad, 32 = TransitionDown wgrad fall back to FFMA
-    # (1 / 8 would change the forward)
-    ref, y_ref = grads(54)
+    # bits: 2 = dense dgrad, 4 = dense wgrad, 16 = TransitionUp wgrad, 32 = TransitionDown wgrad, 1024 = TransitionDown
+    # dgrad fall back to FFMA (1 / 8 / 64 / 512 would change the forward)
+    full = 2 + 4 + 16 + 32 + 1024
+    ref, y_ref = grads(full)
     gmax = max(float(v.abs().max()) for v in ref.values())
-    for mask, what in ((52, "dense dgrad"), (50, "dense wgrad"), (38, "TransitionUp wgrad"), (22, "TransitionDown wgrad"), (0, "all")):
+    for mask, what in ((full - 2, "dense dgrad"), (full - 4, "dense wgrad"), (full - 16, "TransitionUp wgrad"),
+                       (full - 32, "TransitionDown wgrad"), (full - 1024, "TransitionDown dgrad"), (0, "all")):
         got, y = grads(mask)
         assert rel_err(y, y_ref) < 1e-6
         errs = []

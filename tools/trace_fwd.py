@@ -1,12 +1,12 @@
 """Per-phase clock64() trace of CTA 0 of ONE tensor-core DenseLayer forward launch (development aid).
-   ENDO_TC_DEBUG=4 python tools/trace_fwd.py [level]"""
+   ENDO_TC_DEBUG=4 python tools/trace_fwd.py [tf32|tf32x3]"""
 import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["ENDO_TC_DEBUG"] = os.environ.get("ENDO_TC_DEBUG", "4")
 import endo_b200
 from endo_b200 import _lib
-model = endo_b200.models.FCDenseNet57(1, math="tf32")
+model = endo_b200.models.FCDenseNet57(1, math=(sys.argv[1] if len(sys.argv) > 1 else "tf32"))
 endo_b200.engine.kaiming_init_(model, seed=1)
 model.cuda().train()
 x = torch.rand(16, 3, 256, 320, device="cuda") * 2 - 1
