@@ -339,7 +339,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     a.stats = c.BNRED(); a.stats_C = P.maxC;
     a.x = c.X(l); a.ep_coef = c.COEF(d.bn);
     if (tc_d) {
-        tcdgrad::Args t;
+        tcdgrad::Args t{};
         t.g = c.GX(l); t.x = c.X(l); t.ab = c.AB(l); t.coef = c.COEF(d.bn); t.w = c.params + d.conv.w;
         t.gout = c.GX(l); t.db = c.gparams + d.conv.b; t.red = c.BNRED(); t.red_C = P.maxC;
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
@@ -615,6 +615,43 @@ static int trans_up_bwd(const Ctx& c, int i) {
         }
     } else {
         ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.s)));
+    }
+    const long long tmp_need = 4ll * P.B * P.h[l] * P.w[l] * t.cin;
+    if (is_tc(c.math) && !(tc_disable_mask() & 2048) && t.cin <= tcdgrad::NC && (t.cin & 3) == 0 && tmp_need <= P.tdtmp_bytes) {
+        // tcgen05 (tf32): the DenseLayer data-gradient kernel in plain mode, 16 output-gradient channels per pass, raw result
+        // into the (now idle) forward scratch tensor at full resolution; then the 2x2 fold into the half-resolution buffer
+        float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
+        static bool configured = false;
+        if (!configured) {
+            ENDO_CUDA(cudaFuncSetAttribute(tcdgrad::dense_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           tcdgrad::SMEM_BYTES));
+            configured = true;
+        }
+        for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
+            tcdgrad::Args q{};
+            q.g = c.GX(l); q.x = c.X(l); q.ab = c.AB(l); q.coef = nullptr; q.w = c.params + t.conv.w + (size_t)co0 * t.cin * 9;
+            q.gout = nullptr; q.db = nullptr; q.red = nullptr; q.red_C = 0;
+            q.C = P.Ctot[l]; q.out_off = co0; q.Cout = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16; q.in_off = 0; q.Cin = t.cin;
+            q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
+            q.plain = 1; q.first = co0 == 0; q.oC = t.cin; q.o_off = 0; q.po = tmp;
+            q.wpack = c.WPACK_BWD();
+            {
+                ProfScope prof(PC_BN, c.s);
+                tcconv::pack_w_dgrad_kernel<<<cdiv(q.Cin, 64), 256, 0, c.s>>>(q.w, q.Cin, q.Cout, c.WPACK_BWD());
+                ENDO_CHECK_LAUNCH();
+            }
+            dim3 grid(cdiv(q.W, tcconv::TW) * cdiv(q.H, tcconv::TH), 1, q.B);
+            ProfScope prof(PC_DGRAD_TRANS, c.s);
+            tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(q);
+            ENDO_CHECK_LAUNCH();
+        }
+        const long long items = (long long)P.B * P.h[ls] * P.w[ls] * (t.cin / 4);
+        int blocks = (int)((items + 255) / 256);
+        if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+        ProfScope prof(PC_DGRAD_TRANS, c.s);
+        tcdgrad::up_sum_kernel<<<blocks, 256, 0, c.s>>>(tmp, t.cin, c.GX(ls), P.Ctot[ls], t.src_off, P.B, P.h[ls], P.w[ls], t.cin);
+        ENDO_CHECK_LAUNCH();
+        return ENDO_OK;
     }
     ConvArgs a = base_args(c);
     a.in = c.GX(l); a.in2 = c.X(l); a.in_ab = c.AB(l); a.in_C = P.Ctot[l]; a.in_off = 0; a.K = t.conv.cout;

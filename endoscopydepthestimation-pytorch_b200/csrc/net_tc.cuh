@@ -710,6 +710,11 @@ struct Args {
     float* db;                                            // conv bias gradient [Cout] (sum of the output gradient), accumulated
     double* red; int red_C;                               // [G][red_C][2] BN backward sums
     int C, out_off, Cout, in_off, Cin, H, W, B, G;
+    // plain mode (TransitionUp, models.py:70-80: the convolution input is the upsampled map, no BatchNorm / ReLU in front):
+    // the epilogue stores (first = 1) or accumulates the raw data gradient into a scratch tensor [B,H,W,oC] at channel
+    // o_off; up_sum_kernel then folds the 2x2 blocks into the half-resolution gradient buffer
+    int plain, first, oC, o_off;
+    float* po;
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -821,7 +826,7 @@ dense_dgrad_tf32_kernel(const Args A) {
             if (tid < NC) {
                 const int ci = ci0 + tid;
                 float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ci < A.Cin) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)g * A.Cin + ci) * 4));
+                if (ci < A.Cin && !A.plain) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)g * A.Cin + ci) * 4));
                 *reinterpret_cast<float4*>(ctab + tid * 4) = e;
             }
             tc::fence_proxy_async();
@@ -870,12 +875,27 @@ dense_dgrad_tf32_kernel(const Args A) {
                         const int y = y0 + r - 1, x = x0 + cc - 1;
                         off[it] = 0;
                         if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
-                            off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
-                            xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
-                            gv[it] = *reinterpret_cast<const float4*>(A.gout + off[it]);
+                            if (A.plain) {
+                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.oC + A.o_off + ci0 + quad * 4;
+                                gv[it] = A.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(A.po + off[it]);
+                            } else {
+                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
+                                xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
+                                gv[it] = *reinterpret_cast<const float4*>(A.gout + off[it]);
+                            }
                             okmask |= 1u << it;
                         }
                     }
+                    if (A.plain) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            if (okmask & (1u << it)) {
+                                const int p = warp * 16 + it * 2 + psub;
+                                const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
+                                *reinterpret_cast<float4*>(A.po + off[it]) = make_float4(gv[it].x + d.x, gv[it].y + d.y, gv[it].z + d.z, gv[it].w + d.w);
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         if (okmask & (1u << it)) {
@@ -913,7 +933,7 @@ dense_dgrad_tf32_kernel(const Args A) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < 2 * NC) {
                 const int j = tid >> 1, which = tid & 1;
-                if (ci0 + j < A.Cin) {
+                if (ci0 + j < A.Cin && !A.plain) {
                     double sum = 0.0;
 #pragma unroll
                     for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * NC + j) * 2 + which];
@@ -964,6 +984,28 @@ dense_dgrad_tf32_kernel(const Args A) {
     if (warp == 8) {
         __syncwarp();
         tc::tmem_dealloc(tmem, 512);
+    }
+}
+
+// low[p2][c] += sum over the 2x2 block of hi[p][c]  (backward of nearest-neighbour upsampling, models.py:73); thread =
+// (coarse pixel, channel quad)
+__global__ void __launch_bounds__(256)
+up_sum_kernel(const float* __restrict__ hi, int hiC, float* __restrict__ low, int lowC, int low_off, int B, int h2, int w2, int C) {
+    const int nq = C >> 2;
+    const long long total = (long long)B * h2 * w2 * nq;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int q = (int)(i % nq);
+        const long long pp = i / nq;
+        const int x2 = (int)(pp % w2), y2 = (int)((pp / w2) % h2), b = (int)(pp / ((long long)w2 * h2));
+        const float* p00 = hi + (((size_t)b * 2 * h2 + 2 * y2) * 2 * w2 + 2 * x2) * hiC + q * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p00)), b4 = __ldg(reinterpret_cast<const float4*>(p00 + hiC));
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p00 + (size_t)2 * w2 * hiC));
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(p00 + (size_t)2 * w2 * hiC + hiC));
+        float4* o = reinterpret_cast<float4*>(low + (size_t)pp * lowC + low_off + q * 4);
+        float4 v = *o;
+        v.x += (a.x + b4.x) + (c4.x + d4.x); v.y += (a.y + b4.y) + (c4.y + d4.y);
+        v.z += (a.z + b4.z) + (c4.z + d4.z); v.w += (a.w + b4.w) + (c4.w + d4.w);
+        *o = v;
     }
 }
 

@@ -331,12 +331,12 @@ def test_tensor_core_backward_kernels_match_ffma_backward(monkeypatch):
         return {k: p.grad.clone() for k, p in model.named_parameters()}, y.detach().clone()
 
     # bits: 2 = dense dgrad, 4 = dense wgrad, 16 = TransitionUp wgrad, 32 = TransitionDown wgrad, 1024 = TransitionDown
-    # dgrad fall back to FFMA (1 / 8 / 64 / 512 would change the forward)
-    full = 2 + 4 + 16 + 32 + 1024
+    # dgrad, 2048 = TransitionUp dgrad fall back to FFMA (1 / 8 / 64 / 512 would change the forward)
+    full = 2 + 4 + 16 + 32 + 1024 + 2048
     ref, y_ref = grads(full)
     gmax = max(float(v.abs().max()) for v in ref.values())
     for mask, what in ((full - 2, "dense dgrad"), (full - 4, "dense wgrad"), (full - 16, "TransitionUp wgrad"),
-                       (full - 32, "TransitionDown wgrad"), (full - 1024, "TransitionDown dgrad"), (0, "all")):
+                       (full - 32, "TransitionDown wgrad"), (full - 1024, "TransitionDown dgrad"), (full - 2048, "TransitionUp dgrad"), (0, "all")):
         got, y = grads(mask)
         assert rel_err(y, y_ref) < 1e-6
         errs = []
