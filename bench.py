@@ -194,8 +194,9 @@ def pick_cpu_threads(h, w):
 
 def warp_layer_bench(dev, peaks, sizes=(("C2", 8, 256, 320), ("C5", 16, 512, 640)), iters=10):
     """DepthWarpingLayer forward / backward alone (BASELINE.json: 'warp-layer HBM GB/s'): algorithmic bytes
-    (fwd 20*P, bwd 24*P) over the CUDA-event duration of the library call, with a 512 MB write
-    between iterations so the inputs come from HBM, not from the 126 MB L2."""
+    (fwd 20*P, bwd 24*P) over the CUDA-event duration of the library call, with a 512 MB write followed by
+    a 512 MB read between iterations so the inputs come from HBM, not from the 126 MB L2 (the read pass leaves the L2 full
+    of CLEAN lines: after a bare write the timed kernel would also pay for the write-back of the flush buffer)."""
     import endo_b200
     from endo_b200 import _lib
     out = {}
@@ -215,13 +216,13 @@ def warp_layer_bench(dev, peaks, sizes=(("C2", 8, 256, 320), ("C5", 16, 512, 640
         for phase in ("fwd", "bwd"):
             total = 0.0
             for _ in range(iters):
-                flush.zero_()
+                flush.zero_(); flush.sum()
                 if phase == "fwd":
                     with _lib.profile() as prof:
                         wd, _ = layer([x1, x2] + args)
                 else:
                     wd, _ = layer([x1, x2] + args)
-                    flush.zero_()
+                    flush.zero_(); flush.sum()
                     with _lib.profile() as prof:
                         torch.autograd.grad(wd, [x1, x2], gw)
                 total += prof.ms["depth_warp"]

@@ -82,7 +82,7 @@ __host__ inline size_t smem_bytes(int Npad, int K, int mode) {
     return s;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 pw_gemm_kernel(const Args A) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int bstage = b_stage_bytes(A.Npad);
@@ -193,15 +193,15 @@ pw_gemm_kernel(const Args A) {
                 const int c = c0 + u;
                 if (c < nchunks) {
                     const int s = c % NST;
-                    // weights of this chunk (L2-resident image): loads first, the stage wait hides their latency
-                    float4 wq[8];
-                    const float4* wsrc = reinterpret_cast<const float4*>(A.wpack) + (size_t)c * nb4;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = tid + 256 * j;
-                        wq[j] = (i < nb4) ? __ldg(wsrc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
                     if (c >= NST) tc::mbar_wait(bars + NST + s, ((c / NST) - 1) & 1);
+                    // weights of this chunk (L2-resident image): cp.async straight into the stage (no registers), in flight
+                    // while the activations are transformed and stored
+                    {
+                        const float4* wsrc = reinterpret_cast<const float4*>(A.wpack) + (size_t)c * nb4;
+                        unsigned char* b_s = b_st + s * bstage;
+                        for (int i = tid; i < nb4; i += 256) tc::cp_async16(b_s + (size_t)i * 16, wsrc + i, 16u);
+                        tc::cp_async_commit();
+                    }
                     unsigned char* a_s = a_st + s * A_STAGE;
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
@@ -234,12 +234,7 @@ pw_gemm_kernel(const Args A) {
                     }
                     // refill the ring slot just consumed
                     if (A.mode == 0) issue(c + NPF, u); else issue(c + 2, u);
-                    unsigned char* b_s = b_st + s * bstage;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int i = tid + 256 * j;
-                        if (i < nb4) *reinterpret_cast<float4*>(b_s + (size_t)i * 16) = wq[j];
-                    }
+                    tc::cp_async_wait<0>();
                     tc::fence_proxy_async();
                     tc::mbar_arrive(bars + s);
                 }
