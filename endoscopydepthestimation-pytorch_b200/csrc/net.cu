@@ -781,7 +781,13 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         w.g_in = c.GX(0); w.g_x = c.X(0); w.g_ab = c.AB(0); w.g_C = P.Ctot[0]; w.g_off = P.offIn[0]; w.g_K = P.first.cout;
         w.g_h = H; w.g_w = W; w.oh = H; w.ow = W; w.B = B; w.G = P.G;
         w.dw = g_params + P.first.w; w.db = g_params + P.first.b; w.w_cin = cfg->in_channels;
-        ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.s)));
+        if (cfg->in_channels == 3 && P.first.cout == 48 && !(tc_disable_mask() & 4096)) {
+            ProfScope prof(PC_WGRAD_TRANS, c.s);
+            first_wgrad_kernel<<<4 * kNumSMs, FW_THREADS, 0, c.s>>>(w);
+            ENDO_CHECK_LAUNCH();
+        } else {
+            ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.s)));
+        }
     }
     return ENDO_OK;
 }

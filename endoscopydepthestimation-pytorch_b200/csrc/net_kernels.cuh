@@ -968,6 +968,91 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// firstconv weight / bias gradient (models.py:111-113: conv3x3 3 -> 48 on the NCHW input images):
+//   dW[co][ci][ky][kx] = sum_p G[p][co] * img[ci][p + (ky-1, kx-1)],   db[co] = sum_p G[p][co],   G = g + A_c + B_c x (lazy BN term)
+// 1,296 outputs against 48 gradient channels per pixel: the generic kernel (32-channel input chunks, one of 3 used) spent
+// 1.3 ms here.  A block stages a 4x32 gradient tile (24 KB) and the 3 x 6 x 34 image patch; thread = (pixel stream, 4
+// output channels, 7 taps) keeps 28 accumulators in registers: one 16-byte + seven 4-byte shared loads per 28 FMAs.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FW_STREAMS = 5, FW_THREADS = FW_STREAMS * 48, FW_ROWS = 4, FW_PX = FW_ROWS * 32, FW_PR = FW_ROWS + 2;
+__global__ void __launch_bounds__(FW_THREADS)
+first_wgrad_kernel(const WgradArgs A) {
+    __shared__ __align__(16) float g_s[FW_PX * 48];
+    __shared__ float in_s[3 * FW_PR * 34];
+    const int tid = threadIdx.x;
+    const int stream = tid / 48, o = tid - stream * 48;
+    const int cq = o % 12, tg = o / 12;                  // output-channel quad, tap group (taps 7 tg .. 7 tg + 6 of 27)
+    int tap_off[7];                                      // offset of tap k inside the patch, relative to the pixel's (row, col)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const int k = tg * 7 + j, kk = k < 27 ? k : 26;
+        const int ci = kk / 9, ky = (kk % 9) / 3, kx = kk % 3;
+        tap_off[j] = (ci * FW_PR + ky) * 34 + kx;
+    }
+    float acc[4][7], bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc[e][j] = 0.f;
+    const int tiles_x = (A.ow + 31) / 32, tiles_y = (A.oh + FW_ROWS - 1) / FW_ROWS;
+    const int n_tiles = A.B * tiles_x * tiles_y;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int b = t / (tiles_x * tiles_y), rem = t - b * (tiles_x * tiles_y);
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const int y0 = ty * FW_ROWS, x0 = tx * 32;
+        const int g = b / (A.B / A.G);
+        __syncthreads();                                 // previous tile fully consumed
+        // gradient tile [256 px][48] with the lazy BN correction
+        for (int i = tid; i < FW_PX * 12; i += FW_THREADS) {
+            const int px = i / 12, q = i - px * 12;
+            const int y = y0 + (px >> 5), x = x0 + (px & 31);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y < A.oh && x < A.ow) {
+                const size_t off = ((size_t)(b * A.oh + y) * A.ow + x) * A.g_C + A.g_off + q * 4;
+                const float4 gq = ldg4(A.g_in + off), xq = ldg4(A.g_x + off);
+                const float* abp = A.g_ab + ((size_t)g * A.g_C + A.g_off + q * 4) * 2;
+                const float4 c0 = ldg4(abp), c1 = ldg4(abp + 4);
+                v.x = gq.x + fmaf(c0.y, xq.x, c0.x); v.y = gq.y + fmaf(c0.w, xq.y, c0.z);
+                v.z = gq.z + fmaf(c1.y, xq.z, c1.x); v.w = gq.w + fmaf(c1.w, xq.w, c1.z);
+            }
+            *reinterpret_cast<float4*>(g_s + px * 48 + q * 4) = v;
+        }
+        // image patch (NCHW, zero padding)
+        for (int i = tid; i < 3 * FW_PR * 34; i += FW_THREADS) {
+            const int ci = i / (FW_PR * 34), r = (i - ci * (FW_PR * 34)) / 34, cc = i - ci * (FW_PR * 34) - r * 34;
+            const int y = y0 + r - 1, x = x0 + cc - 1;
+            float v = 0.f;
+            if (y >= 0 && y < A.a_h && x >= 0 && x < A.a_w) v = __ldg(A.a_in + ((size_t)(b * 3 + ci) * A.a_h + y) * A.a_w + x);
+            in_s[i] = v;
+        }
+        __syncthreads();
+        for (int px = stream; px < FW_PX; px += FW_STREAMS) {
+            const float4 g4 = *reinterpret_cast<const float4*>(g_s + px * 48 + cq * 4);
+            const float* ip = in_s + (px >> 5) * 34 + (px & 31);
+            if (tg == 0) { bsum[0] += g4.x; bsum[1] += g4.y; bsum[2] += g4.z; bsum[3] += g4.w; }
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const float v = ip[tap_off[j]];
+                acc[0][j] = fmaf(g4.x, v, acc[0][j]); acc[1][j] = fmaf(g4.y, v, acc[1][j]);
+                acc[2][j] = fmaf(g4.z, v, acc[2][j]); acc[3][j] = fmaf(g4.w, v, acc[3][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const int k = tg * 7 + j;
+        if (k < 27) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) atomicAdd(A.dw + (size_t)(cq * 4 + e) * 27 + k, acc[e][j]);
+        }
+    }
+    if (tg == 0 && A.db) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(A.db + cq * 4 + e, bsum[e]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Conv bias gradient alone: db[co] = sum_p (g + A + B x)[p][co].  Only used when the weight gradient runs on the
 // tensor cores but the data gradient does not (debug A/B combinations); normally the dgrad kernel produces it.
 // ---------------------------------------------------------------------------------------------------

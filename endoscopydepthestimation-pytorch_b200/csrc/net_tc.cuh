@@ -1037,9 +1037,13 @@ constexpr int MCH = 64;                                  // input channels per C
 constexpr int A_STAGE = (MCH / 8) * PLANE_BYTES;         // 44,160
 constexpr int G_STAGE = 6 * PLANE_BYTES;                 // 33,120   planes [kx][co half], one margin row in front
 constexpr int STAGE = A_STAGE + G_STAGE;                 // 77,280
-constexpr int SMEM_BYTES = 2 * STAGE + 8 * PLANE_BYTES + 256;   // tail pad: the M = 128 read of stage 1 stays inside the allocation
+constexpr int KTAB_BYTES = 2 * 8 * 144;                  // BatchNorm coefficients of this CTA's 64 channels, both statistic groups:
+                                                         // [g][8-channel group][8 x float4 + 16 B pad] (144 B rows: the 8 groups a warp reads hit distinct banks)
+constexpr int SMEM_BYTES = 2 * STAGE + 8 * PLANE_BYTES + KTAB_BYTES + 256;   // tail pad: the M = 128 read of stage 1 stays inside the allocation
 constexpr int NB = 48;
-constexpr int NTHREADS = 288;
+constexpr int NPROD = 512;                               // 16 producer warps: the staging is ALU work (BN + ReLU + bf16 packing, ~3000
+                                                         // instructions per thread and tile with 8 warps = 2 warps per scheduler: dependent-issue bound, ncu)
+constexpr int NTHREADS = NPROD + 32;
 
 struct Args {
     const float* x; const float* coef;                   // activations + this BN's (a, beta, mean, invstd) [G][Cin][4]
@@ -1063,7 +1067,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __global__ void __launch_bounds__(NTHREADS, 1)
 dense_wgrad_bf16_kernel(const Args A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE + 8 * PLANE_BYTES);   // full[2], empty[2], accum
+    float* ktab = reinterpret_cast<float*>(smem + 2 * STAGE + 8 * PLANE_BYTES);         // [G <= 2][MCH][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE + 8 * PLANE_BYTES + KTAB_BYTES);   // full[2], empty[2], accum
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1073,9 +1078,15 @@ dense_wgrad_bf16_kernel(const Args A) {
     const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
     const int ntiles = t_end - t_begin;
 
-    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
+    if (tid < 2 * MCH) {                                     // coefficient table (zeros for TransitionUp: no BatchNorm in front)
+        const int gi = tid / MCH, cl = tid % MCH, ch = ci0 + cl;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gi < A.G && ch < A.Cin && !A.up) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)gi * A.Cin + ch) * 4));
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ktab) + (gi * 8 + (cl >> 3)) * 144 + (cl & 7) * 16) = e;
+    }
     if (tid == 0) {
-        tc::mbar_init(bars + 0, 256); tc::mbar_init(bars + 1, 256);
+        tc::mbar_init(bars + 0, NPROD); tc::mbar_init(bars + 1, NPROD);
         tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
         tc::mbar_init(bars + 4, 1);
         tc::fence_mbar_init();
@@ -1085,7 +1096,7 @@ dense_wgrad_bf16_kernel(const Args A) {
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < 16) {
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1;
             if (it >= 2) tc::mbar_wait(bars + 2 + s, ((it >> 1) - 1) & 1);
@@ -1103,28 +1114,19 @@ dense_wgrad_bf16_kernel(const Args A) {
                 const int ch = ci0 + grp * 8;
                 const bool ch_ok = ch < A.Cin;                       // Cin is a multiple of 4: a group may be half valid
                 const bool hi_ok = ch + 4 < A.Cin;
-                float4 k[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) k[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ch_ok && !A.up) {
-                    const float* cf = A.coef + ((size_t)g * A.Cin + ch) * 4;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
-                    if (hi_ok) {
-#pragma unroll
-                        for (int e = 4; e < 8; ++e) k[e] = __ldg(reinterpret_cast<const float4*>(cf + e * 4));
-                    }
-                }
+                // (a, beta, mean, invstd) of this thread's 8 channels: registers for the whole tile
+                const float4* kt = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ktab) + (g * 8 + grp) * 144);
+                const float4 k0 = kt[0], k1 = kt[1], k2 = kt[2], k3 = kt[3], k4 = kt[4], k5 = kt[5], k6 = kt[6], k7 = kt[7];
                 const int sh = A.up ? 1 : 0;
                 const int sW = A.W >> sh;
                 const float* xa_b = A.xa + (size_t)b * (A.H >> sh) * sW * A.xa_C + A.in_off + ch;
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {               // 11 pixels per thread: batches of 6 and 5, loads first
-                    float4 q0[6], q1[6];
+                for (int part = 0; part < 2; ++part) {               // 6 pixels per thread: two batches of 3, loads first
+                    float4 q0[3], q1[3];
                     unsigned okmask = 0u;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const int px = (tid >> 3) + 32 * (part * 6 + j);
+                    for (int j = 0; j < 3; ++j) {
+                        const int px = (tid >> 3) + 64 * (part * 3 + j);
                         const int r = px / PITCH, cc = px - r * PITCH;
                         const int y = y0 + r - 1, x = x0 + cc - 1;
                         q0[j] = make_float4(0.f, 0.f, 0.f, 0.f); q1[j] = q0[j];
@@ -1136,20 +1138,20 @@ dense_wgrad_bf16_kernel(const Args A) {
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const int px = (tid >> 3) + 32 * (part * 6 + j);
+                    for (int j = 0; j < 3; ++j) {
+                        const int px = (tid >> 3) + 64 * (part * 3 + j);
                         if (px < A_ROWS) {
                             uint4 o = make_uint4(0u, 0u, 0u, 0u);
                             if (okmask & (1u << j)) {
                                 const float4 a0 = q0[j], a1 = q1[j];
                                 float v0 = a0.x, v1 = a0.y, v2 = a0.z, v3 = a0.w, v4 = a1.x, v5 = a1.y, v6 = a1.z, v7 = a1.w;
                                 if (!A.up) {
-                                    v0 = fmaxf(fmaf(k[0].x, a0.x - k[0].z, k[0].y), 0.f); v1 = fmaxf(fmaf(k[1].x, a0.y - k[1].z, k[1].y), 0.f);
-                                    v2 = fmaxf(fmaf(k[2].x, a0.z - k[2].z, k[2].y), 0.f); v3 = fmaxf(fmaf(k[3].x, a0.w - k[3].z, k[3].y), 0.f);
+                                    v0 = fmaxf(fmaf(k0.x, a0.x - k0.z, k0.y), 0.f); v1 = fmaxf(fmaf(k1.x, a0.y - k1.z, k1.y), 0.f);
+                                    v2 = fmaxf(fmaf(k2.x, a0.z - k2.z, k2.y), 0.f); v3 = fmaxf(fmaf(k3.x, a0.w - k3.z, k3.y), 0.f);
                                     v4 = v5 = v6 = v7 = 0.f;
                                     if (hi_ok) {
-                                        v4 = fmaxf(fmaf(k[4].x, a1.x - k[4].z, k[4].y), 0.f); v5 = fmaxf(fmaf(k[5].x, a1.y - k[5].z, k[5].y), 0.f);
-                                        v6 = fmaxf(fmaf(k[6].x, a1.z - k[6].z, k[6].y), 0.f); v7 = fmaxf(fmaf(k[7].x, a1.w - k[7].z, k[7].y), 0.f);
+                                        v4 = fmaxf(fmaf(k4.x, a1.x - k4.z, k4.y), 0.f); v5 = fmaxf(fmaf(k5.x, a1.y - k5.z, k5.y), 0.f);
+                                        v6 = fmaxf(fmaf(k6.x, a1.z - k6.z, k6.y), 0.f); v7 = fmaxf(fmaf(k7.x, a1.w - k7.z, k7.y), 0.f);
                                     }
                                 }
                                 o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
@@ -1160,18 +1162,19 @@ dense_wgrad_bf16_kernel(const Args A) {
                 }
             }
             // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile
-            //      interior.  One thread per interior pixel: all of its loads are issued before any use, then the 16
-            //      corrected channels are written into the three kx-shifted planes.
+            //      interior.  Two threads per interior pixel (one per 8-channel half): all loads are issued before any use,
+            //      then the corrected channels are written into the three kx-shifted planes.
+            const int gpix = tid & 255, half = tid >> 8;
             if (A.one) {
-                // one thread per pixel of the 8x32 tile; 48 channels in three rounds of 16 (argmax word + g + x loads first)
-                const int r = 1 + (tid >> 5), cc = 1 + (tid & 31);
+                // 1x1 mode: 48 channels in three rounds of 16 (argmax word + g + x loads first)
+                const int r = 1 + (gpix >> 5), cc = 1 + (gpix & 31);
                 const int y = y0 + r - 1, x = x0 + cc - 1;
                 const bool ok = (y < A.H) && (x < A.W);
                 const unsigned pos = (unsigned)(((y & 1) << 1) | (x & 1));
                 const size_t pp = ok ? ((size_t)(b * A.cH + (y >> 1)) * A.cW + (x >> 1)) : 0;
                 const int q = r * PITCH + cc;
                 // halo rows / columns of the six planes must read as zero: clear the few rows the interior never writes
-                for (int i = tid; i < 6 * (A_ROWS + 2); i += 256) {
+                for (int i = tid; i < 6 * (A_ROWS + 2); i += NPROD) {
                     const int pl = i % 6, row = i / 6, src = row - 1;
                     const int rr = src / PITCH, c2 = src - rr * PITCH;
                     if (src < 0 || src >= A_ROWS || rr < 1 || rr > TR || c2 < 1 || c2 > TW)
@@ -1179,11 +1182,11 @@ dense_wgrad_bf16_kernel(const Args A) {
                 }
 #pragma unroll 1
                 for (int sub = 0; sub < 3; ++sub) {
-                    const int cbase = A.out_off + sub * 16;                 // channel inside the conv's output
-                    unsigned am[4];
-                    float4 gq[4], xq[4];
+                    const int cbase = A.out_off + sub * 16 + half * 8;      // channel inside the conv's output
+                    unsigned am[2];
+                    float4 gq[2], xq[2];
 #pragma unroll
-                    for (int h4 = 0; h4 < 4; ++h4) {
+                    for (int h4 = 0; h4 < 2; ++h4) {
                         am[h4] = 0xffffffffu; gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4];
                         if (ok && cbase + h4 * 4 < A.Cout) {
                             am[h4] = __ldg(reinterpret_cast<const unsigned*>(A.argmax + pp * A.Cout + cbase + h4 * 4));
@@ -1191,9 +1194,9 @@ dense_wgrad_bf16_kernel(const Args A) {
                             xq[h4] = __ldg(reinterpret_cast<const float4*>(A.xc + pp * A.cC + A.c_off + cbase + h4 * 4));
                         }
                     }
-                    float v[16];
+                    float v[8];
 #pragma unroll
-                    for (int h4 = 0; h4 < 4; ++h4) {
+                    for (int h4 = 0; h4 < 2; ++h4) {
                         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
                         if (cbase + h4 * 4 < A.Cout) {
                             const float* abp = A.abc + ((size_t)g * A.cC + A.c_off + cbase + h4 * 4) * 2;
@@ -1204,36 +1207,34 @@ dense_wgrad_bf16_kernel(const Args A) {
                         v[h4 * 4 + 2] = (((am[h4] >> 16) & 0xffu) == pos) ? gq[h4].z + fmaf(c1.y, xq[h4].z, c1.x) : 0.f;
                         v[h4 * 4 + 3] = ((am[h4] >> 24) == pos) ? gq[h4].w + fmaf(c1.w, xq[h4].w, c1.z) : 0.f;
                     }
-                    const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-                    *reinterpret_cast<uint4*>(g_s + (sub * 2 + 0) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? lo : make_uint4(0u, 0u, 0u, 0u);
-                    *reinterpret_cast<uint4*>(g_s + (sub * 2 + 1) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? hi : make_uint4(0u, 0u, 0u, 0u);
+                    const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                    *reinterpret_cast<uint4*>(g_s + (sub * 2 + half) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? o : make_uint4(0u, 0u, 0u, 0u);
                 }
             } else
             {
                 uint4* gz = reinterpret_cast<uint4*>(g_s);
-                for (int i = tid; i < G_STAGE / 16; i += 256) gz[i] = make_uint4(0u, 0u, 0u, 0u);
-                const int r = 1 + (tid >> 5), cc = 1 + (tid & 31);
+                for (int i = tid; i < G_STAGE / 16; i += NPROD) gz[i] = make_uint4(0u, 0u, 0u, 0u);
+                const int r = 1 + (gpix >> 5), cc = 1 + (gpix & 31);
                 const int y = y0 + r - 1, x = x0 + cc - 1;
                 const bool ok = (y < A.H) && (x < A.W);
-                float4 gq[4], xq[4];
+                float4 gq[2], xq[2];
 #pragma unroll
-                for (int h4 = 0; h4 < 4; ++h4) { gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4]; }
-                const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off;
+                for (int h4 = 0; h4 < 2; ++h4) { gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4]; }
+                const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + half * 8;
                 if (ok) {
 #pragma unroll
-                    for (int h4 = 0; h4 < 4; ++h4) {
-                        if (h4 * 4 < A.Cout) {
+                    for (int h4 = 0; h4 < 2; ++h4) {
+                        if (half * 8 + h4 * 4 < A.Cout) {
                             gq[h4] = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
                             xq[h4] = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
                         }
                     }
                 }
-                float v[16];
-                const float* abp = A.ab + ((size_t)g * A.C + A.out_off) * 2;
+                float v[8];
+                const float* abp = A.ab + ((size_t)g * A.C + A.out_off + half * 8) * 2;
 #pragma unroll
-                for (int h4 = 0; h4 < 4; ++h4) {
-                    if (ok && h4 * 4 < A.Cout) {
+                for (int h4 = 0; h4 < 2; ++h4) {
+                    if (ok && half * 8 + h4 * 4 < A.Cout) {
                         const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
                         const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
                         v[h4 * 4 + 0] = gq[h4].x + fmaf(c0.y, xq[h4].x, c0.x); v[h4 * 4 + 1] = gq[h4].y + fmaf(c0.w, xq[h4].y, c0.z);
@@ -1242,16 +1243,13 @@ dense_wgrad_bf16_kernel(const Args A) {
                         v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");            // zero fill complete before the interior is written
+                asm volatile("bar.sync 1, 512;" ::: "memory");            // zero fill complete before the interior is written
                 if (ok) {
-                    const uint4 lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    const uint4 hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                    const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                     const int q = r * PITCH + cc;
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + 0) * PLANE_BYTES + (size_t)(q + kx) * 16) = lo;
-                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + 1) * PLANE_BYTES + (size_t)(q + kx) * 16) = hi;
-                    }
+                    for (int kx = 0; kx < 3; ++kx)
+                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + half) * PLANE_BYTES + (size_t)(q + kx) * 16) = o;
                 }
             }
             tc::fence_proxy_async();
@@ -1337,7 +1335,7 @@ dense_wgrad_bf16_kernel(const Args A) {
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         __syncwarp();
         tc::tmem_dealloc(tmem, 512);
     }

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_28.log 2>&1; tail -3 gpurun_out/pytest_28.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_28.log 2>&1; tail -3 gpurun_out/pytest_28.log
 grep -n "^FAILED\|^E  " gpurun_out/pytest_28.log | head -20
 timeout 600 python bench.py --no-cpu-baseline --no-extra --no-e2e --steps 10 --warmup 3 > gpurun_out/bench_28.json 2> gpurun_out/bench_28.err; echo "bench exit $?"
 tail -3 gpurun_out/bench_28.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_net.py -m gpu -q -s -k "transition_down or tensor_core_backward or tf32x3" > gpurun_out/pytest_32.log 2>&1; tail -3 gpurun_out/pytest_32.log
+timeout 900 python -m pytest tests/test_gpu_net.py -m gpu -q -s -k "tensor_core_backward or full_train_step" > gpurun_out/pytest_32.log 2>&1; tail -3 gpurun_out/pytest_32.log
 grep -n "^FAILED\|^E  \|rel err\|gradient error\|forward vs\|tensor-core\|tcgen05" gpurun_out/pytest_32.log | cut -c1-220 | head -40
 timeout 600 python bench.py --no-cpu-baseline --no-extra --no-e2e --steps 10 --warmup 3 > gpurun_out/bench_32.json 2> gpurun_out/bench_32.err; echo "bench exit $?"
 tail -3 gpurun_out/bench_32.err
