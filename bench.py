@@ -40,6 +40,7 @@ if ROOT not in sys.path:
 CONFIGS = {
     # name: (batch per GPU, H, W, math, description)
     "c2": (8, 256, 320, "tf32x3", "1xB200 bs8 256x320 synthetic pairs, FCDenseNet57, full loss stack (dcl 5, sfl 20), fp32"),
+    "c3": (32, 256, 320, "tf32", "1xB200 bs32 256x320, reduced-precision tensor-core conv path (tf32 / bf16 operands), warp layers fp32"),
     "c5": (16, 512, 640, "tf32x3", "bs16/GPU 512x640 (downsampling 2.0), warp-gather stress"),
 }
 METRIC = "image-pairs/sec fwd+bwd @256x320 bs8"
