@@ -58,6 +58,11 @@ __device__ __forceinline__ float tf32_rn(float v) {
 }
 // hi part of the 3xTF32 split v = hi + lo (lo = v - hi is exact in fp32 and fits the 11 bits tf32 keeps up to 2^-23 |v|)
 __device__ __forceinline__ float tf32_hi(float v) { return tf32_rn(v); }
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 
 // Weight images: the exact shared-memory layout of one pipeline stage, built once per layer call by a tiny kernel so
 // that the producers copy them with coalesced 128-bit loads (staging OIHW weights with scalar, serialised loads cost
@@ -87,8 +92,10 @@ pack_w_dgrad_kernel(const float* __restrict__ w, int Cin, int Cout, float* __res
     }
 }
 
-// 3xTF32 (error-compensated, fp32-grade) variants: a chunk holds 8 input channels; block (ky, part) carries the tf32-truncated
-// weights (part 0, "hi") and the remainders w - hi (part 1, "lo") of the same 8 channels.
+// 3xTF32 (error-compensated, fp32-grade) variants: a chunk holds 8 input channels.  x = hi + lo with hi = x rounded to tf32;
+// x*w = hi*hi + (lo*w + x*lo_w) + O(2^-24): block (ky, 0) carries the tf32 hi weights for ONE kind::tf32 MMA (K = 8), block
+// (ky, 1) the bf16 pair [w (8 channels) ; w - hi (8 channels)] for ONE kind::f16 MMA of K = 16 that adds BOTH cross terms
+// against the activation planes [lo ; x] (the cross terms are 2^-12 of the product, so 8-bit operands keep them to 2^-21).
 __global__ void __launch_bounds__(256)
 pack_w_fwd_x3_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ out) {
     const int c = blockIdx.x;
@@ -97,8 +104,14 @@ pack_w_fwd_x3_kernel(const float* __restrict__ w, int K, int N, float* __restric
         const int ky = blk >> 1, part = blk & 1, co = n & 15, kx = n >> 4, cin = c * 8 + kc * 4 + e;
         float v = 0.f;
         if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
-        const float hi = tf32_hi(v);
-        out[(size_t)c * 2304 + d] = part ? (v - hi) : hi;
+        if (part == 0) { out[(size_t)c * 2304 + d] = tf32_hi(v); continue; }
+        // bf16 block: [kc][n][8 bf16]; word e holds channels 2e, 2e + 1 of the chunk; kc = 0: w, kc = 1: w - hi
+        const int c0 = c * 8 + 2 * e;
+        float w0 = 0.f, w1 = 0.f;
+        if (co < N && c0 < K) w0 = __ldg(w + (((size_t)co * K + c0) * 3 + ky) * 3 + kx);
+        if (co < N && c0 + 1 < K) w1 = __ldg(w + (((size_t)co * K + c0 + 1) * 3 + ky) * 3 + kx);
+        if (kc) { w0 -= tf32_hi(w0); w1 -= tf32_hi(w1); }
+        out[(size_t)c * 2304 + d] = __uint_as_float(bf16x2_rn(w0, w1));
     }
 }
 __global__ void __launch_bounds__(256)
@@ -109,18 +122,18 @@ pack_w_1x1_x3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, floa
         const int cin = c * 8 + kc * 4 + e, co = co0 + n;
         float v = 0.f;
         if (co < Ntot && cin < K) v = __ldg(w + (size_t)co * K + cin);
-        const float hi = tf32_hi(v);
-        out[(size_t)c * 2304 + d] = part ? (v - hi) : hi;
+        if (part == 0) { out[(size_t)c * 2304 + d] = tf32_hi(v); continue; }
+        const int c0 = c * 8 + 2 * e;
+        float w0 = 0.f, w1 = 0.f;
+        if (co < Ntot && c0 < K) w0 = __ldg(w + (size_t)co * K + c0);
+        if (co < Ntot && c0 + 1 < K) w1 = __ldg(w + (size_t)co * K + c0 + 1);
+        if (kc) { w0 -= tf32_hi(w0); w1 -= tf32_hi(w1); }
+        out[(size_t)c * 2304 + d] = __uint_as_float(bf16x2_rn(w0, w1));
     }
 }
 
 // bf16x3 (error-compensated bf16: x = b1 + b2, two bf16 terms = 16 significant bits, three kind::f16 MMAs of K = 16 per
 // product -- half the MMA count of 3xTF32): a chunk holds 16 input channels, block (ky, term) = [kc (8 channels)][n][8 bf16].
-__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
 // returns the packed first terms; (rlo, rhi) receive the exact remainders
 __device__ __forceinline__ uint32_t bf16_split(float lo, float hi, float& rlo, float& rhi) {
     const uint32_t p = bf16x2_rn(lo, hi);
@@ -246,7 +259,7 @@ struct FwdArgs {
     const float* wpack;   // weight image built by pack_w_fwd_kernel (2304 floats per 16-channel chunk)
     int one;              // 1: 1x1 convolution, N <= 48 plain output channels, epilogue = + bias, store (no taps, no statistics)
     float* partial; int ksplit; long long pixels;   // split-K (not with `one`): [ksplit][B*H*W][16] raw partial sums, else nullptr
-    int x3;               // 1: 3xTF32 -- a stage holds 8 channels as planes (hi0, hi1, lo0, lo1); D += Alo*Whi + Ahi*Wlo + Ahi*Whi
+    int x3;               // 1: 3xTF32 -- a stage holds 8 channels as planes (tf32 hi0, hi1; bf16 lo; bf16 x): D += [lo;x]*[w;wlo] + hi*whi
                           // 2: bf16x3 -- a stage holds 16 channels as bf16 planes (b1: ch 0-7, 8-15; b2: ch 0-7, 8-15), kind::f16
 };
 
@@ -360,7 +373,8 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 for (int j = 0; j < NIT; ++j) {
                     if (rowok & (1u << j)) {
                         const int px = (tid >> 1) + 256 * j;
-                        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+                        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+                        uint2 lo = make_uint2(0u, 0u), xb = lo;
                         if ((pixok & (1u << j)) && ch_ok) {
                             float4 v = cur[j];
                             if (!A.up) {
@@ -368,10 +382,14 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                                 v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
                             }
                             hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                            lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                            lo = make_uint2(bf16x2_rn(v.x - hi.x, v.y - hi.y), bf16x2_rn(v.z - hi.z, v.w - hi.w));
+                            xb = make_uint2(bf16x2_rn(v.x, v.y), bf16x2_rn(v.z, v.w));
                         }
+                        // plane cg: tf32 hi (4 channels); plane 2: bf16 lo, plane 3: bf16 x (8 channels per 16-byte row, this
+                        // thread's 4 channels = bytes 8 cg .. 8 cg + 7)
                         *reinterpret_cast<float4*>(a_hi_s + (size_t)px * 16) = hi;
-                        *reinterpret_cast<float4*>(a_hi_s + 2 * PLANE_BYTES + (size_t)px * 16) = lo;
+                        *reinterpret_cast<uint2*>(a_st0 + s * A_STAGE_BYTES + 2 * PLANE_BYTES + (size_t)px * 16 + cg * 8) = lo;
+                        *reinterpret_cast<uint2*>(a_st0 + s * A_STAGE_BYTES + 3 * PLANE_BYTES + (size_t)px * 16 + cg * 8) = xb;
                     }
                 }
                 if (tid == 0) ENDO_TRACE(16 + c * 8 + 2);
@@ -622,10 +640,9 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
 #pragma unroll
                         for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc_b, 1u);
                     } else {
+                        // both cross terms in ONE kind::f16 MMA of K = 16: [lo ; x] (planes 2, 3) x [w ; w - hi] (block ky, 1)
 #pragma unroll
-                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc, acc);
-#pragma unroll
-                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), blo, idesc, 1u);
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, alo + (uint64_t)(mb * 128), blo, idesc_b, acc);
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
                     }

@@ -166,7 +166,9 @@ def test_full_train_step_vs_reference_fixture(math_mode):
             loss, dcl, sfl = step.step(cb)
             # (bf16x3 is not held to this trace: its 2e-5 depth error is amplified ~250x by the composite loss at random
             # init and the second step then moves by 5-15 %; its forward is checked in test_tf32x3_*)
-            tol = 2e-3 if it == 0 else 3e-2
+            # first step: the composite loss at random init amplifies depth-map differences ~10^3 x (a 3e-6 depth difference of
+            # the tensor-core path shows up as 2.3e-3 in the flow term); second step: one realisation of the chaotic update
+            tol = (2e-3 if math_mode == "fp32" else 4e-3) if it == 0 else 3e-2
             assert abs(float(loss) - g["loss"][it]) / g["loss"][it] < tol, (pair, it, float(loss), g["loss"][it])
             assert abs(float(dcl) - g["dcl"][it]) / g["dcl"][it] < tol
             assert abs(float(sfl) - g["sfl"][it]) / g["sfl"][it] < tol
