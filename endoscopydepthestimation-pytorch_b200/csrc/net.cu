@@ -124,6 +124,25 @@ static inline bool is_tc(int math) { return math == ENDO_MATH_TF32 || math == EN
 // forward operand scheme of the tensor-core modes: 0 = plain tf32, 1 = 3xTF32, 2 = bf16x3
 static inline int x3_mode(int math) { return math == ENDO_MATH_TF32X3 ? 1 : (math == ENDO_MATH_BF16X3 ? 2 : 0); }
 
+// Weight-gradient kernels only feed the optimiser, and a layer's weight gradient is independent of the same layer's data
+// gradient: they are enqueued on a per-device side stream (forked from / joined to the caller's stream with events) so that
+// the CTAs of one kernel fill the SMs the other leaves idle in its last wave and prologue (every tensor-core kernel here
+// occupies a whole SM per CTA; 5-30 % of a launch is tail).  ENDO_TC_DISABLE bit 8192 keeps everything on one stream.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
+static SideStream* side_stream() {
+    static SideStream tab[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& t = tab[dev];
+    if (!t.ok) {
+        if (cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        t.ok = true;
+    }
+    return &t;
+}
+
 struct Ctx {
     const NetPlan& P;
     char* acts; char* scratch;
@@ -131,6 +150,15 @@ struct Ctx {
     cudaStream_t s;
     int training;
     int math;
+    cudaStream_t sw = nullptr;        // stream of the weight-gradient kernels (== s when the side stream is off)
+    cudaEvent_t ev_fork = nullptr;
+    // everything enqueued on s so far happens-before what is enqueued on sw from now on
+    int fork() const {
+        if (sw == s) return ENDO_OK;
+        ENDO_CUDA(cudaEventRecord(ev_fork, s));
+        ENDO_CUDA(cudaStreamWaitEvent(sw, ev_fork, 0));
+        return ENDO_OK;
+    }
     float* X(int l) const { return reinterpret_cast<float*>(acts + P.x_off[l]); }
     double* ST(int l) const { return reinterpret_cast<double*>(acts + P.stat_off[l]); }
     float* MI(int l) const { return reinterpret_cast<float*>(acts + P.mi_off[l]); }
@@ -291,14 +319,15 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = d.out_off; w.g_K = d.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + d.conv.w; w.db = c.gparams + d.conv.b; w.w_cin = d.cin;
+    ENDO_TRY(c.fork());
     const bool tc_w = is_tc(c.math) && !(tc_disable_mask() & 4);
     const bool tc_d = is_tc(c.math) && !(tc_disable_mask() & 2);
     // the conv bias gradient is produced by exactly one kernel: the tcgen05 dgrad if it runs, else the FFMA wgrad if it
     // runs, else a tiny dedicated reduction
     if (tc_d) w.db = nullptr;
     if (tc_w && !tc_d) {
-        ProfScope prof(PC_WGRAD, c.s);
-        bias_grad_kernel<<<kNumSMs, 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + d.conv.b, P.Ctot[l], d.out_off, d.conv.cout,
+        ProfScope prof(PC_WGRAD, c.sw);
+        bias_grad_kernel<<<kNumSMs, 256, 0, c.sw>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + d.conv.b, P.Ctot[l], d.out_off, d.conv.cout,
                                                   (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
         ENDO_CHECK_LAUNCH();
     }
@@ -322,13 +351,13 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
             configured = true;
         }
         dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
-        ProfScope prof(PC_WGRAD, c.s);
-        tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(t);
+        ProfScope prof(PC_WGRAD, c.sw);
+        tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(t);
         ENDO_CHECK_LAUNCH();
     } else if (d.conv.cout == 12) {
-        ENDO_TRY((launch_wgrad2<3, 12, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+        ENDO_TRY((launch_wgrad2<3, 12, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.sw)));
     } else {
-        ENDO_TRY((launch_wgrad2<3, 16, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.s)));
+        ENDO_TRY((launch_wgrad2<3, 16, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.sw)));
     }
     // data gradient through conv, ReLU and BatchNorm (first term; the mean terms are applied lazily)
     ConvArgs a = base_args(c);
@@ -457,6 +486,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
     w.g_off = P.offIn[l + 1]; w.g_K = cs; w.g_h = P.h[l + 1]; w.g_w = P.w[l + 1];
     w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = cs;
+    ENDO_TRY(c.fork());
     if (is_tc(c.math) && !(tc_disable_mask() & 32)) {
         // tcgen05 (bf16): the weight-gradient kernel in 1x1 mode, 48 output channels per launch; bias gradient = sum of the
         // routed (= of the pooled) gradient, reduced over the coarse buffer
@@ -467,8 +497,8 @@ static int trans_down_bwd(const Ctx& c, int l) {
             configured = true;
         }
         {
-            ProfScope prof(PC_WGRAD_TRANS, c.s);
-            bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.s>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
+            ProfScope prof(PC_WGRAD_TRANS, c.sw);
+            bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.sw>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
                                                                              P.Ctot[l + 1], P.offIn[l + 1], cs,
                                                                              (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
             ENDO_CHECK_LAUNCH();
@@ -488,12 +518,12 @@ static int trans_down_bwd(const Ctx& c, int l) {
             if (want < 1) want = 1;
             q.tiles_per_cta = cdiv(q.n_tiles, want);
             dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
-            ProfScope prof(PC_WGRAD_TRANS, c.s);
-            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(q);
+            ProfScope prof(PC_WGRAD_TRANS, c.sw);
+            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(q);
             ENDO_CHECK_LAUNCH();
         }
     } else {
-        ENDO_TRY((launch_wgrad2<1, 48, 1, 8, LM_BNRELU, LM_GRADPOOL, false>(w, c.s)));
+        ENDO_TRY((launch_wgrad2<1, 48, 1, 8, LM_BNRELU, LM_GRADPOOL, false>(w, c.sw)));
     }
     ConvArgs a = base_args(c);
     a.in = c.GX(l + 1); a.in2 = c.X(l + 1); a.in_ab = c.AB(l + 1); a.argmax = am; a.in_C = P.Ctot[l + 1];
@@ -580,6 +610,10 @@ static int trans_up_bwd(const Ctx& c, int i) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = 0; w.g_K = t.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = t.cin;
+    const long long tmp_need = 4ll * P.B * P.h[l] * P.w[l] * t.cin;
+    const bool dgrad_tc = is_tc(c.math) && !(tc_disable_mask() & 2048) && t.cin <= tcdgrad::NC && (t.cin & 3) == 0 &&
+                          tmp_need <= P.tdtmp_bytes;
+    ENDO_TRY(c.fork());
     if (is_tc(c.math) && !(tc_disable_mask() & 16)) {
         // tcgen05 (bf16): the DenseLayer weight-gradient kernel with the upsampling loader, 16 output channels per pass;
         // the bias gradient comes from the small dedicated reduction
@@ -589,9 +623,9 @@ static int trans_up_bwd(const Ctx& c, int i) {
                                            tcwgrad::SMEM_BYTES));
             configured = true;
         }
-        {
-            ProfScope prof(PC_WGRAD_TRANS, c.s);
-            bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.s>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
+        if (!dgrad_tc) {                                  // otherwise the data-gradient passes below produce the bias gradient
+            ProfScope prof(PC_WGRAD_TRANS, c.sw);
+            bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.sw>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
                                                                                        t.conv.cout, (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
             ENDO_CHECK_LAUNCH();
         }
@@ -609,15 +643,14 @@ static int trans_up_bwd(const Ctx& c, int i) {
             if (want < 1) want = 1;
             q.tiles_per_cta = cdiv(q.n_tiles, want);
             dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
-            ProfScope prof(PC_WGRAD_TRANS, c.s);
-            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.s>>>(q);
+            ProfScope prof(PC_WGRAD_TRANS, c.sw);
+            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(q);
             ENDO_CHECK_LAUNCH();
         }
     } else {
-        ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.s)));
+        ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.sw)));
     }
-    const long long tmp_need = 4ll * P.B * P.h[l] * P.w[l] * t.cin;
-    if (is_tc(c.math) && !(tc_disable_mask() & 2048) && t.cin <= tcdgrad::NC && (t.cin & 3) == 0 && tmp_need <= P.tdtmp_bytes) {
+    if (dgrad_tc) {
         // tcgen05 (tf32): the DenseLayer data-gradient kernel in plain mode, 16 output-gradient channels per pass, raw result
         // into the (now idle) forward scratch tensor at full resolution; then the 2x2 fold into the half-resolution buffer
         float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
@@ -630,7 +663,10 @@ static int trans_up_bwd(const Ctx& c, int i) {
         for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
             tcdgrad::Args q{};
             q.g = c.GX(l); q.x = c.X(l); q.ab = c.AB(l); q.coef = nullptr; q.w = c.params + t.conv.w + (size_t)co0 * t.cin * 9;
-            q.gout = nullptr; q.db = nullptr; q.red = nullptr; q.red_C = 0;
+            q.gout = nullptr; q.red = nullptr; q.red_C = 0;
+            // conv bias gradient = sum of the (corrected) output gradient: a by-product of staging it; when the FFMA weight
+            // gradient runs (debug toggle 16) that kernel produces it instead
+            q.db = (is_tc(c.math) && !(tc_disable_mask() & 16)) ? c.gparams + t.conv.b + co0 : nullptr;
             q.C = P.Ctot[l]; q.out_off = co0; q.Cout = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16; q.in_off = 0; q.Cin = t.cin;
             q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
             q.plain = 1; q.first = co0 == 0; q.oC = t.cin; q.o_off = 0; q.po = tmp;
@@ -704,6 +740,7 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
     ENDO_TRY(build_plan(cfg, B, H, W, groups, P));
     if (acts_bytes < (size_t)P.acts_bytes) return ENDO_ERR_WORKSPACE;
     Ctx c{P, static_cast<char*>(acts), nullptr, params, nullptr, bn_buffers, (cudaStream_t)stream, training, math};
+    c.sw = c.s;
     const int nd = cfg->n_down;
     // statistics accumulate with atomics: clear them
     ENDO_CUDA(cudaMemsetAsync(c.acts + P.stat_off[0], 0, (size_t)(P.mi_off[0] - P.stat_off[0]), c.s));
@@ -752,6 +789,9 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
     if (acts_bytes < (size_t)P.acts_bytes || scratch_bytes < (size_t)P.scratch_bytes) return ENDO_ERR_WORKSPACE;
     if (P.Ctot[0] > 384) return ENDO_ERR_CONFIG;
     Ctx c{P, static_cast<char*>(acts), static_cast<char*>(scratch), params, g_params, nullptr, (cudaStream_t)stream, 1, math};
+    SideStream* side = (tc_disable_mask() & 8192) ? nullptr : side_stream();
+    c.sw = side ? side->s : c.s;
+    c.ev_fork = side ? side->fork : nullptr;
     const int nd = cfg->n_down;
     // gradient buffers of levels >= 1, the lazy-correction arrays and the BN sums start at zero; the level-0
     // gradient buffer (the largest) is fully written by the finalConv backward and needs no clearing
@@ -781,13 +821,18 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         w.g_in = c.GX(0); w.g_x = c.X(0); w.g_ab = c.AB(0); w.g_C = P.Ctot[0]; w.g_off = P.offIn[0]; w.g_K = P.first.cout;
         w.g_h = H; w.g_w = W; w.oh = H; w.ow = W; w.B = B; w.G = P.G;
         w.dw = g_params + P.first.w; w.db = g_params + P.first.b; w.w_cin = cfg->in_channels;
+        ENDO_TRY(c.fork());
         if (cfg->in_channels == 3 && P.first.cout == 48 && !(tc_disable_mask() & 4096)) {
-            ProfScope prof(PC_WGRAD_TRANS, c.s);
-            first_wgrad_kernel<<<4 * kNumSMs, FW_THREADS, 0, c.s>>>(w);
+            ProfScope prof(PC_WGRAD_TRANS, c.sw);
+            first_wgrad_kernel<<<4 * kNumSMs, FW_THREADS, 0, c.sw>>>(w);
             ENDO_CHECK_LAUNCH();
         } else {
-            ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.s)));
+            ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.sw)));
         }
+    }
+    if (c.sw != c.s) {                                       // join: the caller's stream waits for the weight gradients
+        ENDO_CUDA(cudaEventRecord(side->join, c.sw));
+        ENDO_CUDA(cudaStreamWaitEvent(c.s, side->join, 0));
     }
     return ENDO_OK;
 }
