@@ -325,9 +325,19 @@ def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof
     Cin*4 B/pixel for 216*Cin flop/pixel = 54 flop/B against a ridge of ~210), so the bound is HBM; the tensor-pipe
     throughput of the same launches is reported next to it."""
     from endo_b200 import _lib
-    with _lib.profile() as prof:
-        for _ in range(prof_steps):
-            fused.step(resident)
+    # per-class times must be exclusive: keep the weight-gradient kernels on the main stream while profiling (in the timed
+    # arms they run on a forked side stream and overlap the data-gradient kernels)
+    prev = os.environ.get("ENDO_TC_DISABLE")
+    os.environ["ENDO_TC_DISABLE"] = str(int(prev or "0") | 8192)
+    try:
+        with _lib.profile() as prof:
+            for _ in range(prof_steps):
+                fused.step(resident)
+    finally:
+        if prev is None:
+            os.environ.pop("ENDO_TC_DISABLE", None)
+        else:
+            os.environ["ENDO_TC_DISABLE"] = prev
     barrier()
     dense_f, trans_f, final_f = conv_flops_per_image(h, w)
     conv_b = conv_bytes_per_image(h, w)

@@ -1114,6 +1114,14 @@ dense_wgrad_bf16_kernel(const Args A) {
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 16) {
+        // The gradient planes are cleared ONCE: the rows the interior pixels write are the same for every tile (an interior
+        // pixel outside the image stores zeros), every other row -- halo columns / rows of the kx-shifted planes -- stays zero.
+        // (A per-tile clear of 33 KB plus the barrier in front of the interior stores was ~30 % of the staging time.)
+        for (int i = tid; i < 2 * (G_STAGE / 16); i += NPROD) {
+            const int st = i / (G_STAGE / 16), j = i - st * (G_STAGE / 16);
+            reinterpret_cast<uint4*>(smem + st * STAGE + A_STAGE)[j] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1;
             if (it >= 2) tc::mbar_wait(bars + 2 + s, ((it >> 1) - 1) & 1);
@@ -1190,13 +1198,6 @@ dense_wgrad_bf16_kernel(const Args A) {
                 const unsigned pos = (unsigned)(((y & 1) << 1) | (x & 1));
                 const size_t pp = ok ? ((size_t)(b * A.cH + (y >> 1)) * A.cW + (x >> 1)) : 0;
                 const int q = r * PITCH + cc;
-                // halo rows / columns of the six planes must read as zero: clear the few rows the interior never writes
-                for (int i = tid; i < 6 * (A_ROWS + 2); i += NPROD) {
-                    const int pl = i % 6, row = i / 6, src = row - 1;
-                    const int rr = src / PITCH, c2 = src - rr * PITCH;
-                    if (src < 0 || src >= A_ROWS || rr < 1 || rr > TR || c2 < 1 || c2 > TW)
-                        *reinterpret_cast<uint4*>(g_s + pl * PLANE_BYTES + (size_t)row * 16) = make_uint4(0u, 0u, 0u, 0u);
-                }
 #pragma unroll 1
                 for (int sub = 0; sub < 3; ++sub) {
                     const int cbase = A.out_off + sub * 16 + half * 8;      // channel inside the conv's output
@@ -1229,8 +1230,6 @@ dense_wgrad_bf16_kernel(const Args A) {
                 }
             } else
             {
-                uint4* gz = reinterpret_cast<uint4*>(g_s);
-                for (int i = tid; i < G_STAGE / 16; i += NPROD) gz[i] = make_uint4(0u, 0u, 0u, 0u);
                 const int r = 1 + (gpix >> 5), cc = 1 + (gpix & 31);
                 const int y = y0 + r - 1, x = x0 + cc - 1;
                 const bool ok = (y < A.H) && (x < A.W);
@@ -1260,9 +1259,9 @@ dense_wgrad_bf16_kernel(const Args A) {
                         v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
                     }
                 }
-                asm volatile("bar.sync 1, 512;" ::: "memory");            // zero fill complete before the interior is written
-                if (ok) {
-                    const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                {
+                    const uint4 o = ok ? make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]))
+                                       : make_uint4(0u, 0u, 0u, 0u);
                     const int q = r * PITCH + cc;
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
