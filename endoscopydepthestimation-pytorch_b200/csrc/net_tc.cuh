@@ -1145,9 +1145,10 @@ dense_wgrad_bf16_kernel(const Args A) {
                 const int sh = A.up ? 1 : 0;
                 const int sW = A.W >> sh;
                 const float* xa_b = A.xa + (size_t)b * (A.H >> sh) * sW * A.xa_C + A.in_off + ch;
+                const bool v8_ok = (((A.in_off + ci0) | A.xa_C) & 7) == 0 && (reinterpret_cast<uintptr_t>(A.xa) & 31) == 0;
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {               // 6 pixels per thread: two batches of 3, loads first
-                    float4 q0[3], q1[3];
+                    float4 q0[3], q1[3];                             // (one batch of 6 / deeper prefetch measured slower)
                     unsigned okmask = 0u;
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
@@ -1157,8 +1158,15 @@ dense_wgrad_bf16_kernel(const Args A) {
                         q0[j] = make_float4(0.f, 0.f, 0.f, 0.f); q1[j] = q0[j];
                         if (ch_ok && px < A_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) {
                             const float* p = xa_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.xa_C;
-                            q0[j] = __ldg(reinterpret_cast<const float4*>(p));
-                            if (hi_ok) q1[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                            if (hi_ok && v8_ok) {
+                                // one 256-bit load = one whole 32-byte sector per lane, not cached in the (small) L1
+                                asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                             : "=f"(q0[j].x), "=f"(q0[j].y), "=f"(q0[j].z), "=f"(q0[j].w),
+                                               "=f"(q1[j].x), "=f"(q1[j].y), "=f"(q1[j].z), "=f"(q1[j].w) : "l"(p));
+                            } else {
+                                q0[j] = __ldg(reinterpret_cast<const float4*>(p));
+                                if (hi_ok) q1[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                            }
                             okmask |= 1u << j;
                         }
                     }
