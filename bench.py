@@ -370,6 +370,15 @@ def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof
                 "note": kind + "; algorithmic bytes = layer-by-layer operand stream (conv_bytes_per_image), time = sum of the "
                         "class's launches in one step (CUDA events on the launching stream)",
                 "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
+    # dram__bytes_read + dram__bytes_write of the class's largest launch from the committed ncu --set full capture
+    # (profiles/r1_tf32x3_final.md; tcgen05 modes only): traffic well above the algorithmic bytes = wasted re-reads
+    ncu_largest = {"conv_dense_dgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) data gradient", "duration_us": 811.5,
+                                        "dram_bytes": 3.275e9, "algorithmic_bytes": 2.894e9},
+                   "conv_dense_wgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) weight gradient", "duration_us": 559.4,
+                                        "dram_bytes": 1.793e9, "algorithmic_bytes": 1.007e9}}
+    if math_mode != "fp32" and dominant in ncu_largest and (bsz, h, w) == (8, 256, 320):
+        roofline["traffic"] = ncu_largest[dominant]["dram_bytes"]
+        roofline["traffic_of"] = ncu_largest[dominant]
     kernels = {k: {"ms_per_step": round(v, 4), "launch_sites": cat_n[k]} for k, v in cat_ms.items()}
     for k, byts in work_bytes.items():
         if cat_ms.get(k, 0.0) > 0:
