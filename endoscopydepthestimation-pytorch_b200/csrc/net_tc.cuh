@@ -1127,7 +1127,8 @@ dense_wgrad_bf16_kernel(const Args A) {
             if (it >= 2) tc::mbar_wait(bars + 2 + s, ((it >> 1) - 1) & 1);
             const int t = t_begin + it;
             const int b = t / (tiles_x * tiles_y), rem = t - b * (tiles_x * tiles_y);
-            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const int tx = rem / tiles_y, ty = rem - tx * tiles_y;      // column-major: consecutive tiles of a CTA are vertical
+                                                                        // neighbours, the 2 shared halo rows hit L2 instead of DRAM
             const int y0 = ty * TR, x0 = tx * TW;
             const int g = b / (A.B / A.G);
             unsigned char* a_s = smem + s * STAGE;
