@@ -783,12 +783,12 @@ dense_dgrad_tf32_kernel(const Args A) {
             const size_t img = (size_t)b * A.H * A.W;
             float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int part = 0; part < 4; ++part) {                    // 19 pixels per thread in batches of 5 (2 loads each)
-                float4 gq[5], xq[5];
+            for (int part = 0; part < 2; ++part) {                    // 19 pixels per thread in two batches of 10 (2 loads each)
+                float4 gq[10], xq[10];
                 unsigned okmask = 0u;
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int px = (tid >> 2) + 64 * (part * 5 + j);
+                for (int j = 0; j < 10; ++j) {
+                    const int px = (tid >> 2) + 64 * (part * 10 + j);
                     const int r = px / PITCH, cc = px - r * PITCH;
                     const int y = y0 + r - 1, x = x0 + cc - 1;
                     gq[j] = make_float4(0.f, 0.f, 0.f, 0.f); xq[j] = gq[j];
@@ -800,8 +800,8 @@ dense_dgrad_tf32_kernel(const Args A) {
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int px = (tid >> 2) + 64 * (part * 5 + j);
+                for (int j = 0; j < 10; ++j) {
+                    const int px = (tid >> 2) + 64 * (part * 10 + j);
                     if (px < REAL_ROWS) {
                         const int r = px / PITCH, cc = px - r * PITCH;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
