@@ -246,20 +246,44 @@ pw_gemm_kernel(const Args A) {
         const int q = warp & 3, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         if (A.mode == 0) {
-            // thread = pixel (TMEM lane); warps 0-3 take the 16-column groups 0, 2, 4, ..., warps 4-7 the odd ones
-            const long long p = p0 + q * 32 + lane;
-            float* op = A.out + (size_t)p * A.out_C + A.out_off;
-            for (int cg = hf; cg * 16 < A.Npad; cg += 2) {
-                float v[16];
-                tc::tmem_ld16(tmem + lane_base + cg * 16, v);
-                if (p < p_end) {
+            // 64-channel column blocks: TMEM -> transposed shared tile (the pipeline stages are idle now) -> lane = (pixel
+            // parity, channel quad), so that a warp store covers two pixels x 256 contiguous bytes.  (One thread per pixel
+            // writing 16-byte pieces 768 B apart cost 32 line transactions per store instruction: the store path, not HBM,
+            // bounded this kernel.)
+            unsigned char* tbf = smem;
+            const int quad = lane & 15, psub = lane >> 4;
+            for (int cb = 0; cb * 64 < A.Npad; ++cb) {
+                {
+                    const uint32_t taddr = tmem + lane_base + cb * 64 + hf * 32;
+                    unsigned char* row = tbf + (size_t)(q * 32 + lane) * TB_PITCH + hf * 128;
+                    float v[16];
+                    if (cb * 64 + hf * 32 < A.Npad) {
+                        tc::tmem_ld16(taddr, v);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const int n = cg * 16 + j;
-                        if (n < A.N)
-                            *reinterpret_cast<float4*>(op + n) = make_float4(v[j] + ntab[n], v[j + 1] + ntab[n + 1], v[j + 2] + ntab[n + 2], v[j + 3] + ntab[n + 3]);
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(row + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (cb * 64 + hf * 32 + 16 < A.Npad) {
+                        tc::tmem_ld16(taddr + 16, v);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(row + 64 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int n0 = cb * 64 + quad * 4;
+                if (n0 < A.N) {
+                    const float4 bq = *reinterpret_cast<const float4*>(ntab + n0);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int pl = warp * 16 + it * 2 + psub;
+                        const long long p = p0 + pl;
+                        if (p < p_end) {
+                            const float4 d = *reinterpret_cast<const float4*>(tbf + (size_t)pl * TB_PITCH + quad * 16);
+                            *reinterpret_cast<float4*>(A.out + (size_t)p * A.out_C + A.out_off + n0) =
+                                make_float4(d.x + bq.x, d.y + bq.y, d.z + bq.z, d.w + bq.w);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");           // tile reusable
             }
         } else {
             // 64-channel column blocks: TMEM -> transposed shared tile -> lane = (pixel parity, channel quad): ReLU mask,

@@ -542,7 +542,9 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 for (int j = 0; j < 16; ++j) edge[(u * 2 + 0) * 16 + j] = __uint_as_float(r2[j]);    // kx = 2 part of my first pixel
             }
         }
+        if (tid == 0) ENDO_TRACE(6);
         asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid == 0) ENDO_TRACE(7);
         float s1[16], s2[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -582,6 +584,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                 }
             }
         }
+        if (tid == 0) ENDO_TRACE(8);
         // per-channel statistics: warp tree -> shared -> one fp64 atomic per channel per CTA
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
