@@ -555,18 +555,31 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 16, v1);
             tc::tmem_ld16_issue(tmem + lane_base + mb * NB + 32, v2);
             tc::tmem_ld_wait();
+            if (tid == 0) ENDO_TRACE(9 + (mb >> 2) * 2);
             const int L = PITCH + mb * 128 + q * 32 + lane;           // linear index in the halo tile
             const int r = L / PITCH, cc = L - r * PITCH;
             const int y = y0 + r - 1, x = x0 + cc - 1;
             const bool ok = (r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W);
             float o[16];
+            // values of the neighbouring 32-lane units: uniform (broadcast) 16-byte loads + selects.  (Per-channel `if (lane == 0)`
+            // loads were 32 divergent regions per M-block: ~4k of the ~5.5k cycles an M-block took here, clock64 trace.)
+            const float* eL = edge + ((u > 0 ? u - 1 : 0) * 2 + 1) * 16;
+            const float* eR = edge + ((u < NUNITS - 1 ? u + 1 : u) * 2 + 0) * 16;
+            const float keepL = (u > 0) ? 1.f : 0.f, keepR = (u < NUNITS - 1) ? 1.f : 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float left = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
-                float right = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
-                if (lane == 0) left = (u > 0) ? edge[((u - 1) * 2 + 1) * 16 + j] : 0.f;
-                if (lane == 31) right = (u < NUNITS - 1) ? edge[((u + 1) * 2 + 0) * 16 + j] : 0.f;
-                o[j] = (left + __uint_as_float(v1[j])) + right + (A.partial ? 0.f : s_bias[j]);
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+                const float4 l4 = *reinterpret_cast<const float4*>(eL + j4), r4 = *reinterpret_cast<const float4*>(eR + j4);
+                const float lq[4] = {l4.x * keepL, l4.y * keepL, l4.z * keepL, l4.w * keepL};
+                const float rq[4] = {r4.x * keepR, r4.y * keepR, r4.z * keepR, r4.w * keepR};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j4 + e;
+                    float left = __uint_as_float(__shfl_up_sync(0xffffffffu, v0[j], 1));
+                    float right = __uint_as_float(__shfl_down_sync(0xffffffffu, v2[j], 1));
+                    left = (lane == 0) ? lq[e] : left;
+                    right = (lane == 31) ? rq[e] : right;
+                    o[j] = (left + __uint_as_float(v1[j])) + right + (A.partial ? 0.f : s_bias[j]);
+                }
             }
             if (ok && A.partial) {
                 float* pp = A.partial + ((size_t)blockIdx.y * A.pixels + ((size_t)(b * A.H + y) * A.W + x)) * 16;
@@ -577,12 +590,13 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4) {
                     if (j < A.N) {
-                        *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        if (!(A.dbg & 16)) *reinterpret_cast<float4*>(op + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
 #pragma unroll
                         for (int e = 0; e < 4; ++e) { s1[j + e] += o[j + e]; s2[j + e] += o[j + e] * o[j + e]; }
                     }
                 }
             }
+            if (tid == 0) ENDO_TRACE(10 + (mb >> 2) * 2);
         }
         if (tid == 0) ENDO_TRACE(8);
         // per-channel statistics: warp tree -> shared -> one fp64 atomic per channel per CTA

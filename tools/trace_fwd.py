@@ -19,6 +19,7 @@ n = int(t[0]); t0 = t[1]
 print("last traced launch = finalmost DenseLayer (up-block, level 0); chunks:", n)
 print(f"setup->first chunk: {t[16] - t0}; epilogue wait {t[3] - t[2]}; epilogue {t[4] - t[3]} "
       f"(edge pass {t[6] - t[3]}, barrier {t[7] - t[6]}, combine+store {t[8] - t[7]}, statistics {t[4] - t[8]}); total {t[5] - t0} cycles")
+print("combine+store of warp 0, per M-block [TMEM loads done, stores issued] rel. to its start:", [t[i] - t[7] for i in range(9, 15)])
 print("chunk: prod[wait_empty, loads+stores, weights, fence+arrive] | mma[wait_full, issue] | prod start rel, mma start rel")
 for c in range(n):
     b = 16 + c * 8
