@@ -619,16 +619,17 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             atomicAdd(A.stats + ((size_t)g * A.stats_C + A.out_off + j) * 2 + which, sum);
         }
         }   // !A.one
-    } else if (lane == 0) {
-        // ======================================================================== MMA issuer (one thread)
+    } else {
+        // ======================================================================== MMA issuer: warp 16, convergent; one elected lane issues
+        const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NB);
         for (int c = c_begin; c < c_end; ++c) {
             const int it = c - c_begin;
             const int s = it & 1;
-            ENDO_TRACE(16 + c * 8 + 5);
+            if (lane == 0) ENDO_TRACE(16 + c * 8 + 5);
             tc::mbar_wait(bars + s, (it >> 1) & 1);
             tc::tc_fence_after();
-            ENDO_TRACE(16 + c * 8 + 6);
+            if (lane == 0) ENDO_TRACE(16 + c * 8 + 6);
             const uint32_t a_base = tc::smem_u32(a_st0 + s * A_STAGE_BYTES);
             const uint32_t b_base = tc::smem_u32(b_st0 + s * B_STAGE_BYTES);
             const int nk8 = (A.x3 || A.K - c * KCH > 8) ? 2 : 1;   // skip an all-zero K half on the last chunk
@@ -651,17 +652,17 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint32_t acc = (uint32_t)((it | ky) != 0);
                     if (A.x3 == 2) {                                  // bf16x3: same planes / blocks, kind::f16, K = 16 per MMA
 #pragma unroll
-                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc_b, acc);
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16_w(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc_b, acc);
 #pragma unroll
-                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, ahi + (uint64_t)(mb * 128), blo, idesc_b, 1u);
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16_w(tmem + mb * NB, ahi + (uint64_t)(mb * 128), blo, idesc_b, 1u);
 #pragma unroll
-                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc_b, 1u);
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16_w(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc_b, 1u);
                     } else {
                         // both cross terms in ONE kind::f16 MMA of K = 16: [lo ; x] (planes 2, 3) x [w ; w - hi] (block ky, 1)
 #pragma unroll
-                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16(tmem + mb * NB, alo + (uint64_t)(mb * 128), blo, idesc_b, acc);
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16_w(tmem + mb * NB, alo + (uint64_t)(mb * 128), blo, idesc_b, acc);
 #pragma unroll
-                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32_w(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
                     }
                 }
             } else if (A.one) {
@@ -670,7 +671,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)PITCH * 16u) >> 4);
 #pragma unroll
                     for (int mb = 0; mb < MBLK; ++mb)
-                        tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, (uint32_t)((it | k8) != 0));
+                        tc::mma_tf32_w(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, (uint32_t)((it | k8) != 0));
                 }
             } else
 #pragma unroll 1
@@ -682,13 +683,13 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint64_t ad0 = a_hi | (uint64_t)((a_base + (uint32_t)(2 * k8) * PLANE_BYTES + (uint32_t)(PITCH + (ky - 1) * PITCH) * 16u) >> 4);
                     const uint32_t acc = (uint32_t)((it | ky | k8) != 0);
 #pragma unroll
-                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, acc);
+                    for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32_w(tmem + mb * NB, ad0 + (uint64_t)(mb * 128), bd, idesc, acc);
                 }
             }
-            tc::tc_commit(bars + 2 + s);
-            ENDO_TRACE(16 + c * 8 + 7);
+            tc::tc_commit_w(bars + 2 + s);
+            if (lane == 0) ENDO_TRACE(16 + c * 8 + 7);
         }
-        tc::tc_commit(bars + 4);
+        tc::tc_commit_w(bars + 4);
     }
     if (tid == 0) ENDO_TRACE(4);
     tc::tc_fence_before();
