@@ -372,8 +372,9 @@ pw_gemm_kernel(const Args A) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");           // tb / red reusable
             }
         }
-    } else if (lane == 0) {
-        // ======================================================================== MMA issuer (one thread)
+    } else {
+        // ======================================================================== MMA issuer: warp 8, convergent; one elected lane issues
+        const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         // N > 256 is issued as two MMAs of N/2 columns (both multiples of 16)
         const int n_first = A.Npad <= 256 ? A.Npad : ((A.Npad / 2 + 15) & ~15);
         const int n_second = A.Npad - n_first;
@@ -388,8 +389,8 @@ pw_gemm_kernel(const Args A) {
             const uint32_t a_base = tc::smem_u32(a_st + s * A_STAGE), b_base = tc::smem_u32(b_st + s * bstage);
             auto mma = [&](uint32_t a_off, uint32_t b_off, uint32_t acc) {
                 const uint64_t ad = a_hi | (uint64_t)((a_base + a_off) >> 4);
-                tc::mma_tf32(tmem, ad, b_hi | (uint64_t)((b_base + b_off) >> 4), id1, acc);
-                if (n_second) tc::mma_tf32(tmem + n_first, ad, b_hi | (uint64_t)((b_base + b_off + (uint32_t)n_first * 16u) >> 4), id2, acc);
+                tc::mma_tf32_w(tmem, ad, b_hi | (uint64_t)((b_base + b_off) >> 4), id1, acc);
+                if (n_second) tc::mma_tf32_w(tmem + n_first, ad, b_hi | (uint64_t)((b_base + b_off + (uint32_t)n_first * 16u) >> 4), id2, acc);
             };
             if (A.x3) {
                 const uint32_t acc = (uint32_t)(c != 0);
@@ -400,9 +401,9 @@ pw_gemm_kernel(const Args A) {
                 const int nk8 = (A.K - c * 16 > 8) ? 2 : 1;
                 for (int k8 = 0; k8 < nk8; ++k8) mma((uint32_t)(2 * k8) * MT * 16, (uint32_t)(2 * k8) * bplane, (uint32_t)((c | k8) != 0));
             }
-            tc::tc_commit(bars + NST + s);
+            tc::tc_commit_w(bars + NST + s);
         }
-        tc::tc_commit(bars + 2 * NST);
+        tc::tc_commit_w(bars + 2 * NST);
     }
     tc::tc_fence_before();
     __syncthreads();

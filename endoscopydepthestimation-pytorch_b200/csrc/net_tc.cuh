@@ -977,8 +977,9 @@ dense_dgrad_tf32_kernel(const Args A) {
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");               // red / ctab / weights reusable
         }
-    } else if (lane == 0) {
-        // -------------------------------------------------------------------- MMA issuer
+    } else {
+        // -------------------------------------------------------------------- MMA issuer: warp 8, convergent; one elected lane issues
+        const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NC);
         const uint32_t g_base = tc::smem_u32(g_s), w_base = tc::smem_u32(w_s);
         int unit = 0;
@@ -1005,11 +1006,11 @@ dense_dgrad_tf32_kernel(const Args A) {
                                                                (uint32_t)(1 + PITCH + (ky - 1) * PITCH + (kx - 1)) * 16u) >> 4);
                         for (int u = 0; u < gsz; ++u) {
                             const int buf = (unit + u) % NBUF;
-                            tc::mma_tf32(tmem + buf * NC, ad0 + (uint64_t)((mb0 + u) * 128), bd, idesc, (uint32_t)((tap | k8) != 0));
+                            tc::mma_tf32_w(tmem + buf * NC, ad0 + (uint64_t)((mb0 + u) * 128), bd, idesc, (uint32_t)((tap | k8) != 0));
                         }
                     }
                 }
-                for (int u = 0; u < gsz; ++u) tc::tc_commit(bars + 1 + (unit + u) % NBUF);
+                for (int u = 0; u < gsz; ++u) tc::tc_commit_w(bars + 1 + (unit + u) % NBUF);
                 unit += gsz;
             }
         }
@@ -1343,7 +1344,8 @@ dense_wgrad_bf16_kernel(const Args A) {
                 }
             }
         }
-    } else if (lane == 0) {
+    } else {                                                 // warp 16, convergent; one elected lane issues
+        const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         const uint32_t idesc = tc::instr_desc(tc::FMT_BF16, 128, NB, 1, 1);
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1;
@@ -1359,7 +1361,7 @@ dense_wgrad_bf16_kernel(const Args A) {
                 // 1x1: one MMA per 16 pixels, rotating over 9 accumulator tiles
 #pragma unroll 1
                 for (int k16 = 0; k16 < KPX / 16; ++k16)
-                    tc::mma_f16(tmem + (k16 % 9) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16), b_d0 + (uint64_t)(PITCH + k16 * 16), idesc,
+                    tc::mma_f16_w(tmem + (k16 % 9) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16), b_d0 + (uint64_t)(PITCH + k16 * 16), idesc,
                                 (uint32_t)(it != 0 || k16 >= 9));
             } else {
 #pragma unroll 1
@@ -1369,12 +1371,12 @@ dense_wgrad_bf16_kernel(const Args A) {
                 const uint32_t acc = (uint32_t)(it != 0 || k16 >= 3);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky)
-                    tc::mma_f16(tmem + (set * 3 + ky) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16 + (ky - 1) * PITCH), bd, idesc, acc);
+                    tc::mma_f16_w(tmem + (set * 3 + ky) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16 + (ky - 1) * PITCH), bd, idesc, acc);
             }
             }
-            tc::tc_commit(bars + 2 + s);
+            tc::tc_commit_w(bars + 2 + s);
         }
-        tc::tc_commit(bars + 4);
+        tc::tc_commit_w(bars + 4);
     }
     tc::tc_fence_before();
     __syncthreads();
