@@ -878,6 +878,32 @@ dense_dgrad_tf32_kernel(const Args A) {
             float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
             for (int mb = 0; mb < MBLK; ++mb, ++unit) {
                 const int buf = unit % NBUF;
+                // the activations / gradient rows this lane will update (phase 2) do not depend on the accumulator: request them
+                // first, so that they travel while the MMAs finish, the accumulator is drained and the warps meet at the barrier
+                float4 xv[8], gv[8];
+                unsigned okmask = 0u;
+                size_t off[8];
+                if (quad_ok) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {                     // all 16 loads of this unit in flight at once
+                        const int p = warp * 16 + it * 2 + psub;
+                        const int L = PITCH + mb * 128 + p;
+                        const int r = L / PITCH, cc = L - r * PITCH;
+                        const int y = y0 + r - 1, x = x0 + cc - 1;
+                        off[it] = 0;
+                        if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
+                            if (A.plain) {
+                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.oC + A.o_off + ci0 + quad * 4;
+                                gv[it] = A.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(A.po + off[it]);
+                            } else {
+                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
+                                xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
+                                gv[it] = *reinterpret_cast<const float4*>(A.gout + off[it]);
+                            }
+                            okmask |= 1u << it;
+                        }
+                    }
+                }
                 tc::mbar_wait(bars + 1 + buf, (unit / NBUF) & 1);
                 tc::tc_fence_after();
                 // phase 1: TMEM -> registers -> transposed shared tile [pixel][channel]
@@ -899,28 +925,6 @@ dense_dgrad_tf32_kernel(const Args A) {
                 if (chalf == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);      // 128 arrivals: accumulator buffer free again
                 // phase 2: lane = (pixel parity, channel quad); 16 pixels per warp
                 if (quad_ok) {
-                    float4 xv[8], gv[8];
-                    unsigned okmask = 0u;
-                    size_t off[8];
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {                     // all 16 loads of this unit in flight at once
-                        const int p = warp * 16 + it * 2 + psub;
-                        const int L = PITCH + mb * 128 + p;
-                        const int r = L / PITCH, cc = L - r * PITCH;
-                        const int y = y0 + r - 1, x = x0 + cc - 1;
-                        off[it] = 0;
-                        if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
-                            if (A.plain) {
-                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.oC + A.o_off + ci0 + quad * 4;
-                                gv[it] = A.first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(A.po + off[it]);
-                            } else {
-                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
-                                xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
-                                gv[it] = *reinterpret_cast<const float4*>(A.gout + off[it]);
-                            }
-                            okmask |= 1u << it;
-                        }
-                    }
                     if (A.plain) {
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
