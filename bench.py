@@ -372,10 +372,10 @@ def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof
                 "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
     # dram__bytes_read + dram__bytes_write of the class's largest launch from the committed ncu --set full capture
     # (profiles/r1_tf32x3_final.md; tcgen05 modes only): traffic well above the algorithmic bytes = wasted re-reads
-    ncu_largest = {"conv_dense_dgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) data gradient", "duration_us": 811.5,
-                                        "dram_bytes": 3.275e9, "algorithmic_bytes": 2.894e9},
-                   "conv_dense_wgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) weight gradient", "duration_us": 559.4,
-                                        "dram_bytes": 1.793e9, "algorithmic_bytes": 1.007e9}}
+    ncu_largest = {"conv_dense_dgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) data gradient", "duration_us": 764.7,
+                                        "dram_bytes": 3.274e9, "algorithmic_bytes": 2.894e9},
+                   "conv_dense_wgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) weight gradient", "duration_us": 553.6,
+                                        "dram_bytes": 1.600e9, "algorithmic_bytes": 1.007e9}}
     if math_mode != "fp32" and dominant in ncu_largest and (bsz, h, w) == (8, 256, 320):
         roofline["traffic"] = ncu_largest[dominant]["dram_bytes"]
         roofline["traffic_of"] = ncu_largest[dominant]
