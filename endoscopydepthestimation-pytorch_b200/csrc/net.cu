@@ -211,6 +211,44 @@ static int launch_pw(const tcpw::Args& a, int G, cudaStream_t s, int cat) {
         if (_e != ENDO_OK) return _e;  \
     } while (0)
 
+// one launch packs the tensor-core weight images of every DenseLayer (forward / data gradient)
+template <class F>
+static void for_each_dense(const NetPlan& P, F f) {
+    const int nd = P.cfg.n_down;
+    for (int l = 0; l <= nd; ++l) for (const auto& d : P.down[l]) f(d);
+    for (int i = 0; i < nd; ++i) for (const auto& d : P.up[i]) f(d);
+}
+static int pack_dense_weights_fwd(const Ctx& c) {
+    tcconv::PackTable T{};
+    T.mode = x3_mode(c.math);
+    const int per = T.mode == 1 ? 8 : 16;
+    bool fits = true;
+    for_each_dense(c.P, [&](const DenseLayerP& d) {
+        if (T.n >= 112) { fits = false; return; }
+        T.e[T.n++] = tcconv::PackEntry{d.conv.w, d.cin, d.conv.cout, T.total_chunks, d.wp_off};
+        T.total_chunks += cdiv(d.cin, per);
+    });
+    if (!fits) return ENDO_ERR_CONFIG;
+    ProfScope prof(PC_BN, c.s);
+    tcconv::pack_w_fwd_all_kernel<<<T.total_chunks, 256, 0, c.s>>>(c.params, reinterpret_cast<unsigned char*>(c.acts + c.P.wpack_off), T);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+static int pack_dense_weights_bwd(const Ctx& c) {
+    tcconv::PackTable T{};
+    bool fits = true;
+    for_each_dense(c.P, [&](const DenseLayerP& d) {
+        if (T.n >= 112) { fits = false; return; }
+        T.e[T.n++] = tcconv::PackEntry{d.conv.w, d.cin, d.conv.cout, T.total_chunks, d.wpb_off};
+        T.total_chunks += cdiv(d.cin, 64);
+    });
+    if (!fits) return ENDO_ERR_CONFIG;
+    ProfScope prof(PC_BN, c.s);
+    tcconv::pack_w_dgrad_all_kernel<<<T.total_chunks, 256, 0, c.s>>>(c.params, reinterpret_cast<unsigned char*>(c.scratch + c.P.wpack_bwd_off), T);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
 static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
     const NetPlan& P = c.P;
     const int l = d.level;
@@ -226,14 +264,8 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         t.in = a.in; t.coef = a.coef; t.w = a.w; t.bias = a.bias; t.out = a.out; t.stats = a.stats;
         t.in_C = a.in_C; t.in_off = a.in_off; t.K = a.K; t.out_C = a.out_C; t.out_off = a.out_off; t.N = a.N;
         t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask(); t.one = 0;
-        t.wpack = c.WPACK(); t.x3 = x3_mode(c.math);
-        {
-            ProfScope prof(PC_BN, c.s);
-            if (t.x3 == 1) tcconv::pack_w_fwd_x3_kernel<<<cdiv(t.K, 8), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
-            else if (t.x3 == 2) tcconv::pack_w_fwd_b3_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, reinterpret_cast<uint32_t*>(c.WPACK()));
-            else tcconv::pack_w_fwd_kernel<<<cdiv(t.K, 16), 256, 0, c.s>>>(t.w, t.K, t.N, c.WPACK());
-            ENDO_CHECK_LAUNCH();
-        }
+        t.x3 = x3_mode(c.math);
+        t.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + d.wp_off);   // packed by pack_dense_weights_fwd()
         static bool configured = false;
         if (!configured) {
             ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -373,12 +405,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.gout = c.GX(l); t.db = c.gparams + d.conv.b; t.red = c.BNRED(); t.red_C = P.maxC;
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
-        t.wpack = c.WPACK_BWD();
-        {
-            ProfScope prof(PC_BN, c.s);
-            tcconv::pack_w_dgrad_kernel<<<cdiv(t.Cin, 64), 256, 0, c.s>>>(t.w, t.Cin, t.Cout, c.WPACK_BWD());
-            ENDO_CHECK_LAUNCH();
-        }
+        t.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + d.wpb_off);   // packed by pack_dense_weights_bwd()
         static bool configured = false;
         if (!configured) {
             ENDO_CUDA(cudaFuncSetAttribute(tcdgrad::dense_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -752,6 +779,7 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
         a.stats = c.ST(0); a.stats_C = P.Ctot[0];
         ENDO_TRY((launch_conv<3, 2, 48, 8, LM_NCHW, EM_STORE, WM_FWD, false>(a, c.s)));
     }
+    if (is_tc(math) && !(tc_disable_mask() & 1)) ENDO_TRY(pack_dense_weights_fwd(c));
     for (int l = 0; l < nd; ++l) {                           // models.py:175-178
         for (const auto& d : P.down[l]) ENDO_TRY(dense_layer_fwd(c, d));
         ENDO_TRY(trans_down_fwd(c, l));
@@ -806,6 +834,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
             g_y, pre, c.X(0), params + P.final_.w, c.GX(0), g_params + P.final_.w, g_params + P.final_.b, npix, P.Ctot[0], ppc);
         ENDO_CHECK_LAUNCH();
     }
+    if (is_tc(math) && !(tc_disable_mask() & 2)) ENDO_TRY(pack_dense_weights_bwd(c));
     for (int i = nd - 1; i >= 0; --i) {
         for (int j = (int)P.up[i].size() - 1; j >= 0; --j) ENDO_TRY(dense_layer_bwd(c, P.up[i][j]));
         ENDO_TRY(trans_up_bwd(c, i));

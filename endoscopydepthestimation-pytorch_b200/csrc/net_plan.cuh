@@ -28,7 +28,8 @@ constexpr int kMaxLevels = 9;   // n_down <= 8 plus the bottleneck level
 
 struct ConvP { long long w, b; int cin, cout, ks; };           // offsets (floats) into the flat parameter array
 struct BnP { long long gamma, beta; long long rmean, rvar; int c; long long coef; };   // coef: float offset in acts
-struct DenseLayerP { BnP bn; ConvP conv; int level, in_off, cin, out_off; };
+struct DenseLayerP { BnP bn; ConvP conv; int level, in_off, cin, out_off;
+                     long long wp_off, wpb_off; };   // byte offsets of this layer's tensor-core weight images inside the wpack / wpack_bwd regions
 struct TransDownP { BnP bn; ConvP conv; int level; long long argmax; };                 // argmax: byte offset in acts
 struct TransUpP { ConvP conv; int src_level, src_off, cin, dst_level; };
 
@@ -176,9 +177,14 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
     P.pre_off = off; off = align_up(off + 4ll * B * H * W, 256);
     long long maxTD = 0;                                     // widest TransitionDown (1x1 conv C -> C), rounded to 16
     for (int l = 0; l < nd; ++l) { const long long cs = (P.C0[l] + P.Dn[l] + 15) / 16 * 16; if (cs > maxTD) maxTD = cs; }
-    {   // 3x3 layers: one 9,216-byte image per 8-channel chunk (3xTF32); 1x1 layers: the whole matrix as hi + lo planes
+    {   // [shared slot: the transition layer being run | one image per DenseLayer, packed by ONE launch per forward]
+        // 3x3 layers: one 9,216-byte image per 8-channel chunk (3xTF32); 1x1 layers: the whole matrix as hi + lo planes
         long long a = 9216ll * ((P.maxC + 7) / 8) + 9216, b2 = 8ll * maxTD * maxTD + 4096;
-        P.wpack_off = off; off = align_up(off + (a > b2 ? a : b2), 256);
+        long long sz = align_up(a > b2 ? a : b2, 256);
+        auto slot = [&](DenseLayerP& d) { d.wp_off = sz; sz += 9216ll * ((d.cin + 7) / 8); };
+        for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) slot(d);
+        for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) slot(d);
+        P.wpack_off = off; off = align_up(off + sz, 256);
     }
     {
         long long mx = 0;
@@ -194,9 +200,13 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
     for (int l = 0; l <= nd; ++l) { P.gx_off[l] = off; off = align_up(off + 4ll * B * P.h[l] * P.w[l] * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.ab_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }
     P.bnred_off = off; off = align_up(off + 16ll * P.G * P.maxC, 256);
-    {   // 3x3 layers: one 36,864-byte image per 64-channel chunk; 1x1 layers: the transposed matrix, tf32
+    {   // [shared slot | one data-gradient image per DenseLayer]; 3x3 layers: 36,864 bytes per 64-channel chunk; 1x1: transposed matrix
         long long a = 36864ll * ((P.maxC + 63) / 64) + 36864, b2 = 4ll * maxTD * maxTD + 4096;
-        P.wpack_bwd_off = off; off = align_up(off + (a > b2 ? a : b2), 256);
+        long long sz = align_up(a > b2 ? a : b2, 256);
+        auto slot = [&](DenseLayerP& d) { d.wpb_off = sz; sz += 36864ll * ((d.cin + 63) / 64); };
+        for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) slot(d);
+        for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) slot(d);
+        P.wpack_bwd_off = off; off = align_up(off + sz, 256);
     }
     P.scratch_bytes = off;
     return ENDO_OK;

@@ -250,6 +250,66 @@ td_pool_kernel(const float* __restrict__ tmp, float* __restrict__ out, unsigned 
     }
 }
 
+// All DenseLayer weight images of one forward (or backward) in ONE launch: the weights do not change inside a step, and
+// 44 + 44 tiny per-layer pack launches sat on the critical path of the launch-serialised layer chain.
+struct PackEntry { long long w; int K, N, chunk0; long long out; };      // w: float offset in params; out: byte offset in the wpack region
+struct PackTable { int n, total_chunks, mode; PackEntry e[112]; };        // mode: forward 0 = tf32, 1 = 3xTF32, 2 = bf16x3; dgrad: unused
+__global__ void __launch_bounds__(256)
+pack_w_fwd_all_kernel(const float* __restrict__ params, unsigned char* __restrict__ wpack, const PackTable T) {
+    int li = 0;
+    while (li + 1 < T.n && (int)blockIdx.x >= T.e[li + 1].chunk0) ++li;
+    const PackEntry E = T.e[li];
+    const int c = blockIdx.x - E.chunk0, K = E.K, N = E.N;
+    const float* w = params + E.w;
+    float* out = reinterpret_cast<float*>(wpack + E.out);
+    for (int d = threadIdx.x; d < 2304; d += 256) {
+        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
+        const int ky = blk >> 1, part = blk & 1, co = n & 15, kx = n >> 4;
+        float res;
+        if (T.mode == 0) {                                                 // = pack_w_fwd_kernel
+            const int cin = c * 16 + part * 8 + kc * 4 + e;
+            float v = 0.f;
+            if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
+            res = tf32_rn(v);
+        } else if (T.mode == 1 && part == 0) {                             // = pack_w_fwd_x3_kernel, tf32 hi block
+            const int cin = c * 8 + kc * 4 + e;
+            float v = 0.f;
+            if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
+            res = tf32_hi(v);
+        } else {                                                           // bf16 blocks of 3xTF32 (cross terms) and of bf16x3
+            const int c0 = (T.mode == 1) ? c * 8 + 2 * e : c * 16 + kc * 8 + 2 * e;
+            float w0 = 0.f, w1 = 0.f;
+            if (co < N && c0 < K) w0 = __ldg(w + (((size_t)co * K + c0) * 3 + ky) * 3 + kx);
+            if (co < N && c0 + 1 < K) w1 = __ldg(w + (((size_t)co * K + c0 + 1) * 3 + ky) * 3 + kx);
+            if (T.mode == 1) {                                             // kc = 0: w, kc = 1: w - hi
+                if (kc) { w0 -= tf32_hi(w0); w1 -= tf32_hi(w1); }
+                res = __uint_as_float(bf16x2_rn(w0, w1));
+            } else {                                                       // part = 0: first bf16 terms, part = 1: remainders
+                const uint32_t b1 = bf16x2_rn(w0, w1);
+                const float r0 = w0 - __uint_as_float(b1 << 16), r1 = w1 - __uint_as_float(b1 & 0xFFFF0000u);
+                res = __uint_as_float(part ? bf16x2_rn(r0, r1) : b1);
+            }
+        }
+        out[(size_t)c * 2304 + d] = res;
+    }
+}
+__global__ void __launch_bounds__(256)
+pack_w_dgrad_all_kernel(const float* __restrict__ params, unsigned char* __restrict__ wpack, const PackTable T) {
+    int li = 0;
+    while (li + 1 < T.n && (int)blockIdx.x >= T.e[li + 1].chunk0) ++li;
+    const PackEntry E = T.e[li];
+    const int c = blockIdx.x - E.chunk0, Cin = E.K, Cout = E.N;
+    const float* w = params + E.w;
+    float* out = reinterpret_cast<float*>(wpack + E.out);
+    for (int d = threadIdx.x; d < 9216; d += 256) {                        // = pack_w_dgrad_kernel
+        const int blk = d >> 9, r = d & 511, kc = r >> 8, n = (r & 255) >> 2, e = r & 3;
+        const int tap = blk >> 1, k8 = blk & 1, co = k8 * 8 + kc * 4 + e, ci = c * 64 + n;
+        float v = 0.f;
+        if (co < Cout && ci < Cin) v = __ldg(w + ((size_t)co * Cin + ci) * 9 + (8 - tap));
+        out[(size_t)c * 9216 + d] = tf32_rn(v);
+    }
+}
+
 struct FwdArgs {
     const float* in; const float* coef; const float* w; const float* bias; float* out; double* stats;
     int in_C, in_off, K, out_C, out_off, N, H, W, B, G, stats_C;
