@@ -218,35 +218,45 @@ static void for_each_dense(const NetPlan& P, F f) {
     for (int l = 0; l <= nd; ++l) for (const auto& d : P.down[l]) f(d);
     for (int i = 0; i < nd; ++i) for (const auto& d : P.up[i]) f(d);
 }
-static int pack_dense_weights_fwd(const Ctx& c) {
+// images: every DenseLayer + every 16-output-channel pass of the TransitionUp convolutions; tables of <= 112 entries per launch
+template <class K>
+static int pack_all(const Ctx& c, bool bwd, int per, int mode, K kern, unsigned char* region) {
+    const NetPlan& P = c.P;
     tcconv::PackTable T{};
-    T.mode = x3_mode(c.math);
-    const int per = T.mode == 1 ? 8 : 16;
-    bool fits = true;
-    for_each_dense(c.P, [&](const DenseLayerP& d) {
-        if (T.n >= 112) { fits = false; return; }
-        T.e[T.n++] = tcconv::PackEntry{d.conv.w, d.cin, d.conv.cout, T.total_chunks, d.wp_off};
-        T.total_chunks += cdiv(d.cin, per);
-    });
-    if (!fits) return ENDO_ERR_CONFIG;
-    ProfScope prof(PC_BN, c.s);
-    tcconv::pack_w_fwd_all_kernel<<<T.total_chunks, 256, 0, c.s>>>(c.params, reinterpret_cast<unsigned char*>(c.acts + c.P.wpack_off), T);
-    ENDO_CHECK_LAUNCH();
-    return ENDO_OK;
+    T.mode = mode;
+    auto flush = [&]() -> int {
+        if (T.n == 0) return ENDO_OK;
+        ProfScope prof(PC_BN, c.s);
+        kern<<<T.total_chunks, 256, 0, c.s>>>(c.params, region, T);
+        ENDO_CHECK_LAUNCH();
+        T.n = 0; T.total_chunks = 0;
+        return ENDO_OK;
+    };
+    int rc = ENDO_OK;
+    auto add = [&](long long w, int K_, int N_, long long out) {
+        if (rc != ENDO_OK) return;
+        if (T.n == 112) rc = flush();
+        T.e[T.n++] = tcconv::PackEntry{w, K_, N_, T.total_chunks, out};
+        T.total_chunks += cdiv(K_, per);
+    };
+    for_each_dense(P, [&](const DenseLayerP& d) { add(d.conv.w, d.cin, d.conv.cout, bwd ? d.wpb_off : d.wp_off); });
+    for (int i = 0; i < P.cfg.n_down; ++i) {
+        const TransUpP& t = P.tu[i];
+        if (t.conv.cout > 128) return ENDO_ERR_CONFIG;
+        for (int q = 0; q * 16 < t.conv.cout; ++q) {
+            const int n = (t.conv.cout - q * 16) < 16 ? (t.conv.cout - q * 16) : 16;
+            add(t.conv.w + (long long)q * 16 * t.cin * 9, t.cin, n, bwd ? t.wpb_off[q] : t.wp_off[q]);
+        }
+    }
+    if (rc != ENDO_OK) return rc;
+    return flush();
+}
+static int pack_dense_weights_fwd(const Ctx& c) {
+    const int mode = x3_mode(c.math);
+    return pack_all(c, false, mode == 1 ? 8 : 16, mode, tcconv::pack_w_fwd_all_kernel, reinterpret_cast<unsigned char*>(c.acts + c.P.wpack_off));
 }
 static int pack_dense_weights_bwd(const Ctx& c) {
-    tcconv::PackTable T{};
-    bool fits = true;
-    for_each_dense(c.P, [&](const DenseLayerP& d) {
-        if (T.n >= 112) { fits = false; return; }
-        T.e[T.n++] = tcconv::PackEntry{d.conv.w, d.cin, d.conv.cout, T.total_chunks, d.wpb_off};
-        T.total_chunks += cdiv(d.cin, 64);
-    });
-    if (!fits) return ENDO_ERR_CONFIG;
-    ProfScope prof(PC_BN, c.s);
-    tcconv::pack_w_dgrad_all_kernel<<<T.total_chunks, 256, 0, c.s>>>(c.params, reinterpret_cast<unsigned char*>(c.scratch + c.P.wpack_bwd_off), T);
-    ENDO_CHECK_LAUNCH();
-    return ENDO_OK;
+    return pack_all(c, true, 64, 0, tcconv::pack_w_dgrad_all_kernel, reinterpret_cast<unsigned char*>(c.scratch + c.P.wpack_bwd_off));
 }
 
 static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
@@ -610,14 +620,8 @@ static int trans_up_fwd(const Ctx& c, int i) {
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = a.K; f.out_C = a.out_C; f.out_off = a.out_off + co0;
             f.N = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
             f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.up = 1; f.dbg = 0; f.one = 0;
-            f.wpack = c.WPACK(); f.x3 = x3_mode(c.math); f.partial = nullptr; f.ksplit = 1; f.pixels = 0;
-            {
-                ProfScope prof(PC_BN, c.s);
-                if (f.x3 == 1) tcconv::pack_w_fwd_x3_kernel<<<cdiv(f.K, 8), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
-                else if (f.x3 == 2) tcconv::pack_w_fwd_b3_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, reinterpret_cast<uint32_t*>(c.WPACK()));
-                else tcconv::pack_w_fwd_kernel<<<cdiv(f.K, 16), 256, 0, c.s>>>(f.w, f.K, f.N, c.WPACK());
-                ENDO_CHECK_LAUNCH();
-            }
+            f.x3 = x3_mode(c.math); f.partial = nullptr; f.ksplit = 1; f.pixels = 0;
+            f.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + t.wp_off[co0 / 16]);    // packed by pack_dense_weights_fwd()
             dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
             ProfScope prof(PC_CONV_TRANS_FWD, c.s);
             tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(f);
@@ -697,12 +701,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
             q.C = P.Ctot[l]; q.out_off = co0; q.Cout = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16; q.in_off = 0; q.Cin = t.cin;
             q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
             q.plain = 1; q.first = co0 == 0; q.oC = t.cin; q.o_off = 0; q.po = tmp;
-            q.wpack = c.WPACK_BWD();
-            {
-                ProfScope prof(PC_BN, c.s);
-                tcconv::pack_w_dgrad_kernel<<<cdiv(q.Cin, 64), 256, 0, c.s>>>(q.w, q.Cin, q.Cout, c.WPACK_BWD());
-                ENDO_CHECK_LAUNCH();
-            }
+            q.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + t.wpb_off[co0 / 16]);   // packed by pack_dense_weights_bwd()
             dim3 grid(cdiv(q.W, tcconv::TW) * cdiv(q.H, tcconv::TH), 1, q.B);
             ProfScope prof(PC_DGRAD_TRANS, c.s);
             tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(q);
@@ -779,7 +778,7 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
         a.stats = c.ST(0); a.stats_C = P.Ctot[0];
         ENDO_TRY((launch_conv<3, 2, 48, 8, LM_NCHW, EM_STORE, WM_FWD, false>(a, c.s)));
     }
-    if (is_tc(math) && !(tc_disable_mask() & 1)) ENDO_TRY(pack_dense_weights_fwd(c));
+    if (is_tc(math)) ENDO_TRY(pack_dense_weights_fwd(c));
     for (int l = 0; l < nd; ++l) {                           // models.py:175-178
         for (const auto& d : P.down[l]) ENDO_TRY(dense_layer_fwd(c, d));
         ENDO_TRY(trans_down_fwd(c, l));
@@ -834,7 +833,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
             g_y, pre, c.X(0), params + P.final_.w, c.GX(0), g_params + P.final_.w, g_params + P.final_.b, npix, P.Ctot[0], ppc);
         ENDO_CHECK_LAUNCH();
     }
-    if (is_tc(math) && !(tc_disable_mask() & 2)) ENDO_TRY(pack_dense_weights_bwd(c));
+    if (is_tc(math)) ENDO_TRY(pack_dense_weights_bwd(c));
     for (int i = nd - 1; i >= 0; --i) {
         for (int j = (int)P.up[i].size() - 1; j >= 0; --j) ENDO_TRY(dense_layer_bwd(c, P.up[i][j]));
         ENDO_TRY(trans_up_bwd(c, i));

@@ -31,7 +31,8 @@ struct BnP { long long gamma, beta; long long rmean, rvar; int c; long long coef
 struct DenseLayerP { BnP bn; ConvP conv; int level, in_off, cin, out_off;
                      long long wp_off, wpb_off; };   // byte offsets of this layer's tensor-core weight images inside the wpack / wpack_bwd regions
 struct TransDownP { BnP bn; ConvP conv; int level; long long argmax; };                 // argmax: byte offset in acts
-struct TransUpP { ConvP conv; int src_level, src_off, cin, dst_level; };
+struct TransUpP { ConvP conv; int src_level, src_off, cin, dst_level;
+                  long long wp_off[8], wpb_off[8]; };   // weight images of the 16-output-channel passes (cout <= 128)
 
 struct NetPlan {
     endo_net_config cfg;
@@ -184,6 +185,8 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         auto slot = [&](DenseLayerP& d) { d.wp_off = sz; sz += 9216ll * ((d.cin + 7) / 8); };
         for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) slot(d);
         for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) slot(d);
+        for (int i = 0; i < nd; ++i)
+            for (int q = 0; q < 8; ++q) { P.tu[i].wp_off[q] = sz; if (q * 16 < P.tu[i].conv.cout) sz += 9216ll * ((P.tu[i].cin + 7) / 8); }
         P.wpack_off = off; off = align_up(off + sz, 256);
     }
     {
@@ -206,6 +209,8 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         auto slot = [&](DenseLayerP& d) { d.wpb_off = sz; sz += 36864ll * ((d.cin + 63) / 64); };
         for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) slot(d);
         for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) slot(d);
+        for (int i = 0; i < nd; ++i)
+            for (int q = 0; q < 8; ++q) { P.tu[i].wpb_off[q] = sz; if (q * 16 < P.tu[i].conv.cout) sz += 36864ll * ((P.tu[i].cin + 63) / 64); }
         P.wpack_bwd_off = off; off = align_up(off + sz, 256);
     }
     P.scratch_bytes = off;
