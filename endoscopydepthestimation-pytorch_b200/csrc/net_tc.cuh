@@ -64,56 +64,17 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
     return r;
 }
 
-// Weight images: the exact shared-memory layout of one pipeline stage, built once per layer call by a tiny kernel so
+// Weight images: the exact shared-memory layout of one pipeline stage, built once per pass for ALL layers by
+// pack_w_fwd_all_kernel / pack_w_dgrad_all_kernel (the 1x1 fall-back path packs per layer) so
 // that the producers copy them with coalesced 128-bit loads (staging OIHW weights with scalar, serialised loads cost
 // more than the activation stream in the first version of these kernels).
 //   forward : chunk c (16 input channels) -> [blk = ky*2 + k8][kc][n = kx*16 + co][4]           2304 floats
 //   dgrad   : chunk c (64 input channels) -> [blk = tap*2 + k8][kc][n = ci - 64c][4], taps flipped 9216 floats
-__global__ void __launch_bounds__(256)
-pack_w_fwd_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ out) {
-    const int c = blockIdx.x;
-    for (int d = threadIdx.x; d < 2304; d += 256) {
-        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
-        const int ky = blk >> 1, k8 = blk & 1, co = n & 15, kx = n >> 4, cin = c * 16 + k8 * 8 + kc * 4 + e;
-        float v = 0.f;
-        if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
-        out[(size_t)c * 2304 + d] = tf32_rn(v);
-    }
-}
-__global__ void __launch_bounds__(256)
-pack_w_dgrad_kernel(const float* __restrict__ w, int Cin, int Cout, float* __restrict__ out) {
-    const int c = blockIdx.x;
-    for (int d = threadIdx.x; d < 9216; d += 256) {
-        const int blk = d >> 9, r = d & 511, kc = r >> 8, n = (r & 255) >> 2, e = r & 3;
-        const int tap = blk >> 1, k8 = blk & 1, co = k8 * 8 + kc * 4 + e, ci = c * 64 + n;
-        float v = 0.f;
-        if (co < Cout && ci < Cin) v = __ldg(w + ((size_t)co * Cin + ci) * 9 + (8 - tap));
-        out[(size_t)c * 9216 + d] = tf32_rn(v);
-    }
-}
 
 // 3xTF32 (error-compensated, fp32-grade) variants: a chunk holds 8 input channels.  x = hi + lo with hi = x rounded to tf32;
 // x*w = hi*hi + (lo*w + x*lo_w) + O(2^-24): block (ky, 0) carries the tf32 hi weights for ONE kind::tf32 MMA (K = 8), block
 // (ky, 1) the bf16 pair [w (8 channels) ; w - hi (8 channels)] for ONE kind::f16 MMA of K = 16 that adds BOTH cross terms
 // against the activation planes [lo ; x] (the cross terms are 2^-12 of the product, so 8-bit operands keep them to 2^-21).
-__global__ void __launch_bounds__(256)
-pack_w_fwd_x3_kernel(const float* __restrict__ w, int K, int N, float* __restrict__ out) {
-    const int c = blockIdx.x;
-    for (int d = threadIdx.x; d < 2304; d += 256) {
-        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
-        const int ky = blk >> 1, part = blk & 1, co = n & 15, kx = n >> 4, cin = c * 8 + kc * 4 + e;
-        float v = 0.f;
-        if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
-        if (part == 0) { out[(size_t)c * 2304 + d] = tf32_hi(v); continue; }
-        // bf16 block: [kc][n][8 bf16]; word e holds channels 2e, 2e + 1 of the chunk; kc = 0: w, kc = 1: w - hi
-        const int c0 = c * 8 + 2 * e;
-        float w0 = 0.f, w1 = 0.f;
-        if (co < N && c0 < K) w0 = __ldg(w + (((size_t)co * K + c0) * 3 + ky) * 3 + kx);
-        if (co < N && c0 + 1 < K) w1 = __ldg(w + (((size_t)co * K + c0 + 1) * 3 + ky) * 3 + kx);
-        if (kc) { w0 -= tf32_hi(w0); w1 -= tf32_hi(w1); }
-        out[(size_t)c * 2304 + d] = __uint_as_float(bf16x2_rn(w0, w1));
-    }
-}
 __global__ void __launch_bounds__(256)
 pack_w_1x1_x3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* __restrict__ out) {
     const int c = blockIdx.x;
@@ -140,20 +101,6 @@ __device__ __forceinline__ uint32_t bf16_split(float lo, float hi, float& rlo, f
     rlo = lo - __uint_as_float(p << 16);
     rhi = hi - __uint_as_float(p & 0xFFFF0000u);
     return p;
-}
-__global__ void __launch_bounds__(256)
-pack_w_fwd_b3_kernel(const float* __restrict__ w, int K, int N, uint32_t* __restrict__ out) {
-    const int c = blockIdx.x;
-    for (int d = threadIdx.x; d < 2304; d += 256) {
-        const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
-        const int ky = blk >> 1, term = blk & 1, co = n & 15, kx = n >> 4, cin = c * 16 + kc * 8 + e * 2;
-        float v0 = 0.f, v1 = 0.f;
-        if (co < N && cin < K) v0 = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
-        if (co < N && cin + 1 < K) v1 = __ldg(w + (((size_t)co * K + cin + 1) * 3 + ky) * 3 + kx);
-        float r0, r1;
-        const uint32_t b1 = bf16_split(v0, v1, r0, r1);
-        out[(size_t)c * 2304 + d] = term ? bf16x2_rn(r0, r1) : b1;
-    }
 }
 __global__ void __launch_bounds__(256)
 pack_w_1x1_b3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, uint32_t* __restrict__ out) {
@@ -266,12 +213,12 @@ pack_w_fwd_all_kernel(const float* __restrict__ params, unsigned char* __restric
         const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
         const int ky = blk >> 1, part = blk & 1, co = n & 15, kx = n >> 4;
         float res;
-        if (T.mode == 0) {                                                 // = pack_w_fwd_kernel
+        if (T.mode == 0) {                                                 // plain tf32: 16 input channels per chunk, block (ky, k8)
             const int cin = c * 16 + part * 8 + kc * 4 + e;
             float v = 0.f;
             if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
             res = tf32_rn(v);
-        } else if (T.mode == 1 && part == 0) {                             // = pack_w_fwd_x3_kernel, tf32 hi block
+        } else if (T.mode == 1 && part == 0) {                             // 3xTF32: tf32 hi block of the 8-channel chunk
             const int cin = c * 8 + kc * 4 + e;
             float v = 0.f;
             if (co < N && cin < K) v = __ldg(w + (((size_t)co * K + cin) * 3 + ky) * 3 + kx);
@@ -301,7 +248,7 @@ pack_w_dgrad_all_kernel(const float* __restrict__ params, unsigned char* __restr
     const int c = blockIdx.x - E.chunk0, Cin = E.K, Cout = E.N;
     const float* w = params + E.w;
     float* out = reinterpret_cast<float*>(wpack + E.out);
-    for (int d = threadIdx.x; d < 9216; d += 256) {                        // = pack_w_dgrad_kernel
+    for (int d = threadIdx.x; d < 9216; d += 256) {                        // chunk c (64 input channels) -> [blk = tap*2 + k8][kc][n = ci - 64c][4], taps flipped
         const int blk = d >> 9, r = d & 511, kc = r >> 8, n = (r & 255) >> 2, e = r & 3;
         const int tap = blk >> 1, k8 = blk & 1, co = k8 * 8 + kc * 4 + e, ci = c * 64 + n;
         float v = 0.f;
@@ -316,7 +263,7 @@ struct FwdArgs {
     int up;      // 0: operand = relu(bn(x)) of the same-resolution buffer (DenseLayer); 1: operand = x of the half-resolution
                  //    buffer, nearest-upsampled x2, no BatchNorm (TransitionUp, models.py:73-74)
     int dbg;     // performance experiments only (ENDO_TC_DEBUG): 1 = skip the MMAs, 2 = skip the activation loads
-    const float* wpack;   // weight image built by pack_w_fwd_kernel (2304 floats per 16-channel chunk)
+    const float* wpack;   // weight image built by pack_w_fwd_all_kernel (2304 floats per chunk)
     int one;              // 1: 1x1 convolution, N <= 48 plain output channels, epilogue = + bias, store (no taps, no statistics)
     float* partial; int ksplit; long long pixels;   // split-K (not with `one`): [ksplit][B*H*W][16] raw partial sums, else nullptr
     int x3;               // 1: 3xTF32 -- a stage holds 8 channels as planes (tf32 hi0, hi1; bf16 lo; bf16 x): D += [lo;x]*[w;wlo] + hi*whi
@@ -800,7 +747,7 @@ struct Args {
     const float* g; const float* x; const float* ab;      // gradient buffer, activation buffer, lazy correction [G][C][2]
     const float* coef;                                    // this BN's (a, beta, mean, invstd) [G][Cin][4]
     const float* w;                                       // OIHW [Cout][Cin][3][3]
-    const float* wpack;                                   // weight image built by pack_w_dgrad_kernel (9216 floats per 64-channel chunk)
+    const float* wpack;                                   // weight image built by pack_w_dgrad_all_kernel (9216 floats per 64-channel chunk)
     float* gout;                                          // gradient buffer (same as g), accumulated at in_off..in_off+Cin
     float* db;                                            // conv bias gradient [Cout] (sum of the output gradient), accumulated
     double* red; int red_C;                               // [G][red_C][2] BN backward sums
