@@ -108,6 +108,33 @@ def require_cuda(*tensors):
             raise RuntimeError("endo_b200 expects float32 tensors, got " + str(t.dtype))
 
 
+def on_device(fn):
+    """Run a Function.forward / backward with the CUDA device of its first tensor argument current: the library
+    configures per-device kernel attributes lazily for the CURRENT device and borrows its side stream from it
+    (include/endo_b200.h), so a model on cuda:1 must not be driven while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(ctx, *args):
+        dev = next((a.device for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if dev is None:
+            dev = next((t.device for t in getattr(ctx, "saved_tensors", ()) if t.is_cuda), None)
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapper
+
+
+def same_shape(what, ref, *others):
+    """Raise (instead of reading out of bounds) when an operand does not have the reference tensor's shape; the
+    reference's eager ops would broadcast or reject such inputs."""
+    for name, t, shape in others:
+        if tuple(t.shape) != tuple(shape):
+            raise RuntimeError(f"{what}: `{name}` must have shape {tuple(shape)}, got {tuple(t.shape)} "
+                               f"(reference tensor: {tuple(ref.shape)})")
+
+
 def contig(t):
     return t if t.is_contiguous() else t.contiguous()
 

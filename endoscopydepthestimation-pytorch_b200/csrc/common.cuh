@@ -38,6 +38,21 @@ struct ProfScope {
         }                                                           \
     } while (0)
 
+// The opt-in for > 48 KB of dynamic shared memory is a PER-DEVICE function attribute: remember per device (bit mask over
+// the current device ordinal; the header requires the current device to be the one that owns `stream`) which kernels
+// have been configured.  Benign race: two threads may both set the same attribute to the same value.
+#define ENDO_SET_MAX_SMEM(kern, bytes)                                                                     \
+    do {                                                                                                   \
+        static unsigned long long endo_cfg_mask_ = 0ull;                                                   \
+        int endo_dev_ = 0;                                                                                 \
+        ENDO_CUDA(cudaGetDevice(&endo_dev_));                                                              \
+        if (endo_dev_ < 0 || endo_dev_ >= 64) return ENDO_ERR_NO_DEVICE;                                   \
+        if (!((endo_cfg_mask_ >> endo_dev_) & 1ull)) {                                                     \
+            ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            endo_cfg_mask_ |= 1ull << endo_dev_;                                                           \
+        }                                                                                                  \
+    } while (0)
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

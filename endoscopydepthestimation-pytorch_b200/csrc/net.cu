@@ -2,6 +2,8 @@
 // PyTorch derives from it), fp32 FFMA path.  Host side: walks the NetPlan and enqueues the kernels of
 // net_kernels.cuh on the caller's stream; no allocation, no synchronisation.
 #include <cstdlib>
+#include <mutex>
+#include <vector>
 #include "net_kernels.cuh"
 #include "net_plan.cuh"
 #include "net_tc.cuh"
@@ -13,12 +15,8 @@ namespace endo {
 template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP, int KCT = KC, int MINB = 1>
 static int launch_conv(const ConvArgs& a, cudaStream_t s) {
     constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW, KCT>();
-    static bool configured = false;
     auto kern = conv_kernel<KS, PX, CO, NW, LM, EM, WM, UP, KCT, MINB>;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(kern, (int)smem);
     const int tiles = cdiv(a.ow, 32) * cdiv(a.oh, NW * PX);
     dim3 grid(tiles, cdiv(a.N, CO), a.B);
     ProfScope prof(WM == WM_DGRAD ? ((LM == LM_GRADPOOL || EM == EM_DGRAD_UP) ? PC_DGRAD_TRANS : PC_DGRAD)
@@ -33,12 +31,8 @@ template <int PX, int CO>
 static int launch_conv_pf(const ConvArgs& a, cudaStream_t s) {
     constexpr size_t base = conv_smem_bytes<3, PX, CO, 4, 4>();
     constexpr int kMaxK = 1536;
-    static bool configured = false;
     auto kern = conv_kernel<3, PX, CO, 4, LM_BNRELU, EM_STORE, WM_FWD, false, 4, 3, true>;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(base + 16 * kMaxK)));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(kern, (int)(base + 16 * kMaxK));
     if (a.K > kMaxK) return ENDO_ERR_BAD_SHAPE;
     dim3 grid(cdiv(a.ow, 32) * cdiv(a.oh, 4 * PX), cdiv(a.N, CO), a.B);
     ProfScope prof(PC_CONV_DENSE_FWD, s);
@@ -50,12 +44,8 @@ static int launch_conv_pf(const ConvArgs& a, cudaStream_t s) {
 template <int KS, int PX, int CO, int NW, int LM>
 static int launch_conv_splitk(const ConvArgs& a, cudaStream_t s) {
     constexpr size_t smem = conv_smem_bytes<KS, PX, CO, NW>();
-    static bool configured = false;
     auto kern = conv_kernel<KS, PX, CO, NW, LM, EM_PARTIAL, WM_FWD, false>;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(kern, (int)smem);
     dim3 grid(cdiv(a.ow, 32) * cdiv(a.oh, NW * PX), a.ksplit, a.B);
     ProfScope prof(PC_CONV_DENSE_FWD, s);
     kern<<<grid, NW * 32, smem, s>>>(a);
@@ -66,12 +56,8 @@ static int launch_conv_splitk(const ConvArgs& a, cudaStream_t s) {
 template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
 static int launch_wgrad(WgradArgs a, cudaStream_t s) {
     constexpr size_t smem = wgrad_smem_bytes<KS, CW, NCG>();
-    static bool configured = false;
     auto kern = wgrad_kernel<KS, CW, NCG, NPS, LMA, LMG, UP>;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(kern, (int)smem);
     const int ychunks = cdiv(a.a_K, 32), zchunks = cdiv(a.g_K, CW * NCG);
     a.n_tiles = a.B * cdiv(a.oh, 8) * cdiv(a.ow, 32);
     int want = (3 * kNumSMs) / (ychunks * zchunks);
@@ -89,12 +75,8 @@ template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
 static int launch_wgrad2(WgradArgs a, cudaStream_t s) {
     if (a.G > 2) return launch_wgrad<KS, CW, NCG, NPS, LMA, LMG, UP>(a, s);     // coefficient cache holds two statistic groups
     constexpr size_t smem = wgrad2_smem_bytes<KS, CW, NCG>();
-    static bool configured = false;
     auto kern = wgrad2_kernel<KS, CW, NCG, NPS, LMA, LMG, UP>;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(kern, (int)smem);
     const int ychunks = cdiv(a.a_K, 32), zchunks = cdiv(a.g_K, CW * NCG);
     a.n_tiles = a.B * cdiv(a.oh, 8) * cdiv(a.ow, 32);
     int want = (2 * kNumSMs) / (ychunks * zchunks);
@@ -125,23 +107,50 @@ static inline bool is_tc(int math) { return math == ENDO_MATH_TF32 || math == EN
 static inline int x3_mode(int math) { return math == ENDO_MATH_TF32X3 ? 1 : (math == ENDO_MATH_BF16X3 ? 2 : 0); }
 
 // Weight-gradient kernels only feed the optimiser, and a layer's weight gradient is independent of the same layer's data
-// gradient: they are enqueued on a per-device side stream (forked from / joined to the caller's stream with events) so that
+// gradient: they are enqueued on a side stream (forked from / joined to the caller's stream with events) so that
 // the CTAs of one kernel fill the SMs the other leaves idle in its last wave and prologue (every tensor-core kernel here
-// occupies a whole SM per CTA; 5-30 % of a launch is tail).  ENDO_TC_DISABLE bit 8192 keeps everything on one stream.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool ok = false; };
-static SideStream* side_stream() {
-    static SideStream tab[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    SideStream& t = tab[dev];
-    if (!t.ok) {
-        if (cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        t.ok = true;
+// occupies a whole SM per CTA; 5-30 % of a launch is tail).  ENDO_NET_SINGLE_STREAM (math flag) or ENDO_TC_DISABLE bit 8192
+// keeps everything on the caller's stream.
+//
+// Re-entrancy: a call BORROWS a (stream, fork event, join event) triple from a per-device pool for the duration of its
+// host-side enqueue and returns it on every exit path (SideLease), after recording the join; concurrent callers (other host
+// threads / streams) get different triples, so nobody re-records an event another caller is about to wait on.  Re-use by a
+// LATER call is safe: cudaStreamWaitEvent captures the event's most recent record at the time of the call.  The triples are
+// created on first use (not during stream capture: run one warm-up step before capturing a CUDA graph) and live until exit.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static std::mutex g_side_mu;
+static std::vector<SideStream*> g_side_free[64];
+static SideStream* side_acquire(int dev) {
+    {
+        std::lock_guard<std::mutex> lk(g_side_mu);
+        auto& v = g_side_free[dev];
+        if (!v.empty()) { SideStream* t = v.back(); v.pop_back(); return t; }
     }
-    return &t;
+    SideStream* t = new SideStream();
+    if (cudaStreamCreateWithFlags(&t->s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (t->fork) cudaEventDestroy(t->fork);
+        if (t->s) cudaStreamDestroy(t->s);
+        delete t;
+        return nullptr;
+    }
+    return t;
 }
+// joins the side stream into the caller's stream and returns the triple to the pool when it goes out of scope
+struct SideLease {
+    SideStream* t = nullptr; int dev = 0; cudaStream_t caller = nullptr; bool forked = false;
+    ~SideLease() {
+        if (!t) return;
+        if (forked) {           // every exit path: the caller's stream waits for whatever was enqueued on the side stream
+            if (cudaEventRecord(t->join, t->s) != cudaSuccess || cudaStreamWaitEvent(caller, t->join, 0) != cudaSuccess)
+                cudaGetLastError();
+        }
+        std::lock_guard<std::mutex> lk(g_side_mu);
+        g_side_free[dev].push_back(t);
+    }
+};
 
 struct Ctx {
     const NetPlan& P;
@@ -152,11 +161,13 @@ struct Ctx {
     int math;
     cudaStream_t sw = nullptr;        // stream of the weight-gradient kernels (== s when the side stream is off)
     cudaEvent_t ev_fork = nullptr;
+    SideLease* lease = nullptr;
     // everything enqueued on s so far happens-before what is enqueued on sw from now on
     int fork() const {
         if (sw == s) return ENDO_OK;
         ENDO_CUDA(cudaEventRecord(ev_fork, s));
         ENDO_CUDA(cudaStreamWaitEvent(sw, ev_fork, 0));
+        lease->forked = true;
         return ENDO_OK;
     }
     float* X(int l) const { return reinterpret_cast<float*>(acts + P.x_off[l]); }
@@ -191,11 +202,7 @@ static ConvArgs base_args(const Ctx& c) {
 }
 
 static int launch_pw(const tcpw::Args& a, int G, cudaStream_t s, int cat) {
-    static bool configured = false;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(tcpw::pw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(tcpw::pw_gemm_kernel, 227 * 1024);
     const size_t smem = tcpw::smem_bytes(a.Npad, a.K, a.mode);
     if (smem > 227 * 1024) return ENDO_ERR_CONFIG;
     dim3 grid(cdiv(a.per_group, tcpw::MT), G, 1);
@@ -276,12 +283,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask(); t.one = 0;
         t.x3 = x3_mode(c.math);
         t.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + d.wp_off);   // packed by pack_dense_weights_fwd()
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcconv::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcconv::dense_fwd_tf32_kernel, tcconv::SMEM_BYTES);
         // Low-resolution levels: a CTA per 32x32 tile over ALL input channels leaves most SMs idle behind a long serial
         // channel loop.  Split the channel chunks over blockIdx.y (raw partial sums to scratch, splitk_finish_kernel adds
         // the slices in a fixed order, then bias + statistics): pick the slice count that minimises waves x chunks.
@@ -386,12 +388,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         if (want < 1) want = 1;
         if (want > t.n_tiles) want = t.n_tiles;
         t.tiles_per_cta = cdiv(t.n_tiles, want);
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcwgrad::dense_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcwgrad::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcwgrad::dense_wgrad_bf16_kernel, tcwgrad::SMEM_BYTES);
         dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
         ProfScope prof(PC_WGRAD, c.sw);
         tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(t);
@@ -416,12 +413,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         t.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + d.wpb_off);   // packed by pack_dense_weights_bwd()
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcdgrad::dense_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcdgrad::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcdgrad::dense_dgrad_tf32_kernel, tcdgrad::SMEM_BYTES);
         const int tiles = cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH);
         const int ysplit = (tiles * t.B < 4 * kNumSMs && !(tc_disable_mask() & 128)) ? cdiv(t.Cin, tcdgrad::NC) : 1;
         dim3 grid(tiles, ysplit, t.B);
@@ -457,12 +449,7 @@ static int trans_down_fwd(const Ctx& c, int l) {
     a.argmax_out = reinterpret_cast<unsigned char*>(c.acts + t.argmax);
     if (is_tc(c.math) && !(tc_disable_mask() & 64) && cs <= 128 * tcconv::POOL_MAXQ) {
         // tcgen05: 1x1 convolution in passes of 48 output channels into a scratch tensor, then one HBM-bound pooling pass
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcconv::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcconv::dense_fwd_tf32_kernel, tcconv::SMEM_BYTES);
         float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
         const int npad = (cs + 15) / 16 * 16;
         const bool pw = npad <= 512 && !(tc_disable_mask() & 512);
@@ -527,12 +514,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
     if (is_tc(c.math) && !(tc_disable_mask() & 32)) {
         // tcgen05 (bf16): the weight-gradient kernel in 1x1 mode, 48 output channels per launch; bias gradient = sum of the
         // routed (= of the pooled) gradient, reduced over the coarse buffer
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcwgrad::dense_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcwgrad::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcwgrad::dense_wgrad_bf16_kernel, tcwgrad::SMEM_BYTES);
         {
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
             bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.sw>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
@@ -608,12 +590,7 @@ static int trans_up_fwd(const Ctx& c, int i) {
     a.stats = c.ST(l); a.stats_C = P.Ctot[l];
     if (is_tc(c.math) && !(tc_disable_mask() & 8)) {
         // tcgen05: the DenseLayer forward kernel with the upsampling loader, 16 output channels per pass
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcconv::dense_fwd_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcconv::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcconv::dense_fwd_tf32_kernel, tcconv::SMEM_BYTES);
         for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
             tcconv::FwdArgs f;
             f.in = a.in; f.coef = nullptr; f.w = a.w + (size_t)co0 * t.cin * 9; f.bias = a.bias + co0; f.out = a.out; f.stats = a.stats;
@@ -648,12 +625,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
     if (is_tc(c.math) && !(tc_disable_mask() & 16)) {
         // tcgen05 (bf16): the DenseLayer weight-gradient kernel with the upsampling loader, 16 output channels per pass;
         // the bias gradient comes from the small dedicated reduction
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcwgrad::dense_wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcwgrad::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcwgrad::dense_wgrad_bf16_kernel, tcwgrad::SMEM_BYTES);
         if (!dgrad_tc) {                                  // otherwise the data-gradient passes below produce the bias gradient
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
             bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.sw>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
@@ -685,12 +657,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
         // tcgen05 (tf32): the DenseLayer data-gradient kernel in plain mode, 16 output-gradient channels per pass, raw result
         // into the (now idle) forward scratch tensor at full resolution; then the 2x2 fold into the half-resolution buffer
         float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
-        static bool configured = false;
-        if (!configured) {
-            ENDO_CUDA(cudaFuncSetAttribute(tcdgrad::dense_dgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           tcdgrad::SMEM_BYTES));
-            configured = true;
-        }
+        ENDO_SET_MAX_SMEM(tcdgrad::dense_dgrad_tf32_kernel, tcdgrad::SMEM_BYTES);
         for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
             tcdgrad::Args q{};
             q.g = c.GX(l); q.x = c.X(l); q.ab = c.AB(l); q.coef = nullptr; q.w = c.params + t.conv.w + (size_t)co0 * t.cin * 9;
@@ -755,7 +722,8 @@ extern "C" size_t endo_net_backward_scratch_bytes(const endo_net_config* cfg, in
 
 extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const float* params, float* bn_buffers,
                             float* y, void* acts, size_t acts_bytes, int B, int H, int W, int groups, int training,
-                            int math, endo_stream_t stream) {
+                            int math_and_flags, endo_stream_t stream) {
+    const int math = math_and_flags & ENDO_MATH_MASK;
     if (math != ENDO_MATH_FP32 && !is_tc(math)) return ENDO_ERR_CONFIG;
     if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
     if (!x || !params || !bn_buffers || !y || !acts) return ENDO_ERR_BAD_POINTER;
@@ -801,8 +769,9 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
 
 extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const float* x, const float* params,
                             float* g_params, float* g_x, void* acts, size_t acts_bytes, void* scratch,
-                            size_t scratch_bytes, int B, int H, int W, int groups, int accumulate, int math,
+                            size_t scratch_bytes, int B, int H, int W, int groups, int accumulate, int math_and_flags,
                             endo_stream_t stream) {
+    const int math = math_and_flags & ENDO_MATH_MASK, flags = math_and_flags & ~ENDO_MATH_MASK;
     if (math != ENDO_MATH_FP32 && !is_tc(math)) return ENDO_ERR_CONFIG;
     if (groups != 1 && groups != 2) return ENDO_ERR_CONFIG;
     if (g_x != nullptr) return ENDO_ERR_CONFIG;              // train.py never differentiates w.r.t. the images
@@ -816,9 +785,16 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
     if (acts_bytes < (size_t)P.acts_bytes || scratch_bytes < (size_t)P.scratch_bytes) return ENDO_ERR_WORKSPACE;
     if (P.Ctot[0] > 384) return ENDO_ERR_CONFIG;
     Ctx c{P, static_cast<char*>(acts), static_cast<char*>(scratch), params, g_params, nullptr, (cudaStream_t)stream, 1, math};
-    SideStream* side = (tc_disable_mask() & 8192) ? nullptr : side_stream();
-    c.sw = side ? side->s : c.s;
-    c.ev_fork = side ? side->fork : nullptr;
+    SideLease lease;                                         // joined + returned to the pool on every exit path
+    if (!(flags & ENDO_NET_SINGLE_STREAM) && !(tc_disable_mask() & 8192)) {
+        int dev = 0;
+        ENDO_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64) return ENDO_ERR_NO_DEVICE;
+        lease.t = side_acquire(dev); lease.dev = dev; lease.caller = c.s;
+    }
+    c.sw = lease.t ? lease.t->s : c.s;
+    c.ev_fork = lease.t ? lease.t->fork : nullptr;
+    c.lease = &lease;
     const int nd = cfg->n_down;
     // gradient buffers of levels >= 1, the lazy-correction arrays and the BN sums start at zero; the level-0
     // gradient buffer (the largest) is fully written by the finalConv backward and needs no clearing
@@ -858,11 +834,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
             ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.sw)));
         }
     }
-    if (c.sw != c.s) {                                       // join: the caller's stream waits for the weight gradients
-        ENDO_CUDA(cudaEventRecord(side->join, c.sw));
-        ENDO_CUDA(cudaStreamWaitEvent(c.s, side->join, 0));
-    }
-    return ENDO_OK;
+    return ENDO_OK;                                          // ~SideLease: the caller's stream waits for the weight gradients
 }
 
 extern "C" int endo_debug_trace_read(long long* host_out, int n) {

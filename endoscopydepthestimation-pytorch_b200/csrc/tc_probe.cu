@@ -122,11 +122,7 @@ extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_row
     if (rotate > 1 && rotate * N > 512) return ENDO_ERR_BAD_SHAPE;
     const size_t smem = ((size_t)a_rows * K * es + 1023) / 1024 * 1024 + (size_t)N * K * es + 2048;
     if (smem > 200 * 1024) return ENDO_ERR_BAD_SHAPE;
-    static bool configured = false;
-    if (!configured) {
-        ENDO_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    ENDO_SET_MAX_SMEM(tc_probe_kernel, 200 * 1024);
     ProbeArgs p{A, B, D, a_rows, N, K, shift, fmt, a_mn_major, b_mn_major, swizzle, reps, cycles, rotate};
     tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
     ENDO_CHECK_LAUNCH();

@@ -51,5 +51,9 @@ def broadcast_parameters(net, src=0, group=None):
     """Make every rank start from rank `src`'s weights and BN buffers (DataParallel replicates each forward)."""
     if dist.get_world_size(group) == 1:
         return
+    if net.flat_params is None:
+        net.materialize()                      # the flat arrays are otherwise built by the first forward
     dist.broadcast(net.flat_params, src=src, group=group)
     dist.broadcast(net._flat_buf, src=src, group=group)
+    for t in (net._nbt or ()):                 # num_batches_tracked (int64 counters kept by the host wrapper)
+        dist.broadcast(t, src=src, group=group)

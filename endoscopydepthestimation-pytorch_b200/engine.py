@@ -87,6 +87,7 @@ class _NetFn(torch.autograd.Function):
     the graph; parameter gradients are written straight into the module's flat gradient bucket."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, x, anchor, net, groups):
         lib = L.lib()
         b, _, h, w = x.shape
@@ -102,16 +103,26 @@ class _NetFn(torch.autograd.Function):
                                  y.data_ptr(), acts.data_ptr(), acts.numel(), b, h, w, groups, training,
                                  net._math, L.stream_ptr(x.device)), "net_fwd")
         ctx.net, ctx.acts, ctx.groups, ctx.training = net, acts, groups, training
+        ctx.param_version = net._flat._version
         if getattr(net, "_debug_keep_acts", False):
             net._debug_acts = acts
         ctx.save_for_backward(x)
         return y
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_y):
         net = ctx.net
         if not ctx.training:
             raise RuntimeError("FCDenseNet backward is only defined in training mode (BatchNorm batch statistics)")
+        # deviations from the nn.Module autograd contract are errors, not silent differences (the parameter gradients are
+        # written straight into the flat bucket, outside autograd's own accumulation)
+        if ctx.acts is None:
+            raise RuntimeError("FCDenseNet: second backward through the same forward (retain_graph) is not supported: "
+                               "the saved activations are released after the first backward")
+        if net._flat._version != ctx.param_version:
+            raise RuntimeError("FCDenseNet: parameters were modified in place between forward and backward "
+                               "(the backward would differentiate a different function than the forward computed)")
         (x,) = ctx.saved_tensors
         lib = L.lib()
         b, _, h, w = x.shape
@@ -227,6 +238,19 @@ class FCDenseNet(nn.Module):
         self._anchor = torch.zeros((), dtype=torch.float32, device=device, requires_grad=True)
         self._flat_ok = True
 
+    def materialize(self, device=None):
+        """Build the flat parameter / gradient / buffer arrays now (they are otherwise built by the first CUDA forward);
+        needed before anything touches `flat_params` -- e.g. `ddp.broadcast_parameters` -- ahead of the first step."""
+        if device is None:
+            device = next(self.parameters()).device
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("endo_b200.FCDenseNet lives on CUDA devices only (move it with .cuda() first)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._ensure_flat(device)
+        return self
+
     def _ensure_flat(self, device):
         ok = self._flat_ok and self._flat.device == device
         if ok:   # cheap sanity check that nobody re-allocated the parameters behind our back
@@ -277,6 +301,10 @@ class FCDenseNet(nn.Module):
         if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != self._cfg.in_channels:
             raise RuntimeError(f"expected a float32 [B,{self._cfg.in_channels},H,W] input, got {tuple(x.shape)} {x.dtype}")
         self._ensure_flat(x.device)
+        if self.training and torch.is_grad_enabled() and not all(p.requires_grad for p in self._params):
+            raise RuntimeError("endo_b200.FCDenseNet computes the gradient of EVERY parameter in one fused backward; "
+                               "frozen parameters (requires_grad=False) are not supported -- run under torch.no_grad() "
+                               "or leave them out of the optimiser instead")
         x = L.contig(x)
         if torch.is_grad_enabled() and self.training:
             y = _NetFn.apply(x, self._anchor, self, groups)

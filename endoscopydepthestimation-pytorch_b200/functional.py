@@ -9,13 +9,17 @@ import torch
 from . import _lib as L
 
 
-def _dims(t):
+def _dims(t, channels=1, what="input"):
+    if t.dim() != 4 or t.shape[1] != channels:
+        raise RuntimeError(f"{what}: expected a [B,{channels},H,W] tensor, got {tuple(t.shape)}")
     b, c, h, w = t.shape
     return b, h, w
 
 
-def _pose(t, r, k):
+def _pose(t, r, k, b, what):
     L.require_cuda(t, r, k)
+    L.same_shape(what, t, ("translation_vectors", t, (b, 3, 1)), ("rotation_matrices", r, (b, 3, 3)),
+                 ("intrinsic_matrices", k, (b, 3, 3)))
     return L.contig(t), L.contig(r), L.contig(k)
 
 
@@ -23,10 +27,12 @@ class DepthScaleFn(torch.autograd.Function):
     """DepthScalingLayer.forward (/root/reference/models.py:346-363)."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, depth, sparse_depth, sparse_mask, epsilon):
         L.require_cuda(depth, sparse_depth, sparse_mask)
+        b, h, w = _dims(depth, 1, "DepthScalingLayer")
+        L.same_shape("DepthScalingLayer", depth, ("sparse_depths", sparse_depth, depth.shape), ("sparse_masks", sparse_mask, depth.shape))
         depth, sparse_depth, sparse_mask = L.contig(depth), L.contig(sparse_depth), L.contig(sparse_mask)
-        b, h, w = _dims(depth)
         lib = L.lib()
         scaled = torch.empty_like(depth)
         norm_std = torch.empty((), dtype=torch.float32, device=depth.device)
@@ -43,6 +49,7 @@ class DepthScaleFn(torch.autograd.Function):
         return scaled, norm_std
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_scaled, _g_std):
         depth, sparse_depth, stats = ctx.saved_tensors
         b, h, w = _dims(depth)
@@ -61,11 +68,13 @@ class FlowFromDepthFn(torch.autograd.Function):
     """FlowfromDepthLayer.forward (/root/reference/models.py:370-374, :377-451)."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, depth, mask, t, r, k):
         L.require_cuda(depth, mask)
+        b, h, w = _dims(depth, 1, "FlowfromDepthLayer")
+        L.same_shape("FlowfromDepthLayer", depth, ("img_masks", mask, depth.shape))
         depth, mask = L.contig(depth), L.contig(mask)
-        t, r, k = _pose(t, r, k)
-        b, h, w = _dims(depth)
+        t, r, k = _pose(t, r, k, b, "FlowfromDepthLayer")
         flow = torch.empty((b, 2, h, w), dtype=torch.float32, device=depth.device)
         L.check(L.lib().endo_flow_from_depth_fwd(depth.data_ptr(), mask.data_ptr(), t.data_ptr(), r.data_ptr(),
                                                  k.data_ptr(), flow.data_ptr(), b, h, w, L.stream_ptr(depth.device)),
@@ -74,6 +83,7 @@ class FlowFromDepthFn(torch.autograd.Function):
         return flow
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_flow):
         depth, mask, t, r, k = ctx.saved_tensors
         b, h, w = _dims(depth)
@@ -89,11 +99,13 @@ class DepthWarpFn(torch.autograd.Function):
     """DepthWarpingLayer.forward (/root/reference/models.py:460-465, :469-554)."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, d1, d2, mask, t, r, k, epsilon):
         L.require_cuda(d1, d2, mask)
+        b, h, w = _dims(d1, 1, "DepthWarpingLayer")
+        L.same_shape("DepthWarpingLayer", d1, ("depth_maps_2", d2, d1.shape), ("img_masks", mask, d1.shape))
         d1, d2, mask = L.contig(d1), L.contig(d2), L.contig(mask)
-        t, r, k = _pose(t, r, k)
-        b, h, w = _dims(d1)
+        t, r, k = _pose(t, r, k, b, "DepthWarpingLayer")
         warped = torch.empty_like(d1)
         intersect = torch.empty_like(d1)
         L.check(L.lib().endo_depth_warp_fwd(d1.data_ptr(), d2.data_ptr(), mask.data_ptr(), t.data_ptr(), r.data_ptr(),
@@ -105,6 +117,7 @@ class DepthWarpFn(torch.autograd.Function):
         return warped, intersect
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_warped, _g_inter):
         d1, d2, mask, t, r, k = ctx.saved_tensors
         b, h, w = _dims(d1)
@@ -126,10 +139,12 @@ class SparseL1Fn(torch.autograd.Function):
     """SparseMaskedL1Loss.forward (/root/reference/losses.py:62-66)."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, flows, flows_from_depth, masks, epsilon):
         L.require_cuda(flows, flows_from_depth, masks)
+        b, h, w = _dims(masks, 1, "SparseMaskedL1Loss")
+        L.same_shape("SparseMaskedL1Loss", masks, ("flows", flows, (b, 2, h, w)), ("flows_from_depth", flows_from_depth, (b, 2, h, w)))
         flows, flows_from_depth, masks = L.contig(flows), L.contig(flows_from_depth), L.contig(masks)
-        b, h, w = _dims(masks)
         loss = torch.empty((), dtype=torch.float32, device=flows.device)
         stats = torch.empty(b * 2, dtype=torch.float32, device=flows.device)
         ws = _loss_ws(flows, b, h, w)
@@ -141,9 +156,10 @@ class SparseL1Fn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_loss):
         flows, ffd, masks, stats = ctx.saved_tensors
-        b, h, w = _dims(masks)
+        b, h, w = masks.shape[0], masks.shape[2], masks.shape[3]
         g_loss = L.contig(g_loss)
         g_ffd = torch.empty_like(ffd)
         g_f = torch.empty_like(flows) if ctx.needs_input_grad[0] else None
@@ -157,11 +173,14 @@ class NormDistFn(torch.autograd.Function):
     """NormalizedDistanceLoss.forward (/root/reference/losses.py:122-146)."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, depth, warped, intersect, intrinsics, eps):
         L.require_cuda(depth, warped, intersect, intrinsics)
+        b, h, w = _dims(depth, 1, "NormalizedDistanceLoss")
+        L.same_shape("NormalizedDistanceLoss", depth, ("warped_depth_maps", warped, depth.shape),
+                     ("intersect_masks", intersect, depth.shape), ("intrinsics", intrinsics, (b, 3, 3)))
         depth, warped, intersect, intrinsics = (L.contig(depth), L.contig(warped), L.contig(intersect),
                                                 L.contig(intrinsics))
-        b, h, w = _dims(depth)
         loss = torch.empty((), dtype=torch.float32, device=depth.device)
         stats = torch.empty(b * 4, dtype=torch.float32, device=depth.device)
         ws = _loss_ws(depth, b, h, w)
@@ -174,6 +193,7 @@ class NormDistFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_loss):
         depth, warped, intersect, intrinsics, stats = ctx.saved_tensors
         b, h, w = _dims(depth)
@@ -191,10 +211,12 @@ class ScaleInvFn(torch.autograd.Function):
     """ScaleInvariantLoss.forward (/root/reference/losses.py:22-32)."""
 
     @staticmethod
+    @L.on_device
     def forward(ctx, pred, goal, boundaries, epsilon):
         L.require_cuda(pred, goal, boundaries)
+        b, h, w = _dims(pred, 1, "ScaleInvariantLoss")
+        L.same_shape("ScaleInvariantLoss", pred, ("goal_depths", goal, pred.shape), ("boundaries", boundaries, pred.shape))
         pred, goal, boundaries = L.contig(pred), L.contig(goal), L.contig(boundaries)
-        b, h, w = _dims(pred)
         loss = torch.empty((), dtype=torch.float32, device=pred.device)
         stats = torch.empty(b * 4, dtype=torch.float32, device=pred.device)
         ws = _loss_ws(pred, b, h, w)
@@ -206,6 +228,7 @@ class ScaleInvFn(torch.autograd.Function):
         return loss
 
     @staticmethod
+    @L.on_device
     def backward(ctx, g_loss):
         pred, goal, boundaries, stats = ctx.saved_tensors
         b, h, w = _dims(pred)

@@ -13,7 +13,13 @@
  *     C = 1 (or 2 for flow, 3 for colours); pose inputs are row-major t[B*3], R[B*9], K[B*9];
  *   - the caller owns all memory (PyTorch's caching allocator); the library never allocates, frees or
  *     keeps a pointer after the call, and never synchronises the device;
- *   - all work is enqueued on `stream` (a cudaStream_t); functions are re-entrant;
+ *   - the CURRENT device of the calling thread must be the device that owns `stream` and the buffers (per-device kernel
+ *     attributes are configured lazily for the current device);
+ *   - all work is ordered with respect to `stream` (a cudaStream_t): when a call returns, everything it enqueued
+ *     happens-before whatever the caller enqueues on `stream` next.  Functions are re-entrant and keep no per-call
+ *     state.  One exception to "only on `stream`" is documented at endo_net_bwd: the weight-gradient kernels run on a
+ *     library-owned side stream forked from / joined into `stream` with events (capturable in a CUDA graph after one
+ *     warm-up call; switched off with ENDO_NET_SINGLE_STREAM);
  *   - `ws` is scratch of at least endo_*_workspace_bytes(...) bytes, 16-byte aligned, whose first
  *     ENDO_WS_HEADER_BYTES bytes must be zero on entry (they hold self-resetting arrival counters and
  *     are zero again when the enqueued work has finished).  One `ws` must not be shared by calls that
@@ -143,6 +149,10 @@ int endo_scale_inv_bwd(const float* g_loss, const float* pred, const float* goal
  *   backward needs and must stay untouched until endo_net_bwd has run.
  * bwd: g_y[B,1,H,W] -> g_params (flat, same layout as params; ACCUMULATED into if accumulate != 0,
  *   else overwritten) and optionally g_x.  `scratch` (endo_net_backward_scratch_bytes) is transient.
+ *   Unless ENDO_NET_SINGLE_STREAM is set, the weight-gradient kernels (which only feed g_params) are enqueued on a side
+ *   stream borrowed from a per-device pool for the duration of the call: forked from `stream` after the kernels they
+ *   depend on, joined back into `stream` before the function returns ON EVERY EXIT PATH (also on errors), so the
+ *   caller sees plain stream semantics.  Concurrent calls borrow different side streams.
  * math: ENDO_MATH_FP32 = fp32 FFMA (parity path, matches the reference's CPU fp32 results);
  *       ENDO_MATH_TF32 = tcgen05 tensor-core tiles, tf32 operands (what cuDNN runs the reference's convolutions in
  *       by default), fp32 accumulation in TMEM; ENDO_MATH_TF32X3 = tcgen05 with error-compensated operands in the
@@ -163,6 +173,11 @@ typedef struct {
 } endo_net_config;
 
 enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2 /* reserved */, ENDO_MATH_TF32X3 = 3, ENDO_MATH_BF16X3 = 4 };
+/* flags OR-ed into the `math` argument of endo_net_fwd / endo_net_bwd (per call, no global state) */
+enum {
+    ENDO_MATH_MASK = 0xFF,
+    ENDO_NET_SINGLE_STREAM = 0x100  /* endo_net_bwd: enqueue the weight-gradient kernels on `stream` too (no side stream) */
+};
 
 long long endo_net_param_count(const endo_net_config* cfg);
 long long endo_net_buffer_count(const endo_net_config* cfg); /* running_mean + running_var floats */

@@ -7,7 +7,7 @@ DepthWarpingLayer, SparseMaskedL1Loss, NormalizedDistanceLoss, ScaleInvariantLos
 loss assembly, gradient clipping and the SGD-momentum update.  Every function cites the
 reference file:line it restates.
 
-Rules (enforced by tests/test_layout.py):
+Rules (enforced by tests/test_host.py):
   * only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
     legs may import anything from here, and only as the checker / the reported CPU baseline;
   * the product package (`endoscopydepthestimation-pytorch_b200/`) never imports it and has no

@@ -130,12 +130,32 @@ def main():
     print("net_a", y.shape, float(y.mean()))
 
     # ---------------------------------------------------------------- one full train step (train.py:272-328)
-    b, h, w, seed = 2, 64, 64, 404
-    state = onet.init_state(cfg, seed=seed, perturb=False)          # reference init: kaiming / zero bias / gamma 1
+    record_step(ref_models, ref_losses, "step_a", 2, 64, 64, 404, perturb=False, conditioned=False)
+    # well-conditioned variants (oracle.net.condition_state): the bounds that matter -- 1e-4 on every loss term
+    record_step(ref_models, ref_losses, "step_b", 2, 64, 96, 505, perturb=True, conditioned=True)
+    # ... and at the benchmarked configuration (BASELINE.json configs[1]: bs8 256x320, seed of train.py:80)
+    record_step(ref_models, ref_losses, "step_c", 8, 256, 320, 10085, perturb=False, conditioned=True, sparse_prob=0.005,
+                stride=4)
+
+
+STEP_TENSORS = ("firstconv.weight", "finalConv.weight", "denseBlocksUp.4.layers.3.conv.weight",
+                "denseBlocksDown.2.layers.1.norm.weight")
+
+
+def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned, sparse_prob=0.02, stride=1):
+    """Two iterations of train.py:272-328 on the unmodified reference modules; records the loss terms, the gradient norm,
+    per-tensor gradient / weight norms and a few tensors.  `stride` subsamples the stored maps (large configurations)."""
+    import endo_b200
+    from oracle import net as onet
+    cfg = onet.FCDENSENET57
+    names = [k for k in onet.param_shapes(cfg) if not onet.is_buffer(k)]
+    state = onet.init_state(cfg, seed=seed, perturb=perturb)          # perturb=False: reference init (kaiming / zero bias / gamma 1)
+    if conditioned:
+        state = onet.condition_state(state)
     model = ref_models.FCDenseNet57(n_classes=1)
     model.load_state_dict(state, strict=True)
     model.train()
-    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, sparse_prob=0.02)
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, sparse_prob=sparse_prob)
     opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9)
     scale = ref_models.DepthScalingLayer(epsilon=1e-8)
     warp = ref_models.DepthWarpingLayer(epsilon=1e-8)
@@ -143,6 +163,7 @@ def main():
     l1 = ref_losses.SparseMaskedL1Loss()
     ndl = ref_losses.NormalizedDistanceLoss(height=h, width=w)
     rec = {"loss": [], "dcl": [], "sfl": [], "gnorm": []}
+    first = {}
     for it in range(2):
         B = batch
         c1 = B["boundaries"] * B["colors_1"]
@@ -163,21 +184,33 @@ def main():
         loss = dcl + sfl
         opt.zero_grad()
         loss.backward()
+        if it == 0 and conditioned:
+            params = dict(model.named_parameters())
+            first["grad_l2"] = np.array([params[k].grad.double().norm().item() for k in names], dtype=np.float64)
+            for k in STEP_TENSORS:
+                first["grad::" + k] = np32(params[k].grad)
         gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
         opt.step()
         rec["loss"].append(loss.item()); rec["dcl"].append(dcl.item()); rec["sfl"].append(sfl.item())
         rec["gnorm"].append(float(gn))
         if it == 0:
-            first = dict(p1=np32(p1), s1=np32(s1), w21=np32(w21), i1=np32(i1), f1=np32(f1))
+            sub = (slice(None), slice(None), slice(None, None, stride), slice(None, None, stride))
+            first.update(p1=np32(p1[sub]), s1=np32(s1[sub]), w21=np32(w21[sub]), i1=np32(i1[sub]), f1=np32(f1[sub]))
+            if conditioned:
+                first.update(p2=np32(p2[sub]), inter_sum=np.array([float(i1.sum()), float(i2.sum())]))
     out = {k: np.array(v, dtype=np.float64) for k, v in rec.items()}
     out.update(first)
     params = dict(model.named_parameters())
     out["w_l2_after"] = np.array([params[k].double().norm().item() for k in names], dtype=np.float64)
-    for k in ("firstconv.weight", "finalConv.weight", "denseBlocksUp.4.layers.3.conv.weight",
-              "denseBlocksDown.2.layers.1.norm.weight"):
+    for k in STEP_TENSORS:
         out["after::" + k] = np32(params[k])
-    np.savez_compressed(os.path.join(OUT, "step_a.npz"), meta=np.array([b, h, w, seed]), **out)
-    print("step_a", rec)
+    if conditioned:
+        sd = model.state_dict()
+        for k in ("denseBlocksDown.0.layers.0.norm.running_mean", "denseBlocksUp.4.layers.3.norm.running_var",
+                  "bottleneck.bottleneck.layers.3.norm.running_var"):
+            out["buf::" + k] = np32(sd[k])
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), meta=np.array([b, h, w, seed] + ([stride] if conditioned else [])), **out)
+    print(tag, rec)
 
 
 if __name__ == "__main__":

@@ -130,6 +130,21 @@ def init_state(cfg: NetConfig = FCDENSENET57, seed: int = 0, dtype=torch.float32
     return state
 
 
+def condition_state(state: Dict[str, torch.Tensor], spread: float = 0.05, bias: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Make the composite loss of train.py:279-315 WELL-CONDITIONED at initialisation (test fixtures only).
+
+    With the reference's Kaiming init `abs(finalConv(...))` crosses zero, and `DepthScalingLayer` divides the
+    sparse depths by the prediction (models.py:356): 1e-7 differences in the depth map move the loss by 1e-3
+    and the gradient norm is O(1e5), so loss / gradient bounds there cannot separate a correct kernel from a
+    subtly wrong one.  Scaling `finalConv.weight` by `spread` and setting `finalConv.bias = bias` keeps the
+    predicted depth in ~[0.7, 1.3] (what a trained network outputs on depths normalised to ~1): the fp32 and
+    fp64 oracles then agree to <1e-6 on every loss term and the gradient norm is O(10)."""
+    out = OrderedDict(state)
+    out["finalConv.weight"] = state["finalConv.weight"] * spread
+    out["finalConv.bias"] = torch.full_like(state["finalConv.bias"], bias)
+    return out
+
+
 def _batch_norm_train(x, prefix, state, new_buffers):
     """nn.BatchNorm2d in training mode (models.py:22,59): normalise with the batch statistics
     (biased variance) and record the running-buffer update (unbiased variance, momentum 0.1)."""

@@ -27,6 +27,7 @@ class _FakeNet:
         self.flat_grads = self._flat_grad_store[:n]
         self.flat_params = torch.full((n,), float(rank))
         self._flat_buf = torch.full((7,), float(rank) + 10.0)
+        self._nbt = [torch.tensor(rank + 5, dtype=torch.long)]
 
 
 def _worker(rank, world, port, results):
@@ -40,7 +41,7 @@ def _worker(rank, world, port, results):
     n = 1000
     net = _FakeNet(n, rank)
     ddp.broadcast_parameters(net, src=0)
-    assert float(net.flat_params[0]) == 0.0 and float(net._flat_buf[0]) == 10.0
+    assert float(net.flat_params[0]) == 0.0 and float(net._flat_buf[0]) == 10.0 and int(net._nbt[0]) == 5
     # step 1: every rank finite -> flag stays 1, gradients are averaged
     finite = torch.ones(1)
     ddp.allreduce_gradients(net, finite)

@@ -163,3 +163,57 @@ def test_library_ops_mode_matches_restatement():
     assert abs(float(loss) - g["loss"][0]) / g["loss"][0] < 2e-3
     assert rel_err(ex["depth_1"], g["p1"]) < 1e-4
     assert int(new_buf["denseBlocksDown.0.layers.0.norm.num_batches_tracked"]) == 2
+
+
+def _oracle_step_vs_fixture(tag, iters):
+    g = load_golden(tag)
+    b, h, w, seed, stride = [int(v) for v in g["meta"]]
+    cfg = net.FCDENSENET57
+    perturb = tag == "step_b"
+    state = net.condition_state(net.init_state(cfg, seed=seed, perturb=perturb))
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed, sparse_prob=0.02 if tag == "step_b" else 0.005)
+    mom = {}
+    names = [k for k in state if not net.is_buffer(k)]
+    for it in range(iters):
+        loss, dcl, sfl, grads, new_buf, ex = step.forward_backward(state, batch, cfg, 5.0, 20.0)
+        # WELL-CONDITIONED fixture: the stated 1e-4 bound on every loss scalar, both iterations (north_star)
+        for name, got in (("loss", loss), ("dcl", dcl), ("sfl", sfl)):
+            assert abs(float(got) - g[name][it]) / g[name][it] < 1e-4, (tag, it, name, float(got), g[name][it])
+        if it == 0:
+            sub = (slice(None), slice(None), slice(None, None, stride), slice(None, None, stride))
+            assert rel_err(ex["depth_1"][sub], g["p1"]) < 1e-4
+            assert rel_err(ex["depth_2"][sub], g["p2"]) < 1e-4
+            assert rel_err(ex["scaled_1"][sub], g["s1"]) < 1e-4
+            assert rel_err(ex["warped_2to1"][sub], g["w21"]) < 1e-4
+            assert rel_err(ex["flow_1"][sub], g["f1"] * batch["boundaries"][sub].numpy()) < 1e-4
+            assert int((ex["inter_1"][sub].numpy() != g["i1"]).sum()) == 0
+            l2 = np.array([grads[k].double().norm().item() for k in names])
+            assert np.all(np.abs(l2 - g["grad_l2"]) <= 2e-3 * g["grad_l2"] + 1e-5 * g["grad_l2"].max())
+            for k in g:
+                if k.startswith("grad::"):
+                    # two fp32 CPU codes (this restatement / the reference's ATen BatchNorm): measured up to 2.7e-3 on a
+                    # BatchNorm gamma gradient at bs8 256x320 (a cancelling sum over 82k samples), 1e-5 on the conv weights
+                    assert rel_err(grads[k[6:]].detach(), g[k]) < 5e-3, k
+        gn = step.clip_and_sgd(state, grads, mom, lr=1e-3)
+        assert abs(float(gn) - g["gnorm"][it]) / g["gnorm"][it] < 1e-4, (it, float(gn), g["gnorm"][it])
+        state.update(new_buf)
+    if iters == 2:
+        l2 = np.array([state[k].double().norm().item() for k in names])
+        assert np.all(np.abs(l2 - g["w_l2_after"]) <= 1e-5 * g["w_l2_after"] + 1e-7)
+        for k in g:
+            if k.startswith("after::"):
+                assert rel_err(state[k[7:]], g[k]) < 1e-4, k
+            if k.startswith("buf::"):
+                assert rel_err(state[k[5:]], g[k]) < 1e-5, k
+
+
+def test_full_step_well_conditioned():
+    """Two iterations of train.py:272-328 against the reference trace of the well-conditioned fixture
+    (oracle.net.condition_state): 1e-4 on loss / dcl / sfl / gradient norm, 1e-4 on the updated weights."""
+    _oracle_step_vs_fixture("step_b", 2)
+
+
+def test_full_step_benchmark_configuration():
+    """The same at the benchmarked configuration (bs8 256x320, seed 10085; BASELINE.json configs[1]); one
+    iteration (an 8-image fp32 backward of FCDenseNet57 on the CPU takes ~15 s)."""
+    _oracle_step_vs_fixture("step_c", 1)
