@@ -102,9 +102,14 @@ static int tc_disable_mask() {
     return e ? atoi(e) : 0;
 }
 
-static inline bool is_tc(int math) { return math == ENDO_MATH_TF32 || math == ENDO_MATH_TF32X3 || math == ENDO_MATH_BF16X3; }
-// forward operand scheme of the tensor-core modes: 0 = plain tf32, 1 = 3xTF32, 2 = bf16x3
-static inline int x3_mode(int math) { return math == ENDO_MATH_TF32X3 ? 1 : (math == ENDO_MATH_BF16X3 ? 2 : 0); }
+static inline bool is_tc(int math) {
+    return math == ENDO_MATH_TF32 || math == ENDO_MATH_TF32X3 || math == ENDO_MATH_BF16X3 || math == ENDO_MATH_BF16;
+}
+// forward operand scheme of the tensor-core modes: 0 = plain tf32, 1 = 3xTF32, 2 = bf16x3, 3 = plain bf16 (the bf16x3 staging,
+// only the first-term product is issued: activations and weights rounded to bf16, fp32 accumulation -- BASELINE config 3)
+static inline int x3_mode(int math) {
+    return math == ENDO_MATH_TF32X3 ? 1 : (math == ENDO_MATH_BF16X3 ? 2 : (math == ENDO_MATH_BF16 ? 3 : 0));
+}
 
 // Weight-gradient kernels only feed the optimiser, and a layer's weight gradient is independent of the same layer's data
 // gradient: they are enqueued on a side stream (forked from / joined to the caller's stream with events) so that
@@ -259,7 +264,7 @@ static int pack_all(const Ctx& c, bool bwd, int per, int mode, K kern, unsigned 
     return flush();
 }
 static int pack_dense_weights_fwd(const Ctx& c) {
-    const int mode = x3_mode(c.math);
+    const int mode = x3_mode(c.math) == 3 ? 2 : x3_mode(c.math);       // plain bf16 uses the bf16x3 images (first terms)
     return pack_all(c, false, mode == 1 ? 8 : 16, mode, tcconv::pack_w_fwd_all_kernel, reinterpret_cast<unsigned char*>(c.acts + c.P.wpack_off));
 }
 static int pack_dense_weights_bwd(const Ctx& c) {
@@ -458,7 +463,7 @@ static int trans_down_fwd(const Ctx& c, int l) {
             tcpw::Args q{};
             q.in = a.in; q.in_C = a.in_C; q.in_off = a.in_off; q.coef = a.coef; q.wpack = c.WPACK(); q.bias = a.bias;
             q.out = tmp; q.out_C = cs; q.out_off = 0; q.K = cs; q.N = cs; q.Npad = npad;
-            q.per_group = (long long)(P.B / P.G) * a.oh * a.ow; q.mode = 0; q.x3 = x3_mode(c.math) != 0;
+            q.per_group = (long long)(P.B / P.G) * a.oh * a.ow; q.mode = 0; q.x3 = x3_mode(c.math) == 1 || x3_mode(c.math) == 2;   // plain tf32 / bf16 modes: tf32 operands
             {
                 ProfScope prof(PC_BN, c.s);
                 tcpw::pack_w_pw_kernel<<<cdiv(cs, q.x3 ? 8 : 16), 256, 0, c.s>>>(a.w, cs, npad, q.x3, 0, c.WPACK());
@@ -475,7 +480,7 @@ static int trans_down_fwd(const Ctx& c, int l) {
             {
                 ProfScope prof(PC_BN, c.s);
                 if (f.x3 == 1) tcconv::pack_w_1x1_x3_kernel<<<cdiv(cs, 8), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
-                else if (f.x3 == 2) tcconv::pack_w_1x1_b3_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, reinterpret_cast<uint32_t*>(c.WPACK()));
+                else if (f.x3 >= 2) tcconv::pack_w_1x1_b3_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, reinterpret_cast<uint32_t*>(c.WPACK()));
                 else tcconv::pack_w_1x1_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }

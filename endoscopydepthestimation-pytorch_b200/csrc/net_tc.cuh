@@ -467,8 +467,8 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                             }
                             if (A.x3 == 0) v = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
                         }
-                        if (A.x3 == 2) {
-                            // bf16x3: this thread's 4 channels are 8 bytes of the 16-byte (8-channel) row of plane grp / 2 (first
+                        if (A.x3 >= 2) {
+                            // bf16x3 / bf16: this thread's 4 channels are 8 bytes of the 16-byte (8-channel) row of plane grp / 2 (first
                             // terms) and of plane 2 + grp / 2 (second terms = bf16 of the exact remainders)
                             float r0, r1, r2, r3;
                             const uint32_t p0 = bf16_split(v.x, v.y, r0, r1), p1 = bf16_split(v.z, v.w, r2, r3);
@@ -657,7 +657,10 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const uint64_t bhi = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + 0) * B_BLOCK_BYTES) >> 4);
                     const uint64_t blo = b_hi | (uint64_t)((b_base + (uint32_t)(ky * 2 + 1) * B_BLOCK_BYTES) >> 4);
                     const uint32_t acc = (uint32_t)((it | ky) != 0);
-                    if (A.x3 == 2) {                                  // bf16x3: same planes / blocks, kind::f16, K = 16 per MMA
+                    if (A.x3 == 3) {                                  // plain bf16: first-term product only
+#pragma unroll
+                        for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16_w(tmem + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc_b, acc);
+                    } else if (A.x3 == 2) {                           // bf16x3: same planes / blocks, kind::f16, K = 16 per MMA
 #pragma unroll
                         for (int mb = 0; mb < MBLK; ++mb) tc::mma_f16_w(tmem + mb * NB, alo + (uint64_t)(mb * 128), bhi, idesc_b, acc);
 #pragma unroll

@@ -20,7 +20,7 @@ from torch import nn
 
 from . import _lib as L
 
-MATH_MODES = {"fp32": 0, "tf32": 1, "tf32x3": 3, "bf16x3": 4}
+MATH_MODES = {"fp32": 0, "tf32": 1, "bf16": 2, "tf32x3": 3, "bf16x3": 4}
 
 
 # ------------------------------------------------------------------------------------------------

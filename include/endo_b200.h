@@ -158,6 +158,9 @@ int endo_scale_inv_bwd(const float* g_loss, const float* pred, const float* goal
  *       by default), fp32 accumulation in TMEM; ENDO_MATH_TF32X3 = tcgen05 with error-compensated operands in the
  *       forward (x = hi + lo, three tf32 MMAs per product: fp32-grade depth maps and losses on the tensor cores);
  *       gradients as in ENDO_MATH_TF32 (tf32 data gradient, bf16 weight gradient, fp32 accumulation);
+ *       ENDO_MATH_BF16 = tcgen05 with activations and weights of the 3x3 convolutions rounded to bf16 (one kind::f16 MMA per
+ *       product, fp32 accumulation in TMEM, fp32 BatchNorm statistics, fp32 master weights; the 1x1 TransitionDown GEMMs use
+ *       tf32 operands): BASELINE.json configs[2]; gradients as in ENDO_MATH_TF32;
  *       ENDO_MATH_BF16X3 = the same with two-term bf16 operands (x = b1 + b2, 16 significant bits, three kind::f16 MMAs
  *       of K = 16 per product: half the MMA count of 3xTF32, depth maps within ~2e-5 of fp32).
  * ---------------------------------------------------------------------------------------------- */
@@ -172,7 +175,7 @@ typedef struct {
     int n_classes;            /* only 1 is supported */
 } endo_net_config;
 
-enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2 /* reserved */, ENDO_MATH_TF32X3 = 3, ENDO_MATH_BF16X3 = 4 };
+enum { ENDO_MATH_FP32 = 0, ENDO_MATH_TF32 = 1, ENDO_MATH_BF16 = 2, ENDO_MATH_TF32X3 = 3, ENDO_MATH_BF16X3 = 4 };
 /* flags OR-ed into the `math` argument of endo_net_fwd / endo_net_bwd (per call, no global state) */
 enum {
     ENDO_MATH_MASK = 0xFF,

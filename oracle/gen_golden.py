@@ -35,7 +35,17 @@ def np32(t):
     return t.detach().cpu().numpy().astype(np.float32)
 
 
-def main():
+def main(only=None):
+    if only:                                    # regenerate selected step fixtures only: python -m oracle.gen_golden step_d
+        ref_models, ref_losses = load_reference()
+        torch.set_num_threads(8)
+        table = {"step_a": (2, 64, 64, 404, False, False, 0.02, 1, 2), "step_b": (2, 64, 96, 505, True, True, 0.02, 1, 2),
+                 "step_c": (8, 256, 320, 10085, False, True, 0.005, 4, 2), "step_d": (32, 256, 320, 20085, False, True, 0.005, 8, 1)}
+        for tag in only:
+            b, h, w, seed, perturb, cond, sp, stride, iters = table[tag]
+            record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb=perturb, conditioned=cond, sparse_prob=sp,
+                        stride=stride, iters=iters)
+        return
     import endo_b200
     from oracle import net as onet
     ref_models, ref_losses = load_reference()
@@ -136,13 +146,16 @@ def main():
     # ... and at the benchmarked configuration (BASELINE.json configs[1]: bs8 256x320, seed of train.py:80)
     record_step(ref_models, ref_losses, "step_c", 8, 256, 320, 10085, perturb=False, conditioned=True, sparse_prob=0.005,
                 stride=4)
+    # BASELINE.json configs[2]: bs32 256x320 (one iteration, scalars + a coarse depth map: the loss-parity case of the bf16 path)
+    record_step(ref_models, ref_losses, "step_d", 32, 256, 320, 20085, perturb=False, conditioned=True, sparse_prob=0.005,
+                stride=8, iters=1)
 
 
 STEP_TENSORS = ("firstconv.weight", "finalConv.weight", "denseBlocksUp.4.layers.3.conv.weight",
                 "denseBlocksDown.2.layers.1.norm.weight")
 
 
-def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned, sparse_prob=0.02, stride=1):
+def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned, sparse_prob=0.02, stride=1, iters=2):
     """Two iterations of train.py:272-328 on the unmodified reference modules; records the loss terms, the gradient norm,
     per-tensor gradient / weight norms and a few tensors.  `stride` subsamples the stored maps (large configurations)."""
     import endo_b200
@@ -164,7 +177,7 @@ def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned
     ndl = ref_losses.NormalizedDistanceLoss(height=h, width=w)
     rec = {"loss": [], "dcl": [], "sfl": [], "gnorm": []}
     first = {}
-    for it in range(2):
+    for it in range(iters):
         B = batch
         c1 = B["boundaries"] * B["colors_1"]
         c2 = B["boundaries"] * B["colors_2"]
@@ -214,4 +227,4 @@ def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

@@ -5,7 +5,7 @@ Restates /root/reference/models.py:325-554 (`_bilinear_interpolate`, `DepthScali
 instead of calling `F.grid_sample`: the reference calls `grid_sample` without
 `align_corners` (models.py:335) on a grid normalised as 2*x/W-1 (models.py:328-333), which on
 the installed torch means sampling at pixel coordinates (u-0.5, v-0.5) with zeros padding
-(SURVEY.md section 0).  Tensors are torch CPU, any float dtype, NCHW like the reference's API.
+(SURVEY.md section 0).  Tensors are torch CPU (or, for bench.py's reference-on-GPU arm, CUDA) tensors, any float dtype, NCHW like the reference's API.
 """
 import torch
 
@@ -13,7 +13,7 @@ import torch
 def _pose_terms(translation, rotation, intrinsics):
     """models.py:391-399 / 492-499: K^-1 (solve K X = I), T = K R^T, W = T(-t), M = T K^-1."""
     b = intrinsics.shape[0]
-    eye = torch.eye(3, dtype=intrinsics.dtype).reshape(1, 3, 3).expand(b, -1, -1)
+    eye = torch.eye(3, dtype=intrinsics.dtype, device=intrinsics.device).reshape(1, 3, 3).expand(b, -1, -1)
     k_inv = torch.linalg.solve(intrinsics, eye)
     temp = torch.bmm(intrinsics, rotation.transpose(1, 2))
     w_vec = torch.bmm(temp, -translation.reshape(b, 3, 1)).reshape(b, 3)
@@ -21,10 +21,10 @@ def _pose_terms(translation, rotation, intrinsics):
     return k_inv, w_vec, m_mat
 
 
-def _mesh(height, width, dtype):
+def _mesh(height, width, dtype, device=None):
     """models.py:381-386: meshgrid 'ij' => x_grid[h, w] = w, y_grid[h, w] = h."""
-    y = torch.arange(height, dtype=dtype).reshape(1, 1, height, 1).expand(1, 1, height, width)
-    x = torch.arange(width, dtype=dtype).reshape(1, 1, 1, width).expand(1, 1, height, width)
+    y = torch.arange(height, dtype=dtype, device=device).reshape(1, 1, height, 1).expand(1, 1, height, width)
+    x = torch.arange(width, dtype=dtype, device=device).reshape(1, 1, 1, width).expand(1, 1, height, width)
     return x, y
 
 
@@ -48,7 +48,7 @@ def flow_from_depth(depth, mask, translation, rotation, intrinsics):
     """`FlowfromDepthLayer.forward` (models.py:370-374 -> :433-451 -> :377-429). Returns [B,2,H,W]."""
     b, _, h, w = depth.shape
     _, w_vec, m_mat = _pose_terms(translation, rotation, intrinsics)
-    x, y = _mesh(h, w, depth.dtype)
+    x, y = _mesh(h, w, depth.dtype, depth.device)
     m = m_mat.reshape(b, 3, 3, 1, 1)
     q = [m[:, r, 0] * x[0] + m[:, r, 1] * y[0] + m[:, r, 2] for r in range(3)]       # M . [x, y, 1]  (:401-402)
     q = [t.reshape(b, 1, h, w) for t in q]
@@ -116,7 +116,7 @@ def depth_warping(depth_1, depth_2, mask, translation, rotation, intrinsics, eps
     d1 = depth_1 * mask                                                         # :473
     d2 = depth_2 * mask                                                         # :474
     k_inv, w_vec, m_mat = _pose_terms(translation, rotation, intrinsics)
-    x, y = _mesh(h, w, dtype)
+    x, y = _mesh(h, w, dtype, depth_1.device)
     m = m_mat.reshape(b, 3, 3, 1, 1)
     q = [(m[:, r, 0] * x[0] + m[:, r, 1] * y[0] + m[:, r, 2]).reshape(b, 1, h, w) for r in range(3)]
     wv = w_vec.reshape(b, 3, 1, 1, 1)

@@ -26,8 +26,8 @@ def sparse_masked_l1_loss(flows, flows_from_depth, sparse_masks, epsilon=1.0):
 def normalized_distance_loss(depth, warped, intersect, intrinsics, eps=1.0e-5):
     """losses.py:122-146."""
     b, _, h, w = depth.shape
-    y_grid = torch.arange(h, dtype=depth.dtype).reshape(1, 1, h, 1).expand(1, 1, h, w)   # :116-120
-    x_grid = torch.arange(w, dtype=depth.dtype).reshape(1, 1, 1, w).expand(1, 1, h, w)
+    y_grid = torch.arange(h, dtype=depth.dtype, device=depth.device).reshape(1, 1, h, 1).expand(1, 1, h, w)   # :116-120
+    x_grid = torch.arange(w, dtype=depth.dtype, device=depth.device).reshape(1, 1, 1, w).expand(1, 1, h, w)
     fx = intrinsics[:, 0, 0].reshape(-1, 1, 1, 1)
     fy = intrinsics[:, 1, 1].reshape(-1, 1, 1, 1)
     cx = intrinsics[:, 0, 2].reshape(-1, 1, 1, 1)
