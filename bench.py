@@ -40,11 +40,13 @@ if ROOT not in sys.path:
 CONFIGS = {
     # name: (batch per GPU, H, W, math, description)
     "c2": (8, 256, 320, "tf32x3", "1xB200 bs8 256x320 synthetic pairs, FCDenseNet57, full loss stack (dcl 5, sfl 20), fp32"),
-    "c3": (32, 256, 320, "tf32", "1xB200 bs32 256x320, reduced-precision tensor-core conv path (tf32 / bf16 operands), warp layers fp32"),
+    "c3": (32, 256, 320, "bf16", "1xB200 bs32 256x320, bf16 tensor-core conv path, warp layers fp32"),
     "c5": (16, 512, 640, "tf32x3", "bs16/GPU 512x640 (downsampling 2.0), warp-gather stress"),
 }
 METRIC = "image-pairs/sec fwd+bwd @256x320 bs8"
 DTYPE = {"fp32": "fp32 (FFMA convolutions, no tensor cores: strict-parity path)",
+         "bf16": "bf16 operands in the 3x3 convolutions on tcgen05 (tf32 in the 1x1 transitions and the data gradient, bf16 in the "
+                 "weight gradient), fp32 accumulate / BatchNorm statistics / master weights; geometric layers and losses fp32",
          "tf32": "tf32 operands on tcgen05 (forward, data gradient), bf16 operands (weight gradient), fp32 accumulate",
          "bf16x3": "fp32 (forward: error-compensated two-term bf16 operands on tcgen05, three kind::f16 MMAs per product, depth maps "
                    "within ~2e-5 of fp32; gradients: tf32 / bf16 operands on tcgen05; fp32 accumulate in TMEM; everything else fp32)",
@@ -401,37 +403,41 @@ def cpu_baseline_sample(h, w, budget_s=20.0):
 
 
 def resident_arm(model, h, w, bsz, resident, steps, warmup, world, dev, pg, barrier, max_over_ranks, sampler=None):
-    """Device-resident step (inputs in HBM, fused pair forward, fused optimiser tail): returns timing + launch count."""
-    from endo_b200 import _lib, train_step
-    fused = train_step.TrainStep(model, h, w, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0, sfl_weight=20.0,
-                                 pair=True, process_group=pg)
+    """Device-resident step (inputs in HBM): the whole optimisation step replayed from ONE CUDA graph
+    (train_step.GraphedTrainStep: fused pair forward, loss stack, backward, device-side NaN guard, fused clip + SGD;
+    with N > 1 the gradient all-reduce sits between two graphs).  Returns timing + launch count."""
+    from endo_b200 import train_step
+    fused = train_step.GraphedTrainStep(model, h, w, resident, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0,
+                                        sfl_weight=20.0, pair=True, process_group=pg, warmup=2)
     for _ in range(warmup):
-        fused.step(resident)
+        fused.replay()
     barrier()
     if sampler is not None:
         sampler.start()
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        loss, _, _ = fused.step(resident)
+        loss, _, _ = fused.replay()
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - launches0
     if sampler is not None:
         sampler.stop_flag = True
         sampler.join(timeout=2)
-    return fused, dict(ms_per_step=ms_total / steps, value=world * bsz * steps / (ms_total / 1e3), launches=int(launches),
+    return fused, dict(ms_per_step=ms_total / steps, value=world * bsz * steps / (ms_total / 1e3),
+                       launches=int(fused.launches_per_step * steps), launches_per_step=int(fused.launches_per_step),
                        loss=float(loss))
 
 
-def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof_steps=3):
+def kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg=None, prof_steps=3):
     """Per-kernel-class CUDA-event timing inside the library (endo_prof_*, events on the launching stream) -> roofline of the
     dominant class.  The convolution classes are bounded by their operand stream (a DenseLayer moves
     Cin*4 B/pixel for 216*Cin flop/pixel = 54 flop/B against a ridge of ~210), so the bound is HBM; the tensor-pipe
     throughput of the same launches is reported next to it."""
-    from endo_b200 import _lib
+    from endo_b200 import _lib, train_step
+    fused = train_step.TrainStep(model, h, w, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0, sfl_weight=20.0,
+                                 pair=True, process_group=pg)          # eager launches: CUDA events between kernels
+    fused.step(resident)
     # per-class times must be exclusive: keep the weight-gradient kernels on the main stream while profiling (in the timed
     # arms they run on a forked side stream and overlap the data-gradient kernels)
     prev = os.environ.get("ENDO_TC_DISABLE")
@@ -466,6 +472,7 @@ def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof
     kind = {"fp32": "fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe)",
             "tf32": "tcgen05 kernels, tf32 / bf16 operands, fp32 accumulate in TMEM",
             "tf32x3": "tcgen05 kernels: 3xTF32 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM",
+            "bf16": "tcgen05 kernels: bf16 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM",
             "bf16x3": "tcgen05 kernels: bf16x3 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM"}[math_mode]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
@@ -477,15 +484,16 @@ def kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode, prof
                 "note": kind + "; algorithmic bytes = layer-by-layer operand stream (conv_bytes_per_image), time = sum of the "
                         "class's launches in one step (CUDA events on the launching stream)",
                 "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
-    # dram__bytes_read + dram__bytes_write of the class's largest launch from the committed ncu --set full capture
-    # (profiles/r1_tf32x3_final.md; tcgen05 modes only): traffic well above the algorithmic bytes = wasted re-reads
-    ncu_largest = {"conv_dense_dgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) data gradient", "duration_us": 764.7,
-                                        "dram_bytes": 3.274e9, "algorithmic_bytes": 2.894e9},
-                   "conv_dense_wgrad": {"launch": "denseBlocksUp.4.layers.3 (Cin 180) weight gradient", "duration_us": 553.6,
-                                        "dram_bytes": 1.600e9, "algorithmic_bytes": 1.007e9}}
-    if math_mode != "fp32" and dominant in ncu_largest and (bsz, h, w) == (8, 256, 320):
-        roofline["traffic"] = ncu_largest[dominant]["dram_bytes"]
-        roofline["traffic_of"] = ncu_largest[dominant]
+    # dram__bytes_read + dram__bytes_write per launch of the dominant class from the committed `ncu --set full` capture of
+    # THIS round's tree (profiles/ncu_traffic.json, written by tools/summarize_ncu.py): same launch as `traffic_of.launch`,
+    # with that launch's own algorithmic bytes beside it -- traffic well above the algorithmic bytes = wasted re-reads
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if math_mode != "fp32" and (bsz, h, w) == (8, 256, 320) and os.path.exists(tpath):
+        with open(tpath) as fh:
+            table = json.load(fh)
+        if dominant in table:
+            roofline["traffic"] = table[dominant]["dram_bytes"]
+            roofline["traffic_of"] = table[dominant]
     kernels = {k: {"ms_per_step": round(v, 4), "launch_sites": cat_n[k]} for k, v in cat_ms.items()}
     for k, byts in work_bytes.items():
         if cat_ms.get(k, 0.0) > 0:
@@ -503,9 +511,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=os.environ.get("ENDO_BENCH_CONFIG", "c2"), choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "tf32x3", "bf16x3"],
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32", "bf16", "tf32x3", "bf16x3"],
                     help="arithmetic of the conv path for the headline arm (default: the config's, fp32)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (kernel development runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other math modes and the warp-layer microbenchmark")
@@ -570,27 +578,22 @@ def main():
     fused, res = resident_arm(model, h, w, bsz, resident, args.steps, args.warmup, world, dev, pg, barrier, max_over_ranks, sampler)
 
     # ------------------------------------------------------------------ end-to-end arm (e2e)
+    # The call a user makes: GraphedTrainStep on PINNED HOST batches.  Per step, inside the timed region: the H2D copy of the
+    # NEXT step's 16 input tensors (copy stream, overlapping this step's compute), the device-to-device hand-over into the
+    # graph's inputs, one graph launch, and the D2H read of the loss (train.py:317 / :330).
     e2e = None
     if not args.no_e2e:
         model2 = new_model(math_mode)
-        stack = train_step.LossStack(h, w, dcl_weight=5.0, sfl_weight=20.0)
-        opt = torch.optim.SGD(model2.parameters(), lr=1e-4, momentum=0.9)          # train.py:202
+        g2 = train_step.GraphedTrainStep(model2, h, w, resident, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0,
+                                         sfl_weight=20.0, pair=True, process_group=pg, warmup=2)
 
         def e2e_step():
-            cb = {k: host[k].to(dev, non_blocking=True) for k in keys}             # train.py:254-270
-            lv, _, _, _ = stack.loss(model2, cb)                                   # :272-315 (two separate net() calls)
-            val = lv.item()                                                        # :317 device->host read
-            if train_step.is_bad(val):
-                opt.zero_grad()
-                return val
-            opt.zero_grad()
-            lv.backward()
-            if world > 1:
-                ddp.allreduce_gradients(model2)
-            torch.nn.utils.clip_grad_norm_(model2.parameters(), 10.0)              # :327
-            opt.step()                                                             # :328
-            return val
+            g2.swap_in()
+            g2.prefetch(host)                                                      # next step's inputs: H2D from pinned memory
+            lv, _, _ = g2.replay()
+            return lv.item()                                                       # device->host read of the step's result
 
+        g2.prefetch(host)
         for _ in range(args.warmup):
             e2e_step()
         barrier()
@@ -601,30 +604,83 @@ def main():
         e1.record()
         barrier()
         e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-        e2e = {"value": world * bsz * args.steps / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+        e2e = {"value": world * bsz * args.steps / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": g2.h2d_bytes,
                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
-               "path": "reference-facing nn.Modules as train.py:254-328 drives them, pinned host buffers"}
+               "path": "train_step.GraphedTrainStep on pinned host batches: prefetch (H2D, copy stream) + swap_in + one CUDA-graph "
+                       "launch + loss.item() per step"}
+        del g2
+        # the reference-facing nn.Modules driven exactly as train.py:254-328 drives them (two net() calls, torch.optim.SGD,
+        # clip_grad_norm_, loss.item(), synchronous H2D): the drop-in path, no graph
+        stack = train_step.LossStack(h, w, dcl_weight=5.0, sfl_weight=20.0)
+        opt = torch.optim.SGD(model2.parameters(), lr=1e-4, momentum=0.9)          # train.py:202
+
+        def modules_step():
+            cb = {k: host[k].to(dev, non_blocking=True) for k in keys}             # train.py:254-270
+            lv, _, _, _ = stack.loss(model2, cb)                                   # :272-315 (two separate net() calls)
+            val = lv.item()                                                        # :317 device->host read
+            opt.zero_grad()
+            if train_step.is_bad(val):
+                return val
+            lv.backward()
+            if world > 1:
+                ddp.allreduce_gradients(model2)
+            torch.nn.utils.clip_grad_norm_(model2.parameters(), 10.0)              # :327
+            opt.step()                                                             # :328
+            return val
+
+        n_mod = max(args.steps // 2, 3)
+        for _ in range(3):
+            modules_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_mod):
+            modules_step()
+        e1.record()
+        barrier()
+        mod_ms = max_over_ranks(e0.elapsed_time(e1))
+        e2e["modules_as_train_py"] = {"value": world * bsz * n_mod / (mod_ms / 1e3), "unit": "pairs/s",
+                                      "ms_per_step": mod_ms / n_mod, "steps": n_mod,
+                                      "path": "reference-facing nn.Modules as train.py:254-328 drives them, pinned host buffers"}
         del model2, opt, stack
 
     # ------------------------------------------------------------------ per-kernel-class timing (roofline)
-    roofline, kernels = kernel_breakdown(fused, resident, h, w, bsz, peaks, barrier, math_mode)
+    roofline, kernels = kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg)
 
     # ------------------------------------------------------------------ extra arms (single GPU only)
     other_arms, warp_layer, cpu = {}, None, None
-    if world == 1 and not args.no_extra:
+    extra_cfg = {}
+    if not args.no_extra:
+        # The other GPU configurations of BASELINE.json as short arms of the same run, so that the driver's N = 1/2/4/8
+        # launches carry them too: configs[2] (bs32, bf16 conv path) and configs[4] (bs16/GPU 512x640, warp-gather stress).
         del fused, model
         torch.cuda.empty_cache()
+        for name, mode in (("c3", "bf16"), ("c5", "tf32x3")):
+            if name == args.config:
+                continue
+            b3, h3, w3, _, d3 = CONFIGS[name]
+            hb = endo_b200.synthetic.make_batch(b3, h3, w3, seed=10085 + rank)
+            rb = {k: hb[k].to(dev) for k in keys}
+            m3 = new_model(mode)
+            n3 = max(min(args.steps, 6), 3)
+            f3, r3 = resident_arm(m3, h3, w3, b3, rb, n3, 3, world, dev, pg, barrier, max_over_ranks)
+            extra_cfg[name] = {"workload": d3, "math": mode, "dtype": DTYPE[mode], "value": r3["value"], "unit": "pairs/s",
+                               "ms_per_step": r3["ms_per_step"], "steps": n3, "n_gpus": world, "loss": r3["loss"],
+                               "gpu_launches_per_step": r3["launches_per_step"]}
+            del f3, m3, rb, hb
+            torch.cuda.empty_cache()
+    if world == 1 and not args.no_extra:
         notes = {"fp32": "strict-parity path: every convolution in fp32 FFMA (no tensor cores); gradients at CPU-fp32 level",
                  "tf32": "every DenseLayer / transition convolution with plain tf32 operands (what cuDNN runs the reference's "
                          "convolutions in by default): depth maps within 2e-2 of the fp64 oracle (measured 1.3e-3)",
                  "tf32x3": "3xTF32 forward (fp32-grade: depth maps within 2e-6 of the fp64 oracle), tf32 / bf16-operand gradients",
                  "bf16x3": "two-term bf16 forward (depth maps within 2e-5 of the fp64 oracle), tf32 / bf16-operand gradients"}
-        for mode in ("fp32", "tf32", "tf32x3", "bf16x3"):
+        for mode in ("fp32", "tf32", "tf32x3"):
             if mode == math_mode:
                 continue
             m2 = new_model(mode)
             f2, r2 = resident_arm(m2, h, w, bsz, resident, max(args.steps // 2, 3), 3, world, dev, pg, barrier, max_over_ranks)
-            roof2, kern2 = kernel_breakdown(f2, resident, h, w, bsz, peaks, barrier, mode)
+            roof2, kern2 = kernel_breakdown(m2, resident, h, w, bsz, peaks, barrier, mode, pg)
             other_arms[mode] = {"dtype": DTYPE[mode], "value": r2["value"], "unit": "pairs/s", "ms_per_step": r2["ms_per_step"],
                                 "gpu_launches": r2["launches"], "loss": r2["loss"], "roofline": roof2, "kernels": kern2,
                                 "note": notes[mode]}
@@ -642,8 +698,9 @@ def main():
                            "model": "FCDenseNet57 (Kaiming init, finalConv conditioned: weight x0.05, bias 1 -> depth ~[0.7,1.3])", "parallelism": f"dp{world}", "math": math_mode,
                            "l2": "per-step working set (~3 GB of activations and gradients) >> 126 MB L2: no explicit flush",
                            "loss": res["loss"]},
-                "e2e": e2e, "gpu_launches": res["launches"], "clocks": sampler.summary(), "roofline": roofline,
-                "kernels": kernels, "other_math_modes": other_arms, "warp_layer": warp_layer, "cpu_baseline": cpu}
+                "e2e": e2e, "gpu_launches": res["launches"], "gpu_launches_per_step": res["launches_per_step"], "clocks": sampler.summary(), "roofline": roofline,
+                "kernels": kernels, "other_math_modes": other_arms, "other_configs": extra_cfg, "warp_layer": warp_layer,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "endo_sgd_workspace_bytes": (c_size_t, [c_longlong]),
     "endo_sgd_clip_step": (c_int, [_P, _P, _P, c_longlong, c_float, c_float, c_float, c_int, _P, _P, _P, c_size_t,
                                    _P]),
+    "endo_sgd_clip_step_dev": (c_int, [_P, _P, _P, c_longlong, _P, c_float, c_float, _P, _P, _P, c_size_t, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -145,7 +146,7 @@ _ws_cache = {}
 def workspace(device, nbytes: int) -> torch.Tensor:
     """Per (device, stream) scratch with a zeroed, self-resetting counter header (see endo_b200.h)."""
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream)
+           torch.cuda.current_stream(device).cuda_stream, torch.cuda.is_current_stream_capturing())
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)

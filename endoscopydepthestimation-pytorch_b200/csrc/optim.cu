@@ -43,8 +43,9 @@ grad_sqnorm_kernel(const float* __restrict__ g, long long n, unsigned* counter, 
 __global__ void __launch_bounds__(kOT)
 sgd_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, long long n, float lr,
                 float momentum, float max_norm, int first_step, const float* __restrict__ finite_flag,
-                const double* __restrict__ total) {
+                const double* __restrict__ total, const float* __restrict__ lr_dev) {
     if (finite_flag && finite_flag[0] == 0.0f) return;            // device-side NaN guard (train.py:317-322)
+    if (lr_dev) lr = lr_dev[0];                                   // learning rate as a device scalar (CUDA-graph replay + LR schedule)
     const float norm = (float)sqrt(total[0]);
     const float raw = max_norm / (norm + 1.0e-6f);                // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
     const float coef = (raw > 1.0f) ? 1.0f : raw;                 // a NaN norm stays NaN (torch.clamp keeps NaN)
@@ -85,9 +86,9 @@ extern "C" size_t endo_sgd_workspace_bytes(long long n) {
     return ENDO_WS_HEADER_BYTES + sizeof(double) * (size_t)(sgd_blocks(n) + 2) + 64;
 }
 
-extern "C" int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long long n, float lr,
-                                  float momentum, float max_norm, int first_step, const float* finite_flag,
-                                  float* grad_norm_out, void* ws, size_t ws_bytes, endo_stream_t stream) {
+static int sgd_clip_step(float* params, float* grads, float* momentum_buf, long long n, float lr, const float* lr_dev,
+                         float momentum, float max_norm, int first_step, const float* finite_flag,
+                         float* grad_norm_out, void* ws, size_t ws_bytes, endo_stream_t stream) {
     if (n <= 0) return ENDO_ERR_BAD_SHAPE;
     if (!params || !grads || !momentum_buf) return ENDO_ERR_BAD_POINTER;
     if (!aligned16(params) || !aligned16(grads) || !aligned16(momentum_buf)) return ENDO_ERR_BAD_POINTER;
@@ -102,7 +103,22 @@ extern "C" int endo_sgd_clip_step(float* params, float* grads, float* momentum_b
     ENDO_CHECK_LAUNCH();
     const int nb2 = cdiv(cdiv(n, 4), kOT);
     sgd_clip_kernel<<<nb2, kOT, 0, s>>>(params, grads, momentum_buf, n, lr, momentum, max_norm, first_step,
-                                        finite_flag, total);
+                                        finite_flag, total, lr_dev);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
+}
+
+extern "C" int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long long n, float lr,
+                                  float momentum, float max_norm, int first_step, const float* finite_flag,
+                                  float* grad_norm_out, void* ws, size_t ws_bytes, endo_stream_t stream) {
+    return sgd_clip_step(params, grads, momentum_buf, n, lr, nullptr, momentum, max_norm, first_step, finite_flag,
+                         grad_norm_out, ws, ws_bytes, stream);
+}
+
+extern "C" int endo_sgd_clip_step_dev(float* params, float* grads, float* momentum_buf, long long n, const float* lr_dev,
+                                      float momentum, float max_norm, const float* finite_flag, float* grad_norm_out,
+                                      void* ws, size_t ws_bytes, endo_stream_t stream) {
+    if (!lr_dev) return ENDO_ERR_BAD_POINTER;
+    return sgd_clip_step(params, grads, momentum_buf, n, 0.f, lr_dev, momentum, max_norm, 0, finite_flag, grad_norm_out, ws,
+                         ws_bytes, stream);
 }

@@ -17,6 +17,28 @@ class FusedClipSGD:
         self.grad_norm = None
         self.steps = 0
 
+    def step_graph(self, lr_dev, finite_flag=None):
+        """The same update with the learning rate read from the device scalar `lr_dev` and no step-dependent launch
+        parameter (capturable in a CUDA graph; the momentum buffer starts at zero, which reproduces torch's first step)."""
+        net = self.net
+        flat, grad = net.flat_params, net.flat_grads
+        if flat is None:
+            raise RuntimeError("FusedClipSGD.step_graph() before the first forward/backward of the network")
+        L.require_cuda(flat, grad, lr_dev)
+        if self.buf is None or self.buf.numel() != flat.numel() or self.buf.device != flat.device:
+            self.buf = torch.zeros_like(flat)
+            self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat.device)
+            self.steps = 0
+        lib = L.lib()
+        n = flat.numel()
+        ws = L.workspace(flat.device, lib.endo_sgd_workspace_bytes(n))
+        with torch.cuda.device(flat.device):
+            L.check(lib.endo_sgd_clip_step_dev(flat.data_ptr(), grad.data_ptr(), self.buf.data_ptr(), n, lr_dev.data_ptr(),
+                                               self.momentum, self.max_norm, L.ptr(finite_flag), self.grad_norm.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), L.stream_ptr(flat.device)), "sgd_clip_step_dev")
+        self.steps += 1
+        return self.grad_norm
+
     def step(self, finite_flag=None, lr=None):
         net = self.net
         flat, grad = net.flat_params, net.flat_grads

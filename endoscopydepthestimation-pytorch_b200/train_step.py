@@ -102,3 +102,105 @@ class TrainStep:
 
 def is_bad(loss_value: float) -> bool:
     return math.isnan(loss_value) or math.isinf(loss_value)                           # train.py:317
+
+
+class GraphedTrainStep:
+    """The whole optimisation step (train.py:272-328) captured ONCE in a CUDA graph and replayed per step.
+
+    The step has no host-side control flow: the NaN guard of train.py:317-322 is the device-side is-finite flag of the
+    fused optimiser tail, the learning rate is a device scalar (`set_lr`, so an LR schedule does not invalidate the
+    graph) and the BatchNorm / optimiser state lives in fixed flat arrays.  Inputs are copied into fixed device buffers:
+
+        ts = GraphedTrainStep(net, h, w, example_batch)            # warm-up + capture
+        loss, dcl, sfl = ts.step(device_batch)                      # D2D into the static inputs + one graph launch
+        # host-resident batches (pinned memory) with the copy of step i+1 overlapping the compute of step i:
+        ts.prefetch(host_batch0)
+        for batch in loader:                                        # batch = the NEXT step's pinned host tensors
+            ts.swap_in(); ts.prefetch(batch); loss, dcl, sfl = ts.replay(); value = loss.item()
+
+    On several GPUs the gradient all-reduce runs between two graphs (forward + backward | optimiser tail)."""
+
+    def __init__(self, net, height, width, example_batch, lr=1.0e-3, momentum=0.9, max_norm=10.0, dcl_weight=5.0,
+                 sfl_weight=20.0, epsilon=1.0e-8, pair=True, process_group=None, warmup=3):
+        from .synthetic import BATCH_KEYS_H2D
+        self.keys = [k for k in BATCH_KEYS_H2D if k in example_batch]
+        dev = next(net.parameters()).device
+        self.dev = dev
+        self.net = net
+        self.inner = TrainStep(net, height, width, lr=lr, momentum=momentum, max_norm=max_norm, dcl_weight=dcl_weight,
+                               sfl_weight=sfl_weight, epsilon=epsilon, pair=pair, process_group=process_group)
+        self.world, self.pg = self.inner.world, process_group
+        self.static = {k: example_batch[k].to(dev, copy=True) for k in self.keys}
+        self.staging = {k: torch.empty_like(v) for k, v in self.static.items()}
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copy_done = torch.cuda.Event()
+        self.staging_free = torch.cuda.Event()
+        self.staging_free.record(torch.cuda.current_stream(dev))
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.static.values())
+        from . import _lib
+        # warm-up on a side stream (allocator, lazily created library state: per-device kernel attributes, side-stream pool)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 2)):
+                self._eager_fwd_bwd()
+                self._eager_tail()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        n0 = _lib.launch_count()
+        self.g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_main):
+            self._eager_fwd_bwd()
+            if self.world == 1:
+                self._eager_tail()
+        self.g_tail = None
+        if self.world > 1:
+            self.g_tail = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_tail):
+                self._eager_tail()
+        self.launches_per_step = int(_lib.launch_count() - n0)     # library kernels captured = launched by every replay
+
+    def _eager_fwd_bwd(self):
+        self.loss, self.dcl, self.sfl, _ = self.inner.stack.forward_backward(self.net, self.static, pair=self.inner.pair)
+        self.finite = torch.isfinite(self.loss).to(torch.float32).reshape(1)
+
+    def _eager_tail(self):
+        self.inner.opt.step_graph(self.lr_dev, finite_flag=self.finite)
+
+    def set_lr(self, lr):
+        self.lr_dev.fill_(float(lr))
+
+    @property
+    def grad_norm(self):
+        return self.inner.opt.grad_norm
+
+    def replay(self):
+        self.g_main.replay()
+        if self.world > 1:
+            from . import ddp
+            ddp.allreduce_gradients(self.net, self.finite, self.pg)
+            self.g_tail.replay()
+        return self.loss, self.dcl, self.sfl
+
+    def step(self, batch):
+        """`batch`: device tensors (copied into the graph's static inputs unless they already are them)."""
+        for k in self.keys:
+            if batch[k].data_ptr() != self.static[k].data_ptr():
+                self.static[k].copy_(batch[k], non_blocking=True)
+        return self.replay()
+
+    def prefetch(self, host_batch):
+        """Asynchronous H2D copy of a (pinned) host batch into the staging buffers on the copy stream."""
+        self.copy_stream.wait_event(self.staging_free)
+        with torch.cuda.stream(self.copy_stream):
+            for k in self.keys:
+                self.staging[k].copy_(host_batch[k], non_blocking=True)
+            self.copy_done.record(self.copy_stream)
+
+    def swap_in(self):
+        """Make the prefetched batch the graph's input (device-to-device, ~45 MB at bs8 256x320: tens of microseconds)."""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.copy_done)
+        torch._foreach_copy_([self.static[k] for k in self.keys], [self.staging[k] for k in self.keys])
+        self.staging_free.record(cur)

@@ -207,6 +207,14 @@ int endo_sgd_clip_step(float* params, float* grads, float* momentum_buf, long lo
                        float momentum, float max_norm, int first_step, const float* finite_flag,
                        float* grad_norm_out, void* ws, size_t ws_bytes, endo_stream_t stream);
 
+/* The same step with NOTHING step-dependent in the launch parameters, so that a CUDA graph of the whole optimisation
+ * step (train.py:272-328) can be replayed under a learning-rate schedule (train.py:203, scheduler.py): the learning rate is
+ * read from the device scalar lr_dev[0], and `momentum_buf` must be ZERO before the first step (momentum * 0 + g == g is
+ * exactly torch.optim.SGD's first-step initialisation, so no first_step flag is needed). */
+int endo_sgd_clip_step_dev(float* params, float* grads, float* momentum_buf, long long n, const float* lr_dev,
+                           float momentum, float max_norm, const float* finite_flag, float* grad_norm_out, void* ws,
+                           size_t ws_bytes, endo_stream_t stream);
+
 /* Development aid: copies the clock64() trace that CTA 0 of the last tensor-core forward launch recorded when
  * ENDO_TC_DEBUG has bit 4 set (tools/trace_fwd.py decodes it).  Synchronises the device. */
 int endo_debug_trace_read(long long* host_out, int n);

@@ -44,7 +44,7 @@ def main(only=None):
         for tag in only:
             b, h, w, seed, perturb, cond, sp, stride, iters = table[tag]
             record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb=perturb, conditioned=cond, sparse_prob=sp,
-                        stride=stride, iters=iters)
+                        stride=stride, iters=iters, forward_only=(tag == "step_d"))
         return
     import endo_b200
     from oracle import net as onet
@@ -148,16 +148,21 @@ def main(only=None):
                 stride=4)
     # BASELINE.json configs[2]: bs32 256x320 (one iteration, scalars + a coarse depth map: the loss-parity case of the bf16 path)
     record_step(ref_models, ref_losses, "step_d", 32, 256, 320, 20085, perturb=False, conditioned=True, sparse_prob=0.005,
-                stride=8, iters=1)
+                stride=8, iters=1, forward_only=True)
 
 
 STEP_TENSORS = ("firstconv.weight", "finalConv.weight", "denseBlocksUp.4.layers.3.conv.weight",
                 "denseBlocksDown.2.layers.1.norm.weight")
 
 
-def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned, sparse_prob=0.02, stride=1, iters=2):
+def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned, sparse_prob=0.02, stride=1, iters=2,
+                forward_only=False):
     """Two iterations of train.py:272-328 on the unmodified reference modules; records the loss terms, the gradient norm,
-    per-tensor gradient / weight norms and a few tensors.  `stride` subsamples the stored maps (large configurations)."""
+    per-tensor gradient / weight norms and a few tensors.  `stride` subsamples the stored maps (large configurations).
+    `forward_only`: train.py:272-315 under no_grad (BatchNorm in training mode), loss terms and maps only -- the bs32
+    case: autograd would keep ~46 GB of activations alive for the two 32-image forwards, more than this container has."""
+    if forward_only:
+        torch.set_grad_enabled(False)
     import endo_b200
     from oracle import net as onet
     cfg = onet.FCDENSENET57
@@ -195,6 +200,11 @@ def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned
         w12, i2 = warp([s2, s1, B["boundaries"], B["translations_2_wrt_1"], B["rotations_2_wrt_1"], B["intrinsics"]])
         dcl = 5.0 * 0.5 * (ndl([s1, w21, i1, B["intrinsics"]]) + ndl([s2, w12, i2, B["intrinsics"]]))
         loss = dcl + sfl
+        if forward_only:
+            rec["loss"].append(loss.item()); rec["dcl"].append(dcl.item()); rec["sfl"].append(sfl.item())
+            sub = (slice(None), slice(None), slice(None, None, stride), slice(None, None, stride))
+            first.update(p1=np32(p1[sub]), p2=np32(p2[sub]), s1=np32(s1[sub]), w21=np32(w21[sub]), i1=np32(i1[sub]))
+            break
         opt.zero_grad()
         loss.backward()
         if it == 0 and conditioned:
@@ -213,6 +223,11 @@ def record_step(ref_models, ref_losses, tag, b, h, w, seed, perturb, conditioned
                 first.update(p2=np32(p2[sub]), inter_sum=np.array([float(i1.sum()), float(i2.sum())]))
     out = {k: np.array(v, dtype=np.float64) for k, v in rec.items()}
     out.update(first)
+    if forward_only:
+        torch.set_grad_enabled(True)
+        np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), meta=np.array([b, h, w, seed, stride]), **out)
+        print(tag, rec)
+        return
     params = dict(model.named_parameters())
     out["w_l2_after"] = np.array([params[k].double().norm().item() for k in names], dtype=np.float64)
     for k in STEP_TENSORS:

