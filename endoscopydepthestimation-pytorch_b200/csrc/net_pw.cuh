@@ -316,7 +316,7 @@ pw_gemm_kernel(const Args A) {
                 }
                 float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
                 if (quad_ok) {
-                    float4 xv[8], gv[8];
+                    float4 xv[8];
                     unsigned okmask = 0u;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
@@ -324,7 +324,8 @@ pw_gemm_kernel(const Args A) {
                         if (p < p_end) {
                             const size_t off = (size_t)p * A.out_C + A.out_off + n0;
                             xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off));
-                            gv[it] = *reinterpret_cast<const float4*>(A.out + off);
+                            // the same pixels of the next 64-channel column block: into the L2 now (even quads = every sector once)
+                            if (!(quad & 1) && n0 + 64 < A.N) tcconv::prefetch_l2(A.x + off + 64);
                             okmask |= 1u << it;
                         }
                     }
@@ -334,7 +335,6 @@ pw_gemm_kernel(const Args A) {
                             const int pl = warp * 16 + it * 2 + psub;
                             const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)pl * TB_PITCH + quad * 16);
                             const float4 xq = xv[it];
-                            float4 gq = gv[it];
                             const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
                             const float g0 = fmaf(ca[0], e0, cbt[0]) > 0.f ? d.x : 0.f;
                             const float g1 = fmaf(ca[1], e1, cbt[1]) > 0.f ? d.y : 0.f;
@@ -344,9 +344,8 @@ pw_gemm_kernel(const Args A) {
                             s1[1] += g1; s2[1] += g1 * (e1 * cs[1]);
                             s1[2] += g2; s2[2] += g2 * (e2 * cs[2]);
                             s1[3] += g3; s2[3] += g3 * (e3 * cs[3]);
-                            gq.x = fmaf(ca[0], g0, gq.x); gq.y = fmaf(ca[1], g1, gq.y);
-                            gq.z = fmaf(ca[2], g2, gq.z); gq.w = fmaf(ca[3], g3, gq.w);
-                            *reinterpret_cast<float4*>(A.out + (size_t)(p0 + pl) * A.out_C + A.out_off + n0) = gq;
+                            // out[p][ci] += a * g as one 16-byte L2 reduction (each element is touched once per launch)
+                            tcconv::red_add_v4(A.out + (size_t)(p0 + pl) * A.out_C + A.out_off + n0, ca[0] * g0, ca[1] * g1, ca[2] * g2, ca[3] * g3);
                         }
                     }
                 }
