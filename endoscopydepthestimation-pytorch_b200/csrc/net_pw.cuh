@@ -324,8 +324,6 @@ pw_gemm_kernel(const Args A) {
                         if (p < p_end) {
                             const size_t off = (size_t)p * A.out_C + A.out_off + n0;
                             xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off));
-                            // the same pixels of the next 64-channel column block: into the L2 now (even quads = every sector once)
-                            if (!(quad & 1) && n0 + 64 < A.N) tcconv::prefetch_l2(A.x + off + 64);
                             okmask |= 1u << it;
                         }
                     }

@@ -56,11 +56,16 @@ __device__ __forceinline__ float tf32_rn(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
-// DRAM -> L2 prefetch of the 32-byte sector at p (no destination register, no scoreboard entry): the staging loops below keep
-// only ONE pipeline step of loads in flight in registers, which bounds them by (bytes in flight) / (loaded DRAM latency ~2 us);
-// sectors several steps ahead are requested here so that the register loads later hit the L2 (r2: clock64 trace of the forward
-// producer showed ~2,000 of every ~4,200 cycles per channel chunk waiting for the single in-flight chunk).
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// 16-byte read-only load that asks the L2 to fetch the whole 256-byte-aligned block around it from DRAM.  The forward producers
+// walk the channels of a pixel chunk by chunk (32 or 64 bytes of a pixel per pipeline step, pixels 4*C bytes apart): without
+// the hint every step is one scattered 32-byte DRAM sector per pixel; with it the DRAM access is 256 contiguous bytes and the
+// following chunks of the pixel hit the L2.  (Explicit prefetch.global.L2 instructions several chunks ahead were measured
+// SLOWER, +5-10 % per kernel: they are cache-control operations competing for the same issue / LSU slots.)
+__device__ __forceinline__ float4 ldg_l2_256(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 // v += d as ONE 16-byte reduction performed by the L2 (REDG.E.ADD.F32x4): the read-modify-write of a gradient tile no longer
 // round-trips through the SM (no load to wait for, no registers held across the wait)
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -354,19 +359,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             for (int j = 0; j < NIT; ++j) {
                 cur[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if ((pixok & (1u << j)) && c_begin * 8 + cg * 4 < A.K)
-                    cur[j] = __ldg(reinterpret_cast<const float4*>(in_img + c_begin * 8 + poff[j]));
-            }
-            // DRAM -> L2 prefetch distance in chunks (one chunk = one 32-byte sector per pixel; the even thread of a pixel asks)
-            constexpr int PFD = 6;
-            if (cg == 0) {
-#pragma unroll 1
-                for (int d = 2; d < PFD; ++d) {
-                    if (c_begin + d < c_end && (c_begin + d) * 8 < A.K) {
-#pragma unroll
-                        for (int j = 0; j < NIT; ++j)
-                            if (pixok & (1u << j)) prefetch_l2(in_img + (c_begin + d) * 8 + poff[j]);
-                    }
-                }
+                    cur[j] = ldg_l2_256(in_img + c_begin * 8 + poff[j]);
             }
             for (int c = c_begin; c < c_end; ++c) {
                 const int it = c - c_begin;
@@ -377,13 +370,9 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
 #pragma unroll
                 for (int j = 0; j < NIT; ++j) {                        // prefetch chunk c + 1
                     nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if ((pixok & (1u << j)) && nxt_ok) nxt[j] = __ldg(reinterpret_cast<const float4*>(in_img + (c + 1) * 8 + poff[j]));
+                    if ((pixok & (1u << j)) && nxt_ok) nxt[j] = ldg_l2_256(in_img + (c + 1) * 8 + poff[j]);
                 }
-                if (cg == 0 && c + PFD < c_end && (c + PFD) * 8 < A.K) {
-#pragma unroll
-                    for (int j = 0; j < NIT; ++j)
-                        if (pixok & (1u << j)) prefetch_l2(in_img + (c + PFD) * 8 + poff[j]);
-                }
+
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
                 if (ch_ok && !A.up) {
                     const float* cf = A.coef + ((size_t)g * A.K + ch) * 4;
@@ -466,9 +455,6 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
             {
                 float4 q[10];
                 unsigned okmask = 0u;
-                // this path keeps no loads in flight across chunks: the sectors of the chunks 2 and 3 ahead go to the L2 now
-                const bool pf3 = !(grp & 1) && c + 3 < c_end && ch + 3 * kch < A.K;
-                const bool pf12 = !(grp & 1) && it == 0;
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
                     const int px = (tid >> 2) + 128 * j;
@@ -477,13 +463,7 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
                     const bool ok = ch_ok && (px < REAL_ROWS) && y >= 0 && y < A.H && x >= 0 && x < A.W && !(A.dbg & 2);
                     q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ok) {
-                        const float* src = in_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.in_C;
-                        q[j] = __ldg(reinterpret_cast<const float4*>(src));
-                        if (pf3) prefetch_l2(src + 3 * kch);
-                        if (pf12) {
-                            if (c + 1 < c_end && ch + kch < A.K) prefetch_l2(src + kch);
-                            if (c + 2 < c_end && ch + 2 * kch < A.K) prefetch_l2(src + 2 * kch);
-                        }
+                        q[j] = ldg_l2_256(in_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.in_C);
                         okmask |= 1u << j;
                     }
                 }
@@ -943,17 +923,6 @@ dense_dgrad_tf32_kernel(const Args A) {
                             } else {
                                 off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
                                 xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
-                                // the same pixels of the NEXT M-block (128 linear pixels further: + 3 rows + 26 columns, or the
-                                // next channel chunk of the first M-block) are requested into the L2 now: even channel quads
-                                // cover every 32-byte sector once
-                                if (!(quad & 1)) {
-                                    const bool wrap = mb + 1 == MBLK;
-                                    const int Ln = wrap ? PITCH + p : L + 128;
-                                    const int rn = Ln / PITCH, cn = Ln - rn * PITCH;
-                                    const int yn = y0 + rn - 1, xn = x0 + cn - 1;
-                                    if ((!wrap || (c + 1 < c_end && ci0 + NC + quad * 4 < A.Cin)) && (rn <= TH) && (cn >= 1) && (cn <= TW) && (yn < A.H) && (xn < A.W))
-                                        tcconv::prefetch_l2(A.x + ((size_t)(b * A.H + yn) * A.W + xn) * A.C + A.in_off + ci0 + (wrap ? NC : 0) + quad * 4);
-                                }
                             }
                             okmask |= 1u << it;
                         }
@@ -1211,39 +1180,6 @@ dense_wgrad_bf16_kernel(const Args A) {
             unsigned char* a_s = smem + s * STAGE;
             unsigned char* g_s = a_s + A_STAGE;
             const size_t img = (size_t)b * A.H * A.W;
-            // The staging below keeps no loads in flight across tiles (ncu r1: long-scoreboard stall 6.1 per issue): request the
-            // operand sectors of the tile after the next one (and, on the first tile, of the next one) into the L2 now.
-            for (int ahead = (it == 0 ? 1 : 2); ahead <= 2; ++ahead) {
-                const int tn = t + ahead;
-                if (tn >= t_end) break;
-                const int bn = tn / (tiles_x * tiles_y), remn = tn - bn * (tiles_x * tiles_y);
-                const int txn = remn / tiles_y, tyn = remn - txn * tiles_y;
-                const int y0n = tyn * TR, x0n = txn * TW;
-                {
-                    const int grp = tid & 7, ch = ci0 + grp * 8;
-                    const int sh = A.up ? 1 : 0, sW = A.W >> sh;
-                    const float* xa_n = A.xa + (size_t)bn * (A.H >> sh) * sW * A.xa_C + A.in_off + ch;
-                    if (ch < A.Cin) {
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            const int px = (tid >> 3) + 64 * j;
-                            const int r = px / PITCH, cc = px - r * PITCH;
-                            const int y = y0n + r - 1, x = x0n + cc - 1;
-                            if (px < A_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W && (!sh || !((x | y) & 1) || cc == 0 || r == 0))
-                                tcconv::prefetch_l2(xa_n + ((size_t)(y >> sh) * sW + (x >> sh)) * A.xa_C);
-                        }
-                    }
-                }
-                if (!A.one) {
-                    const int gpix = tid & 255, half = tid >> 8;
-                    const int y = y0n + (gpix >> 5), x = x0n + (gpix & 31);
-                    if (y < A.H && x < A.W && half * 8 < A.Cout) {
-                        const size_t oo = (((size_t)bn * A.H + y) * A.W + x) * A.C + A.out_off + half * 8;
-                        tcconv::prefetch_l2(A.g + oo); tcconv::prefetch_l2(A.x + oo);
-                        if (half * 8 + 4 < A.Cout) { tcconv::prefetch_l2(A.g + oo + 4); tcconv::prefetch_l2(A.x + oo + 4); }
-                    }
-                }
-            }
             // ---- activations: (pixel, 8-channel group) items, BN+ReLU, bf16
             {
                 const int grp = tid & 7;
