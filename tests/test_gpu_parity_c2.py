@@ -39,8 +39,10 @@ def _fixture_setup(tag):
 # fp32: the fp32 FFMA path must sit at the CPU-vs-CPU yardstick.  tf32x3: forward fp32-grade, data gradient with tf32
 # operands, weight gradient with bf16 operands (fp32 accumulate) -- what cuDNN's default TF32 convolutions give the
 # reference on a GPU, see bench.py --impl reference-gpu.
-GRAD_BOUNDS = {"fp32": dict(median=5e-4, p90=3e-3, max=2e-2, norm=2e-3),
-               "tf32x3": dict(median=3e-3, p90=1e-2, max=5e-2, norm=5e-3)}
+# Measured on B200 (profiles/r2_parity.md), bs8 256x320: fp32 4e-5 / 3e-4 / 2.4e-3, norm 8e-7; tf32x3 7e-5 / 4e-4 / 2.4e-3,
+# norm 5e-6; single tensors up to 3.8e-3 (a BatchNorm gamma gradient) -- the bounds leave ~4x.
+GRAD_BOUNDS = {"fp32": dict(median=2e-4, p90=1.5e-3, max=1.5e-2, norm=1e-4),
+               "tf32x3": dict(median=3e-4, p90=2e-3, max=1.5e-2, norm=1e-4)}
 
 
 @pytest.mark.parametrize("tag", ["step_b", "step_c"])
@@ -234,9 +236,9 @@ def test_run_to_run_reproducibility_bs8_256x320(math_mode):
 
 # BASELINE.json configs[2]: "1xB200 bs32 256x320, bf16 tensor-core conv path, warp layers fp32, loss parity vs reference".
 # Stated tolerances for the reduced-precision path (operands of the 3x3 convolutions rounded to bf16 = 8 significant bits,
-# fp32 accumulate / BatchNorm statistics / master weights; geometric layers and losses fp32): depth maps 2e-2 of their
-# scale, every loss term 5e-2 relative.  The fp32-grade tensor-core path must meet 1e-4 at this size as well.
-C3_TOL = {"bf16": dict(depth=2e-2, loss=5e-2), "tf32x3": dict(depth=DEPTH_TOL, loss=LOSS_TOL)}
+# fp32 accumulate / BatchNorm statistics / master weights; geometric layers and losses fp32): depth maps 1e-2 of their
+# scale, every loss term 1e-3 relative.  The fp32-grade tensor-core path must meet 1e-4 at this size as well.
+C3_TOL = {"bf16": dict(depth=1e-2, loss=1e-3), "tf32x3": dict(depth=DEPTH_TOL, loss=LOSS_TOL)}   # measured: 1.7e-3 / 7.7e-5
 
 
 @pytest.mark.parametrize("math_mode", ["bf16", "tf32x3"])
