@@ -128,3 +128,38 @@ extern "C" int endo_tc_probe(const float* A, const float* B, float* D, int a_row
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ TMA probe
+// out[box_h][box_w][box_c] = the box of an NHWC buffer at (c0, x0, y0, b), loaded by ONE cp.async.bulk.tensor (zero fill
+// outside the tensor): checks the tensor-map conventions the convolution kernels rely on (tests/test_gpu_tc_probe.py).
+#include "tma.cuh"
+namespace endo {
+__global__ void __launch_bounds__(128)
+tma_probe_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ out, int c0, int x0, int y0, int b, int n) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar;
+    if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc::mbar_expect_tx(&bar, (uint32_t)n * 4u);
+        tma::load_4d(smem, &map, c0, x0, y0, b, &bar);
+        tc::mbar_arrive(&bar);
+    }
+    tc::mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = reinterpret_cast<const float*>(smem)[i];
+}
+}  // namespace endo
+
+extern "C" int endo_tma_probe(const float* src, int B, int H, int W, int C, int box_c, int box_w, int box_h, int c0, int x0,
+                              int y0, int b, float* out, endo_stream_t stream) {
+    if (!src || !out) return ENDO_ERR_BAD_POINTER;
+    if (C % 4 || box_c % 4 || box_c > 256 || box_w > 256 || box_h > 256) return ENDO_ERR_BAD_SHAPE;
+    CUtensorMap map;
+    if (!endo::tma::make_nhwc_map(&map, src, B, H, W, C, box_c, box_w, box_h)) return ENDO_ERR_CUDA;
+    const int n = box_c * box_w * box_h;
+    if ((size_t)n * 4 > 200 * 1024) return ENDO_ERR_BAD_SHAPE;
+    ENDO_SET_MAX_SMEM(endo::tma_probe_kernel, 200 * 1024);
+    endo::tma_probe_kernel<<<1, 128, (size_t)n * 4, (cudaStream_t)stream>>>(map, out, c0, x0, y0, b, n);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}

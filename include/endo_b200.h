@@ -231,6 +231,11 @@ int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, i
                   int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles, int rotate,
                   endo_stream_t stream);   /* rotate > 1 (timing only): reps cycle over that many accumulator tiles */
 
+/* TMA bring-up probe (tests only): out[box_h][box_w][box_c] = the box of the NHWC fp32 buffer src[B][H][W][C] at channel c0,
+ * column x0, row y0 (either may be negative or overhang: zero fill) of image b, loaded by one cp.async.bulk.tensor. */
+int endo_tma_probe(const float* src, int B, int H, int W, int C, int box_c, int box_w, int box_h, int c0, int x0,
+                   int y0, int b, float* out, endo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

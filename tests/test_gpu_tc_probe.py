@@ -120,3 +120,27 @@ def test_tf32_operand_conversion_and_split_accuracy():
     e32 = float(((a @ b.t()).double() - ref_full).abs().max() / ref_full.abs().max())
     print(f"3xTF32 split: {e3:.2e}   (fp32 FFMA matmul: {e32:.2e})")
     assert e3 < 2e-6, e3
+
+
+@pytest.mark.parametrize("c0,x0,y0", [(0, 0, 0), (8, -1, -1), (40, 30, 50), (184, 300, 250)])
+def test_tma_box_load_with_zero_fill(c0, x0, y0):
+    """cp.async.bulk.tensor box of an NHWC level buffer: dense [h][w][c] block in shared memory, zero fill outside the
+    tensor (negative start coordinates, overhang past the right / bottom edge and past the last channel)."""
+    import ctypes
+    from endo_b200 import _lib as L
+    B, H, W, C = 2, 256, 320, 192
+    bc, bw, bh = 8, 34, 18
+    src = torch.randn(B, H, W, C, device="cuda")
+    out = torch.full((bh, bw, bc), 7.0, device="cuda")
+    L.check(L.lib().endo_tma_probe(src.data_ptr(), B, H, W, C, bc, bw, bh, c0, x0, y0, 1, out.data_ptr(),
+                                   L.stream_ptr(src.device)), "tma_probe")
+    torch.cuda.synchronize()
+    ref = torch.zeros(bh, bw, bc, device="cuda")
+    ys, xs, cs = range(y0, y0 + bh), range(x0, x0 + bw), range(c0, c0 + bc)
+    yv = [i for i, y in enumerate(ys) if 0 <= y < H]
+    xv = [i for i, x in enumerate(xs) if 0 <= x < W]
+    cv = [i for i, c in enumerate(cs) if 0 <= c < C]
+    if yv and xv and cv:
+        ref[yv[0]:yv[-1] + 1, xv[0]:xv[-1] + 1, cv[0]:cv[-1] + 1] = src[1, ys[yv[0]]:ys[yv[-1]] + 1, xs[xv[0]]:xs[xv[-1]] + 1,
+                                                                      cs[cv[0]]:cs[cv[-1]] + 1]
+    assert torch.equal(out, ref)
