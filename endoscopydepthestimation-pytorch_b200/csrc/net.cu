@@ -8,6 +8,7 @@
 #include "net_plan.cuh"
 #include "net_tc.cuh"
 #include "net_pw.cuh"
+#include "net_wgrad2.cuh"
 
 namespace endo {
 
@@ -359,6 +360,38 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
     return launch_conv<3, 6, 16, 4, LM_BNRELU, EM_STORE, WM_FWD, false>(a, c.s);
 }
 
+// Weight-gradient launch (DenseLayer / TransitionUp / TransitionDown 1x1 modes): the TMA-fed kernel of net_wgrad2.cuh, one
+// persistent CTA per SM (channel blocks x tile ranges); ENDO_TC_DISABLE bit 16384 selects the round-1 register-staged kernel.
+static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
+    const int yblocks = cdiv(cin, tcwgrad::MCH);
+    t.n_tiles = t.B * cdiv(t.H, tcwgrad::TR) * cdiv(t.W, tcwgrad::TW);
+    if (tc_disable_mask() & 16384) {
+        int want = (2 * kNumSMs) / yblocks;
+        if (want < 1) want = 1;
+        if (want > t.n_tiles) want = t.n_tiles;
+        t.tiles_per_cta = cdiv(t.n_tiles, want);
+        dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
+        ProfScope prof(cat, s);
+        tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, s>>>(t);
+        ENDO_CHECK_LAUNCH();
+        return ENDO_OK;
+    }
+    int want = kNumSMs / yblocks;                            // one wave of persistent CTAs
+    if (want < 1) want = 1;
+    if (want > t.n_tiles) want = t.n_tiles;
+    t.tiles_per_cta = cdiv(t.n_tiles, want);
+    const int sh = t.up ? 1 : 0;
+    CUtensorMap xmap;
+    if (!tma::make_nhwc_map(&xmap, t.xa, t.B, t.H >> sh, t.W >> sh, t.xa_C, tcwgrad::MCH, tcwgrad::TW >> sh, tcwgrad::TR >> sh))
+        return ENDO_ERR_CUDA;
+    ENDO_SET_MAX_SMEM(tcwgrad2::dense_wgrad_tma_kernel, tcwgrad2::SMEM_BYTES);
+    dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
+    ProfScope prof(cat, s);
+    tcwgrad2::dense_wgrad_tma_kernel<<<grid, tcwgrad2::NTHREADS, tcwgrad2::SMEM_BYTES, s>>>(t, xmap);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
 static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     const NetPlan& P = c.P;
     const int l = d.level;
@@ -387,17 +420,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.xa = c.X(l); t.xa_C = P.Ctot[l]; t.up = 0; t.one = 0;
         t.C = P.Ctot[l]; t.in_off = d.in_off; t.Cin = d.cin; t.out_off = d.out_off; t.Cout = d.conv.cout;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
-        t.n_tiles = P.B * cdiv(t.H, tcwgrad::TR) * cdiv(t.W, tcwgrad::TW);
-        const int yblocks = cdiv(d.cin, tcwgrad::MCH);
-        int want = (2 * kNumSMs) / yblocks;
-        if (want < 1) want = 1;
-        if (want > t.n_tiles) want = t.n_tiles;
-        t.tiles_per_cta = cdiv(t.n_tiles, want);
-        ENDO_SET_MAX_SMEM(tcwgrad::dense_wgrad_bf16_kernel, tcwgrad::SMEM_BYTES);
-        dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
-        ProfScope prof(PC_WGRAD, c.sw);
-        tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(t);
-        ENDO_CHECK_LAUNCH();
+        ENDO_TRY(launch_wgrad_tc(t, d.cin, c.sw, PC_WGRAD));
     } else if (d.conv.cout == 12) {
         ENDO_TRY((launch_wgrad2<3, 12, 1, 4, LM_BNRELU, LM_GRAD, false>(w, c.sw)));
     } else {
@@ -519,7 +542,6 @@ static int trans_down_bwd(const Ctx& c, int l) {
     if (is_tc(c.math) && !(tc_disable_mask() & 32)) {
         // tcgen05 (bf16): the weight-gradient kernel in 1x1 mode, 48 output channels per launch; bias gradient = sum of the
         // routed (= of the pooled) gradient, reduced over the coarse buffer
-        ENDO_SET_MAX_SMEM(tcwgrad::dense_wgrad_bf16_kernel, tcwgrad::SMEM_BYTES);
         {
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
             bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.sw>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
@@ -535,16 +557,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
             q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
             q.one = 1; q.argmax = am; q.gc = c.GX(l + 1); q.xc = c.X(l + 1); q.abc = c.AB(l + 1); q.cC = P.Ctot[l + 1];
             q.c_off = P.offIn[l + 1]; q.cH = P.h[l + 1]; q.cW = P.w[l + 1];
-            q.n_tiles = P.B * cdiv(q.H, tcwgrad::TR) * cdiv(q.W, tcwgrad::TW);
-            const int yblocks = cdiv(cs, tcwgrad::MCH);
-            int want = (2 * kNumSMs) / yblocks;
-            if (want > q.n_tiles) want = q.n_tiles;
-            if (want < 1) want = 1;
-            q.tiles_per_cta = cdiv(q.n_tiles, want);
-            dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
-            ProfScope prof(PC_WGRAD_TRANS, c.sw);
-            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(q);
-            ENDO_CHECK_LAUNCH();
+            ENDO_TRY(launch_wgrad_tc(q, cs, c.sw, PC_WGRAD_TRANS));
         }
     } else {
         ENDO_TRY((launch_wgrad2<1, 48, 1, 8, LM_BNRELU, LM_GRADPOOL, false>(w, c.sw)));
@@ -630,7 +643,6 @@ static int trans_up_bwd(const Ctx& c, int i) {
     if (is_tc(c.math) && !(tc_disable_mask() & 16)) {
         // tcgen05 (bf16): the DenseLayer weight-gradient kernel with the upsampling loader, 16 output channels per pass;
         // the bias gradient comes from the small dedicated reduction
-        ENDO_SET_MAX_SMEM(tcwgrad::dense_wgrad_bf16_kernel, tcwgrad::SMEM_BYTES);
         if (!dgrad_tc) {                                  // otherwise the data-gradient passes below produce the bias gradient
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
             bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.sw>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
@@ -644,16 +656,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
             q.xa = c.X(ls); q.xa_C = P.Ctot[ls]; q.up = 1; q.one = 0;
             q.C = P.Ctot[l]; q.in_off = t.src_off; q.Cin = t.cin; q.out_off = co0; q.Cout = nco;
             q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
-            q.n_tiles = P.B * cdiv(q.H, tcwgrad::TR) * cdiv(q.W, tcwgrad::TW);
-            const int yblocks = cdiv(t.cin, tcwgrad::MCH);
-            int want = (2 * kNumSMs) / yblocks;
-            if (want > q.n_tiles) want = q.n_tiles;
-            if (want < 1) want = 1;
-            q.tiles_per_cta = cdiv(q.n_tiles, want);
-            dim3 grid(cdiv(q.n_tiles, q.tiles_per_cta), yblocks, 1);
-            ProfScope prof(PC_WGRAD_TRANS, c.sw);
-            tcwgrad::dense_wgrad_bf16_kernel<<<grid, tcwgrad::NTHREADS, tcwgrad::SMEM_BYTES, c.sw>>>(q);
-            ENDO_CHECK_LAUNCH();
+            ENDO_TRY(launch_wgrad_tc(q, t.cin, c.sw, PC_WGRAD_TRANS));
         }
     } else {
         ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_PLAIN, LM_GRAD, true>(w, c.sw)));

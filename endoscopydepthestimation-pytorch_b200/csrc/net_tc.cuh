@@ -758,8 +758,7 @@ constexpr int W_BYTES = 9 * 2 * WBLK_BYTES;               // 36,864
 constexpr int TB_PITCH = NC * 4 + 16;                     // 272 B per pixel row (bank spread)
 constexpr int TB_BYTES = 128 * TB_PITCH;                  // 34,816
 constexpr int NBUF = 8;                                   // TMEM accumulator buffers (8 x 64 = 512 columns)
-constexpr int XRING_BYTES = 2 * 8 * 256 * 16;             // two units of activation rows: 8 x 16 B per epilogue thread each
-constexpr int SMEM_BYTES = G_BYTES + W_BYTES + TB_BYTES + NC * 4 * 4 + 8 * NC * 2 * 4 + 256 + XRING_BYTES;
+constexpr int SMEM_BYTES = G_BYTES + W_BYTES + TB_BYTES + NC * 4 * 4 + 8 * NC * 2 * 4 + 256;
 constexpr int NTHREADS = 288;
 
 struct Args {
@@ -872,163 +871,138 @@ dense_dgrad_tf32_kernel(const Args A) {
         }
         const int q = warp & 3, chalf = warp >> 2;            // TMEM lane quadrant, column half (32 columns)
         const int quad = lane & 15, psub = lane >> 4;         // phase-2 mapping: channel quad, pixel parity
-        // ---- per-unit epilogue, software-pipelined through SHARED MEMORY: the activation rows of unit n + 1 (the only global data
-        //      phase 2 waits for, now that the gradient accumulate is an L2 reduction) are requested with cp.async BEFORE unit n is
-        //      drained and combined, into a two-deep ring of thread-private 16-byte slots (no barrier: a thread reads back exactly
-        //      what it copied).  A register double buffer was measured 39 % SLOWER: the hardware tracks in-flight loads with six
-        //      scoreboard counters per warp, and re-targeting a register buffer waits for the counter it shares with the buffer
-        //      still in flight (r2 ncu: 28 % of the samples on the address arithmetic of the second batch).  cp.async copies are
-        //      tracked by commit groups instead.  Units are numbered over (channel chunk, M-block).
-        const int n_units = (c_end - c_begin) * MBLK;
-        const float* x_img = A.x + (size_t)b * A.H * A.W * A.C;
-        float* gout_img = A.plain ? A.po + (size_t)b * A.H * A.W * A.oC : A.gout + (size_t)b * A.H * A.W * A.C;
-        unsigned char* xring = tb + TB_BYTES + NC * 4 * 4 + 8 * NC * 2 * 4 + 256;     // [2][8][256 threads][16 B]
-        uint32_t off_cur[8], off_nxt[8];
-        unsigned ok_cur = 0u, ok_nxt = 0u;
-        auto issue_x = [&](int n) {                                  // offsets + cp.async of unit n -> (off_nxt, ok_nxt), ring[n & 1]
-            ok_nxt = 0u;
-            if (n < n_units) {
-                const int cn = n / MBLK, mb = n - cn * MBLK;
-                const int ci = (c_begin + cn) * NC + quad * 4;
-                if (ci < A.Cin) {
+        int unit = 0;
+        for (int c = c_begin; c < c_end; ++c) {
+            const int ci0 = c * NC;
+            // ------------------------------------------------------------ weights + BN table of this ci chunk
+            {   // 36,864-byte weight image of this chunk, copied verbatim (9 x 16 B per thread, all loads first)
+                const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 9216);
+                float4 wq[9];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
+                for (int j = 0; j < 9; ++j) wq[j] = __ldg(src + tid + 256 * j);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) *reinterpret_cast<float4*>(w_s + (size_t)(tid + 256 * j) * 16) = wq[j];
+            }
+            if (tid < NC) {
+                const int ci = ci0 + tid;
+                float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ci < A.Cin && !A.plain) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)g * A.Cin + ci) * 4));
+                *reinterpret_cast<float4*>(ctab + tid * 4) = e;
+            }
+            tc::fence_proxy_async();
+            tc::mbar_arrive(bars + 0);                         // w_full: phase c
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // ctab visible to all epilogue threads
+            // per-lane constants for the 4 channels this lane owns in phase 2
+            float ca[4], cb[4], cm[4], cs[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 t4 = *reinterpret_cast<const float4*>(ctab + (quad * 4 + e) * 4);
+                ca[e] = t4.x; cb[e] = t4.y; cm[e] = t4.z; cs[e] = t4.w;
+            }
+            const bool quad_ok = (ci0 + quad * 4) < A.Cin;
+            float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int mb = 0; mb < MBLK; ++mb, ++unit) {
+                const int buf = unit % NBUF;
+                // the activations / gradient rows this lane will update (phase 2) do not depend on the accumulator: request them
+                // first, so that they travel while the MMAs finish, the accumulator is drained and the warps meet at the barrier
+                float4 xv[8];
+                unsigned okmask = 0u;
+                size_t off[8];
+                if (quad_ok) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {                     // all 8 loads of this unit in flight at once
                         const int p = warp * 16 + it * 2 + psub;
-                        const int Lp = PITCH + mb * 128 + p;
-                        const int r = Lp / PITCH, cc = Lp - r * PITCH;
+                        const int L = PITCH + mb * 128 + p;
+                        const int r = L / PITCH, cc = L - r * PITCH;
                         const int y = y0 + r - 1, x = x0 + cc - 1;
-                        off_nxt[it] = 0u;
+                        off[it] = 0;
                         if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
                             if (A.plain) {
-                                off_nxt[it] = (uint32_t)((y * A.W + x) * A.oC + A.o_off + ci);
+                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.oC + A.o_off + ci0 + quad * 4;
                             } else {
-                                off_nxt[it] = (uint32_t)((y * A.W + x) * A.C + A.in_off + ci);
-                                tc::cp_async16(xring + ((size_t)(((n & 1) * 8 + it) * 256 + tid)) * 16, x_img + off_nxt[it], 16u);
+                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
+                                xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
                             }
-                            ok_nxt |= 1u << it;
+                            okmask |= 1u << it;
                         }
                     }
                 }
-            }
-            tc::cp_async_commit();                                   // one group per unit, empty or not
-        };
-        float ca[4], cb[4], cm[4], cs[4];                         // per-lane BN constants of the current chunk (phase 2)
-        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-        issue_x(0);
-#pragma unroll 1
-        for (int n = 0; n < n_units; ++n) {
+                tc::mbar_wait(bars + 1 + buf, (unit / NBUF) & 1);
+                tc::tc_fence_after();
+                // phase 1: TMEM -> registers -> transposed shared tile [pixel][channel]
+                {
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * NC + chalf * 32;
+                    float v[16];
+                    unsigned char* row = tb + (size_t)(q * 32 + lane) * TB_PITCH + chalf * 128;
+                    tc::tmem_ld16(taddr, v);
 #pragma unroll
-            for (int it = 0; it < 8; ++it) off_cur[it] = off_nxt[it];
-            ok_cur = ok_nxt;
-            issue_x(n + 1);
-            const int cn = n / MBLK, mb = n - cn * MBLK;
-            const int c = c_begin + cn, ci0 = c * NC;
-            const int buf = n % NBUF;
-            if (mb == 0) {
-                // -------------------------------------------------------- weights + BN table of this ci chunk
-                {   // 36,864-byte weight image of this chunk, copied verbatim (9 x 16 B per thread, all loads first)
-                    const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 9216);
-                    float4 wq[9];
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(row + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    tc::tmem_ld16(taddr + 16, v);
 #pragma unroll
-                    for (int j = 0; j < 9; ++j) wq[j] = __ldg(src + tid + 256 * j);
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) *reinterpret_cast<float4*>(w_s + (size_t)(tid + 256 * j) * 16) = wq[j];
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(row + 64 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                if (tid < NC) {
-                    const int ci = ci0 + tid;
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ci < A.Cin && !A.plain) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)g * A.Cin + ci) * 4));
-                    *reinterpret_cast<float4*>(ctab + tid * 4) = e;
-                }
-                tc::fence_proxy_async();
-                tc::mbar_arrive(bars + 0);                         // w_full: phase c
-                asm volatile("bar.sync 1, 256;" ::: "memory");     // ctab visible to all epilogue threads
+                tc::tc_fence_before();
+                asm volatile("bar.sync 1, 256;" ::: "memory");               // all 8 warps have drained their TMEM part
+                if (chalf == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);      // 128 arrivals: accumulator buffer free again
+                // phase 2: lane = (pixel parity, channel quad); 16 pixels per warp
+                if (quad_ok) {
+                    if (A.plain) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(ctab + (quad * 4 + e) * 4);
-                    ca[e] = t4.x; cb[e] = t4.y; cm[e] = t4.z; cs[e] = t4.w;
-                    s1[e] = 0.f; s2[e] = 0.f;
-                }
-            }
-            tc::mbar_wait(bars + 1 + buf, (n / NBUF) & 1);
-            tc::tc_fence_after();
-            // phase 1: TMEM -> registers -> transposed shared tile [pixel][channel]
-            {
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * NC + chalf * 32;
-                float v[16];
-                unsigned char* row = tb + (size_t)(q * 32 + lane) * TB_PITCH + chalf * 128;
-                tc::tmem_ld16(taddr, v);
+                        for (int it = 0; it < 8; ++it) {
+                            if (okmask & (1u << it)) {
+                                const int p = warp * 16 + it * 2 + psub;
+                                const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
+                                if (A.first) *reinterpret_cast<float4*>(A.po + off[it]) = d;
+                                else tcconv::red_add_v4(A.po + off[it], d.x, d.y, d.z, d.w);
+                            }
+                        }
+                    } else
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(row + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                tc::tmem_ld16(taddr + 16, v);
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(row + 64 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            tc::tc_fence_before();
-            tc::cp_async_wait<1>();                                      // this thread's copies of unit n have landed (unit n + 1 may fly)
-            asm volatile("bar.sync 1, 256;" ::: "memory");               // all 8 warps have drained their TMEM part
-            if (chalf == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);      // 128 arrivals: accumulator buffer free again
-            // phase 2: lane = (pixel parity, channel quad); 16 pixels per warp
-            if (A.plain) {
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    if (ok_cur & (1u << it)) {
-                        const int p = warp * 16 + it * 2 + psub;
-                        const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
-                        if (A.first) *reinterpret_cast<float4*>(gout_img + off_cur[it]) = d;
-                        else tcconv::red_add_v4(gout_img + off_cur[it], d.x, d.y, d.z, d.w);
+                    for (int it = 0; it < 8; ++it) {
+                        if (okmask & (1u << it)) {
+                            const int p = warp * 16 + it * 2 + psub;
+                            const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
+                            const float4 xq = xv[it];
+                            const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
+                            const float g0 = fmaf(ca[0], e0, cb[0]) > 0.f ? d.x : 0.f;
+                            const float g1 = fmaf(ca[1], e1, cb[1]) > 0.f ? d.y : 0.f;
+                            const float g2 = fmaf(ca[2], e2, cb[2]) > 0.f ? d.z : 0.f;
+                            const float g3 = fmaf(ca[3], e3, cb[3]) > 0.f ? d.w : 0.f;
+                            s1[0] += g0; s2[0] += g0 * (e0 * cs[0]);
+                            s1[1] += g1; s2[1] += g1 * (e1 * cs[1]);
+                            s1[2] += g2; s2[2] += g2 * (e2 * cs[2]);
+                            s1[3] += g3; s2[3] += g3 * (e3 * cs[3]);
+                            // gout[p][ci] += a * g: each (pixel, channel) is touched by exactly one thread of one CTA per launch
+                            tcconv::red_add_v4(A.gout + off[it], ca[0] * g0, ca[1] * g1, ca[2] * g2, ca[3] * g3);
+                        }
                     }
                 }
-            } else {
+                asm volatile("bar.sync 1, 256;" ::: "memory");           // transposed tile free for the next unit
+            }
+            // ------------------------------------------------------------ BN-backward sums of this chunk
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    if (ok_cur & (1u << it)) {
-                        const int p = warp * 16 + it * 2 + psub;
-                        const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
-                        const float4 xq = *reinterpret_cast<const float4*>(xring + ((size_t)(((n & 1) * 8 + it) * 256 + tid)) * 16);
-                        const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
-                        const float g0 = fmaf(ca[0], e0, cb[0]) > 0.f ? d.x : 0.f;
-                        const float g1 = fmaf(ca[1], e1, cb[1]) > 0.f ? d.y : 0.f;
-                        const float g2 = fmaf(ca[2], e2, cb[2]) > 0.f ? d.z : 0.f;
-                        const float g3 = fmaf(ca[3], e3, cb[3]) > 0.f ? d.w : 0.f;
-                        s1[0] += g0; s2[0] += g0 * (e0 * cs[0]);
-                        s1[1] += g1; s2[1] += g1 * (e1 * cs[1]);
-                        s1[2] += g2; s2[2] += g2 * (e2 * cs[2]);
-                        s1[3] += g3; s2[3] += g3 * (e3 * cs[3]);
-                        // gout[p][ci] += a * g as ONE 16-byte L2 reduction: each (pixel, channel) is touched by exactly one
-                        // thread of one CTA per launch, so the result does not depend on any ordering
-                        tcconv::red_add_v4(gout_img + off_cur[it], ca[0] * g0, ca[1] * g1, ca[2] * g2, ca[3] * g3);
-                    }
+            for (int e = 0; e < 4; ++e) {
+                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+                if (psub == 0) {
+                    red[(warp * NC + quad * 4 + e) * 2] = s1[e];
+                    red[(warp * NC + quad * 4 + e) * 2 + 1] = s2[e];
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");           // transposed tile free for the next unit
-            if (mb == MBLK - 1) {
-                // -------------------------------------------------------- BN-backward sums of this chunk
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < 2 * NC) {
+                const int j = tid >> 1, which = tid & 1;
+                if (ci0 + j < A.Cin && !A.plain) {
+                    double sum = 0.0;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
-                    s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
-                    if (psub == 0) {
-                        red[(warp * NC + quad * 4 + e) * 2] = s1[e];
-                        red[(warp * NC + quad * 4 + e) * 2 + 1] = s2[e];
-                    }
+                    for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * NC + j) * 2 + which];
+                    atomicAdd(A.red + ((size_t)g * A.red_C + ci0 + j) * 2 + which, sum);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (tid < 2 * NC) {
-                    const int j = tid >> 1, which = tid & 1;
-                    if (ci0 + j < A.Cin && !A.plain) {
-                        double sum = 0.0;
-#pragma unroll
-                        for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * NC + j) * 2 + which];
-                        atomicAdd(A.red + ((size_t)g * A.red_C + ci0 + j) * 2 + which, sum);
-                    }
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");           // red / ctab / weights reusable
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // red / ctab / weights reusable
         }
-        tc::cp_async_wait<0>();
     } else {
         // -------------------------------------------------------------------- MMA issuer: warp 8, convergent; one elected lane issues
         const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
@@ -1108,10 +1082,16 @@ up_sum_kernel(const float* __restrict__ hi, int hiC, float* __restrict__ low, in
 // group of 8 channels, 8 consecutive pixels x 16 bytes form one 128-byte core matrix -- which is exactly the
 // plane layout of the forward kernel (pixels 16 B apart), with bf16 packing 8 channels into the 16 bytes.
 //   A = act planes          M = 64 input channels of this CTA's channel block (rows 64..127 of the MMA read
-//                           whatever follows in shared memory and are ignored), K = 16 pixels
-//   B = shifted G planes    N = 3 (kx) x 16 (co): the horizontal taps are folded into N by writing each staged
-//                           gradient pixel into three planes shifted by kx-1 rows; the vertical tap is an A
-//                           start-address offset of +-34 rows.  Three accumulators D_ky[ci][kx*16+co] (144 TMEM
+//                           whatever follows in shared memory and are ignored), K = 16 pixels.  ONLY THE 8x32 TILE
+//                           INTERIOR is staged (the two pad columns of the pitch-34 rows stay zero): the halo a 3x3
+//                           tap needs sits on the small operand,
+//   B = shifted G planes    N = 3 (kx) x 16 (co): the (8+2) x 34 halo tile of the OUTPUT GRADIENT (real values of the
+//                           neighbouring tiles, zero outside the image; 12 channels instead of Cin) with the horizontal
+//                           taps folded into N by writing each staged gradient pixel into three planes shifted by kx
+//                           rows; the vertical tap is a B start-address offset of -+34 rows:
+//                               dW[ky][kx] = sum_{p in tile} act[p] * G[p - (ky-1, kx-1)]
+//                           (round 1 shifted the activations instead and read 10/8 of them plus 64-channel padding:
+//                           1.59x the algorithmic DRAM bytes, ncu).  Three accumulators D_ky[ci][kx*16+co] (144 TMEM
 //                           columns) stay resident while the CTA walks over its share of 8x32-pixel tiles; one
 //                           fp32 atomicAdd per weight at the end.
 // =====================================================================================================
@@ -1185,13 +1165,10 @@ dense_wgrad_bf16_kernel(const Args A) {
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 16) {
-        // The gradient planes are cleared ONCE: the rows the interior pixels write are the same for every tile (an interior
-        // pixel outside the image stores zeros), every other row -- halo columns / rows of the kx-shifted planes -- stays zero.
-        // (A per-tile clear of 33 KB plus the barrier in front of the interior stores was ~30 % of the staging time.)
-        for (int i = tid; i < 2 * (G_STAGE / 16); i += NPROD) {
-            const int st = i / (G_STAGE / 16), j = i - st * (G_STAGE / 16);
-            reinterpret_cast<uint4*>(smem + st * STAGE + A_STAGE)[j] = make_uint4(0u, 0u, 0u, 0u);
-        }
+        // Both stages are cleared ONCE: every tile writes the same rows (activation planes: the 8x32 interior, a pixel
+        // outside the image stores zeros; gradient planes: rows kx .. 339 + kx of plane kx), every other row -- the pad columns
+        // of the activation rows, the margins of the kx-shifted planes -- stays zero.
+        for (int i = tid; i < 2 * (STAGE / 16); i += NPROD) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("bar.sync 1, 512;" ::: "memory");
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1;
@@ -1205,6 +1182,27 @@ dense_wgrad_bf16_kernel(const Args A) {
             unsigned char* a_s = smem + s * STAGE;
             unsigned char* g_s = a_s + A_STAGE;
             const size_t img = (size_t)b * A.H * A.W;
+            // ---- output gradient, round 0: the loads are issued FIRST and consumed after the activation planes are written
+            //      (r2 ncu: three serialised load round trips per tile were 37 % of all warp-stall samples of this kernel)
+            float4 gq0[2], xq0[2];
+            bool g0_ok = false;
+            int g0_q = 0, g0_hf = 0;
+            size_t g0_oo = 0;
+            if (!A.one) {
+                g0_hf = tid >= A_ROWS ? 1 : 0; g0_q = tid - g0_hf * A_ROWS;
+                const int r = g0_q / PITCH, cc = g0_q - r * PITCH;
+                const int y = y0 + r - 1, x = x0 + cc - 1;
+                g0_ok = (y >= 0) && (y < A.H) && (x >= 0) && (x < A.W);
+                g0_oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + g0_hf * 8;
+#pragma unroll
+                for (int h4 = 0; h4 < 2; ++h4) {
+                    gq0[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq0[h4] = gq0[h4];
+                    if (g0_ok && g0_hf * 8 + h4 * 4 < A.Cout) {
+                        gq0[h4] = __ldg(reinterpret_cast<const float4*>(A.g + g0_oo + h4 * 4));
+                        xq0[h4] = __ldg(reinterpret_cast<const float4*>(A.x + g0_oo + h4 * 4));
+                    }
+                }
+            }
             // ---- activations: (pixel, 8-channel group) items, BN+ReLU, bf16
             {
                 const int grp = tid & 7;
@@ -1218,52 +1216,47 @@ dense_wgrad_bf16_kernel(const Args A) {
                 const int sW = A.W >> sh;
                 const float* xa_b = A.xa + (size_t)b * (A.H >> sh) * sW * A.xa_C + A.in_off + ch;
                 const bool v8_ok = (((A.in_off + ci0) | A.xa_C) & 7) == 0 && (reinterpret_cast<uintptr_t>(A.xa) & 31) == 0;
+                float4 q0[4], q1[4];                                 // 4 interior pixels per thread, all loads first
+                unsigned okmask = 0u;
 #pragma unroll
-                for (int part = 0; part < 2; ++part) {               // 6 pixels per thread: two batches of 3, loads first
-                    float4 q0[3], q1[3];                             // (one batch of 6 / deeper prefetch measured slower)
-                    unsigned okmask = 0u;
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int px = (tid >> 3) + 64 * (part * 3 + j);
-                        const int r = px / PITCH, cc = px - r * PITCH;
-                        const int y = y0 + r - 1, x = x0 + cc - 1;
-                        q0[j] = make_float4(0.f, 0.f, 0.f, 0.f); q1[j] = q0[j];
-                        if (ch_ok && px < A_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) {
-                            const float* p = xa_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.xa_C;
-                            if (hi_ok && v8_ok) {
-                                // one 256-bit load = one whole 32-byte sector per lane, not cached in the (small) L1
-                                asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                                             : "=f"(q0[j].x), "=f"(q0[j].y), "=f"(q0[j].z), "=f"(q0[j].w),
-                                               "=f"(q1[j].x), "=f"(q1[j].y), "=f"(q1[j].z), "=f"(q1[j].w) : "l"(p));
-                            } else {
-                                q0[j] = __ldg(reinterpret_cast<const float4*>(p));
-                                if (hi_ok) q1[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
-                            }
-                            okmask |= 1u << j;
+                for (int j = 0; j < 4; ++j) {
+                    const int ip = (tid >> 3) + 64 * j;              // interior pixel 0 .. 255
+                    const int y = y0 + (ip >> 5), x = x0 + (ip & 31);
+                    q0[j] = make_float4(0.f, 0.f, 0.f, 0.f); q1[j] = q0[j];
+                    if (ch_ok && y < A.H && x < A.W) {
+                        const float* p = xa_b + ((size_t)(y >> sh) * sW + (x >> sh)) * A.xa_C;
+                        if (hi_ok && v8_ok) {
+                            // one 256-bit load = one whole 32-byte sector per lane, not cached in the (small) L1
+                            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=f"(q0[j].x), "=f"(q0[j].y), "=f"(q0[j].z), "=f"(q0[j].w),
+                                           "=f"(q1[j].x), "=f"(q1[j].y), "=f"(q1[j].z), "=f"(q1[j].w) : "l"(p));
+                        } else {
+                            q0[j] = __ldg(reinterpret_cast<const float4*>(p));
+                            if (hi_ok) q1[j] = __ldg(reinterpret_cast<const float4*>(p + 4));
                         }
+                        okmask |= 1u << j;
                     }
+                }
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const int px = (tid >> 3) + 64 * (part * 3 + j);
-                        if (px < A_ROWS) {
-                            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                            if (okmask & (1u << j)) {
-                                const float4 a0 = q0[j], a1 = q1[j];
-                                float v0 = a0.x, v1 = a0.y, v2 = a0.z, v3 = a0.w, v4 = a1.x, v5 = a1.y, v6 = a1.z, v7 = a1.w;
-                                if (!A.up) {
-                                    v0 = fmaxf(fmaf(k0.x, a0.x - k0.z, k0.y), 0.f); v1 = fmaxf(fmaf(k1.x, a0.y - k1.z, k1.y), 0.f);
-                                    v2 = fmaxf(fmaf(k2.x, a0.z - k2.z, k2.y), 0.f); v3 = fmaxf(fmaf(k3.x, a0.w - k3.z, k3.y), 0.f);
-                                    v4 = v5 = v6 = v7 = 0.f;
-                                    if (hi_ok) {
-                                        v4 = fmaxf(fmaf(k4.x, a1.x - k4.z, k4.y), 0.f); v5 = fmaxf(fmaf(k5.x, a1.y - k5.z, k5.y), 0.f);
-                                        v6 = fmaxf(fmaf(k6.x, a1.z - k6.z, k6.y), 0.f); v7 = fmaxf(fmaf(k7.x, a1.w - k7.z, k7.y), 0.f);
-                                    }
-                                }
-                                o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
+                for (int j = 0; j < 4; ++j) {
+                    const int ip = (tid >> 3) + 64 * j;
+                    const int px = (1 + (ip >> 5)) * PITCH + 1 + (ip & 31);      // row of the pitch-34 plane
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (okmask & (1u << j)) {
+                        const float4 a0 = q0[j], a1 = q1[j];
+                        float v0 = a0.x, v1 = a0.y, v2 = a0.z, v3 = a0.w, v4 = a1.x, v5 = a1.y, v6 = a1.z, v7 = a1.w;
+                        if (!A.up) {
+                            v0 = fmaxf(fmaf(k0.x, a0.x - k0.z, k0.y), 0.f); v1 = fmaxf(fmaf(k1.x, a0.y - k1.z, k1.y), 0.f);
+                            v2 = fmaxf(fmaf(k2.x, a0.z - k2.z, k2.y), 0.f); v3 = fmaxf(fmaf(k3.x, a0.w - k3.z, k3.y), 0.f);
+                            v4 = v5 = v6 = v7 = 0.f;
+                            if (hi_ok) {
+                                v4 = fmaxf(fmaf(k4.x, a1.x - k4.z, k4.y), 0.f); v5 = fmaxf(fmaf(k5.x, a1.y - k5.z, k5.y), 0.f);
+                                v6 = fmaxf(fmaf(k6.x, a1.z - k6.z, k6.y), 0.f); v7 = fmaxf(fmaf(k7.x, a1.w - k7.z, k7.y), 0.f);
                             }
-                            *reinterpret_cast<uint4*>(a_s + grp * PLANE_BYTES + (size_t)px * 16) = o;
                         }
+                        o = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), pack_bf16(v4, v5), pack_bf16(v6, v7));
                     }
+                    *reinterpret_cast<uint4*>(a_s + grp * PLANE_BYTES + (size_t)px * 16) = o;
                 }
             }
             // ---- output gradient: plane (kx, half) row (1 + q) holds G[q - (kx-1)][half*8 .. +8], zero outside the tile
@@ -1308,44 +1301,48 @@ dense_wgrad_bf16_kernel(const Args A) {
                     const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                     *reinterpret_cast<uint4*>(g_s + (sub * 2 + half) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? o : make_uint4(0u, 0u, 0u, 0u);
                 }
-            } else
-            {
-                const int r = 1 + (gpix >> 5), cc = 1 + (gpix & 31);
-                const int y = y0 + r - 1, x = x0 + cc - 1;
-                const bool ok = (y < A.H) && (x < A.W);
-                float4 gq[2], xq[2];
+            } else {
+                // (8 + 2) x 34 halo tile, two threads per pixel (one per 8-channel half): 680 items in two rounds
+#pragma unroll 1
+                for (int rnd = 0; rnd < 2; ++rnd) {
+                    const int i = tid + NPROD * rnd;
+                    if (i >= 2 * A_ROWS) break;
+                    int hf = g0_hf, q = g0_q;
+                    bool ok = g0_ok;
+                    float4 gq[2] = {gq0[0], gq0[1]}, xq[2] = {xq0[0], xq0[1]};
+                    if (rnd == 1) {
+                        hf = i >= A_ROWS ? 1 : 0; q = i - hf * A_ROWS;
+                        const int r = q / PITCH, cc = q - r * PITCH;
+                        const int y = y0 + r - 1, x = x0 + cc - 1;
+                        ok = (y >= 0) && (y < A.H) && (x >= 0) && (x < A.W);
+                        const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + hf * 8;
 #pragma unroll
-                for (int h4 = 0; h4 < 2; ++h4) { gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4]; }
-                const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + half * 8;
-                if (ok) {
-#pragma unroll
-                    for (int h4 = 0; h4 < 2; ++h4) {
-                        if (half * 8 + h4 * 4 < A.Cout) {
-                            gq[h4] = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
-                            xq[h4] = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            gq[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[h4] = gq[h4];
+                            if (ok && hf * 8 + h4 * 4 < A.Cout) {
+                                gq[h4] = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
+                                xq[h4] = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
+                            }
                         }
                     }
-                }
-                float v[8];
-                const float* abp = A.ab + ((size_t)g * A.C + A.out_off + half * 8) * 2;
+                    float v[8];
+                    const float* abp = A.ab + ((size_t)g * A.C + A.out_off + hf * 8) * 2;
 #pragma unroll
-                for (int h4 = 0; h4 < 2; ++h4) {
-                    if (ok && half * 8 + h4 * 4 < A.Cout) {
-                        const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
-                        const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
-                        v[h4 * 4 + 0] = gq[h4].x + fmaf(c0.y, xq[h4].x, c0.x); v[h4 * 4 + 1] = gq[h4].y + fmaf(c0.w, xq[h4].y, c0.z);
-                        v[h4 * 4 + 2] = gq[h4].z + fmaf(c1.y, xq[h4].z, c1.x); v[h4 * 4 + 3] = gq[h4].w + fmaf(c1.w, xq[h4].w, c1.z);
-                    } else {
-                        v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
+                    for (int h4 = 0; h4 < 2; ++h4) {
+                        if (ok && hf * 8 + h4 * 4 < A.Cout) {
+                            const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
+                            const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
+                            v[h4 * 4 + 0] = gq[h4].x + fmaf(c0.y, xq[h4].x, c0.x); v[h4 * 4 + 1] = gq[h4].y + fmaf(c0.w, xq[h4].y, c0.z);
+                            v[h4 * 4 + 2] = gq[h4].z + fmaf(c1.y, xq[h4].z, c1.x); v[h4 * 4 + 3] = gq[h4].w + fmaf(c1.w, xq[h4].w, c1.z);
+                        } else {
+                            v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
+                        }
                     }
-                }
-                {
                     const uint4 o = ok ? make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]))
                                        : make_uint4(0u, 0u, 0u, 0u);
-                    const int q = r * PITCH + cc;
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx)
-                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + half) * PLANE_BYTES + (size_t)(q + kx) * 16) = o;
+                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + hf) * PLANE_BYTES + (size_t)(q + kx) * 16) = o;
                 }
             }
             tc::fence_proxy_async();
@@ -1419,11 +1416,11 @@ dense_wgrad_bf16_kernel(const Args A) {
 #pragma unroll 1
             for (int k16 = 0; k16 < KPX / 16; ++k16) {
                 const int set = k16 % 3;
-                const uint64_t bd = b_d0 + (uint64_t)(PITCH + k16 * 16);
+                const uint64_t ad = a_d0 + (uint64_t)(PITCH + k16 * 16);
                 const uint32_t acc = (uint32_t)(it != 0 || k16 >= 3);
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
-                    tc::mma_f16_w(tmem + (set * 3 + ky) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16 + (ky - 1) * PITCH), bd, idesc, acc);
+                for (int ky = 0; ky < 3; ++ky)          // act[p] pairs with G[p - (ky-1) rows]: B rows slide, A stays
+                    tc::mma_f16_w(tmem + (set * 3 + ky) * NB, ad, b_d0 + (uint64_t)(PITCH + k16 * 16 - (ky - 1) * PITCH), idesc, acc);
             }
             }
             tc::tc_commit_w(bars + 2 + s);
