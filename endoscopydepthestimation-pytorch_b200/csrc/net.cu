@@ -365,6 +365,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
 static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
     const int yblocks = cdiv(cin, tcwgrad::MCH);
     t.n_tiles = t.B * cdiv(t.H, tcwgrad::TR) * cdiv(t.W, tcwgrad::TW);
+    t.dbg = tc_debug_mask();
     if (tc_disable_mask() & 16384) {
         int want = (2 * kNumSMs) / yblocks;
         if (want < 1) want = 1;
@@ -376,13 +377,14 @@ static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
         ENDO_CHECK_LAUNCH();
         return ENDO_OK;
     }
+    t.n_tiles = t.B * cdiv(t.H, tcwgrad2::TR) * cdiv(t.W, tcwgrad2::TW);
     int want = kNumSMs / yblocks;                            // one wave of persistent CTAs
     if (want < 1) want = 1;
     if (want > t.n_tiles) want = t.n_tiles;
     t.tiles_per_cta = cdiv(t.n_tiles, want);
     const int sh = t.up ? 1 : 0;
     CUtensorMap xmap;
-    if (!tma::make_nhwc_map(&xmap, t.xa, t.B, t.H >> sh, t.W >> sh, t.xa_C, tcwgrad::MCH, tcwgrad::TW >> sh, tcwgrad::TR >> sh))
+    if (!tma::make_nhwc_map(&xmap, t.xa, t.B, t.H >> sh, t.W >> sh, t.xa_C, tcwgrad::MCH, tcwgrad2::TW >> sh, tcwgrad2::TR >> sh))
         return ENDO_ERR_CUDA;
     ENDO_SET_MAX_SMEM(tcwgrad2::dense_wgrad_tma_kernel, tcwgrad2::SMEM_BYTES);
     dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);

@@ -1124,6 +1124,7 @@ struct Args {
     // 1x1 mode (TransitionDown, models.py:56-67): no taps, N = 48 output channels [out_off, out_off + 48) per launch; the
     // output gradient is the max-pool-routed gradient of the NEXT level's buffer (gc, xc, abc: stride cC, first channel c_off)
     int one; const unsigned char* argmax; const float* gc; const float* xc; const float* abc; int cC, c_off, cH, cW;
+    int dbg;                                             // ENDO_TC_DEBUG bit 8: clock64 trace of CTA (0, 0) (tools/trace_wgrad.py)
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -9,14 +9,16 @@
 // tracked by six scoreboard counters per warp, and refilling a register buffer waits for the counter it shares with the batch
 // still in flight (measured on the data-gradient kernel: +39 %).  Here the UNTRANSFORMED activation tile travels by TMA:
 //
-//   warp 17, one lane : cp.async.bulk.tensor box (64 channels, 32 x 8 pixels) of the NHWC level buffer -> raw ring (2 x 64 KB),
+//   warp 17, one lane : cp.async.bulk.tensor box (64 channels, 16 x 8 pixels) of the NHWC level buffer -> raw ring (2 x 32 KB),
 //                       up to two tiles ahead of the consumers, out-of-image pixels zero-filled by the hardware;
-//   warps 0-15        : raw fp32 (shared) -> BatchNorm + ReLU -> bf16 -> operand planes (shared), then the gradient halo tile
-//                       (registers, prefetched ONE tile ahead: a single batch in flight) -> three kx-shifted planes;
-//   warp 16           : 51 MMAs per tile (17 K-steps x 3 vertical taps), accumulators resident in TMEM across all tiles.
+//   warps 0-15        : raw fp32 (shared) -> BatchNorm + ReLU -> bf16 -> operand planes (shared); the (8+2) x 18 gradient halo
+//                       tile (g and x, 12 channels) arrives by cp.async one tile ahead in a ring of thread-private slots and
+//                       is corrected / packed into three kx-shifted planes;
+//   warp 16           : 27 MMAs per tile (9 K-steps x 3 vertical taps), accumulators resident in TMEM across all tiles.
 //
-// The operand stage is single (the raw ring took its place in shared memory): transform and MMAs of consecutive tiles
-// alternate, ~4 k cycles per tile together, against ~10 k for the load-latency-bound round-1 loop.
+// Everything is double-buffered (raw ring, operand stages, gradient ring): TMA, transform and MMAs of consecutive tiles
+// overlap.  History (clock64 traces, r2): with 8x32 tiles, a single operand stage and the gradient rows prefetched in
+// REGISTERS across the loop edge, 55 % of the tile period was the loop top waiting for those registers.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -26,32 +28,42 @@
 namespace endo {
 namespace tcwgrad2 {
 
-using tcwgrad::Args; using tcwgrad::PITCH; using tcwgrad::TR; using tcwgrad::TW; using tcwgrad::KPX; using tcwgrad::A_ROWS;
-using tcwgrad::PLANE_BYTES; using tcwgrad::MCH; using tcwgrad::NB; using tcwgrad::pack_bf16;
+// trace slots: [0] = tiles, [1] = start; producers (thread 0) 16 + 8 it + {0 loop top, 1 raw landed, 2 planes free, 3 activations
+// written, 4 gradient written / arrived}; MMA warp 16 + 8 it + {5 operands ready, 6 issued}; TMA thread 16 + 8 it + 7 = issued
+#define WG_TRACE(slot) do { if ((A.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 2048) g_tc_trace[(slot)] = clock64(); } while (0)
 
-constexpr int RAW_BYTES = TR * TW * MCH * 4;             // 65,536: [8][32][64] fp32
+using tcwgrad::Args; using tcwgrad::MCH; using tcwgrad::NB; using tcwgrad::pack_bf16;
+
+constexpr int TR = 8, TW = 16, PITCH = TW + 2;           // 8 x 16 interior pixels per tile, rows of the operand planes 18 pixels apart
+constexpr int KPX = TR * PITCH;                          // 144 pixels = 9 K-steps of 16
+constexpr int H_ROWS = (TR + 2) * PITCH;                 // 180 pixels of the gradient halo tile
+constexpr int PLANE_BYTES = 185 * 16;                    // 2,960 (= 16 mod 128: the 8 channel groups of a pixel spread over all banks)
+constexpr int RAW_BYTES = TR * TW * MCH * 4;             // 32,768: [8][16][64] fp32
 constexpr int NRAW = 2;
-constexpr int A_BYTES = (MCH / 8) * PLANE_BYTES;         // 44,160
-constexpr int G_BYTES = 6 * PLANE_BYTES;                 // 33,120
-constexpr int OP_OFF = NRAW * RAW_BYTES;                 // 131,072
-constexpr int PAD_BYTES = 2 * PLANE_BYTES;               // the M = 128 read of the A operand runs 16 planes far
-constexpr int KTAB_OFF = OP_OFF + A_BYTES + G_BYTES + PAD_BYTES;
+constexpr int A_BYTES = (MCH / 8) * PLANE_BYTES;         // 23,680
+constexpr int G_BYTES = 6 * PLANE_BYTES;                 // 17,760
+constexpr int STAGE = A_BYTES + G_BYTES;                 // 41,440
+constexpr int OP_OFF = NRAW * RAW_BYTES;                 // 65,536
+constexpr int PAD_BYTES = 2 * PLANE_BYTES;               // the M = 128 read of the A operand runs 16 planes far (stage 1: past its end)
+constexpr int GITEMS = 2 * H_ROWS;                       // (halo pixel, 8-channel half) items of the gradient tile
+constexpr int GRING_OFF = OP_OFF + 2 * STAGE + PAD_BYTES;
+constexpr int GRING_BYTES = 4 * GITEMS * 16;             // per tile: [g lo, g hi, x lo, x hi][item][16 B] = 23,040
+constexpr int KTAB_OFF = GRING_OFF + 2 * GRING_BYTES;
 constexpr int KTAB_BYTES = 2 * 8 * 144;
 constexpr int BAR_OFF = KTAB_OFF + KTAB_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + 256;
+constexpr int SMEM_BYTES = BAR_OFF + 256;                // 202,976
 constexpr int NPROD = 512;
 constexpr int NTHREADS = NPROD + 64;                     // + MMA warp + TMA warp
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* a_s = smem + OP_OFF;
-    unsigned char* g_s = a_s + A_BYTES;
+    unsigned char* gring = smem + GRING_OFF;
     float* ktab = reinterpret_cast<float*>(smem + KTAB_OFF);                    // [G <= 2][8 groups][8 x float4 + pad]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);               // raw_full[2], raw_empty[2], op_full, op_empty, accum
-    uint64_t* raw_full = bars; uint64_t* raw_empty = bars + 2; uint64_t* op_full = bars + 4; uint64_t* op_empty = bars + 5;
-    uint64_t* accum = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint64_t* raw_full = bars; uint64_t* raw_empty = bars + 2; uint64_t* op_full = bars + 4; uint64_t* op_empty = bars + 6;
+    uint64_t* accum = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ci0 = blockIdx.y * MCH;
@@ -60,6 +72,7 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
     const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
     const int ntiles = t_end - t_begin;
     const int sh = A.up ? 1 : 0;
+    if (tid == 0) { WG_TRACE(1); if ((A.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0) g_tc_trace[0] = ntiles; }
 
     if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
     if (tid < 2 * MCH) {                                     // coefficient table (zeros for TransitionUp: no BatchNorm in front)
@@ -69,9 +82,11 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
         *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ktab) + (gi * 8 + (cl >> 3)) * 144 + (cl & 7) * 16) = e;
     }
     if (tid == 0) {
-        tc::mbar_init(raw_full + 0, 1); tc::mbar_init(raw_full + 1, 1);
-        tc::mbar_init(raw_empty + 0, NPROD); tc::mbar_init(raw_empty + 1, NPROD);
-        tc::mbar_init(op_full, NPROD); tc::mbar_init(op_empty, 1); tc::mbar_init(accum, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, NPROD);
+            tc::mbar_init(op_full + i, NPROD); tc::mbar_init(op_empty + i, 1);
+        }
+        tc::mbar_init(accum, 1);
         tc::fence_mbar_init();
     }
     tc::tc_fence_before();
@@ -87,72 +102,36 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
     };
 
     if (warp < 16) {
-        // The operand stage is cleared ONCE: every tile writes the same rows (activation planes: the 8x32 interior; gradient
-        // planes: rows kx .. 339 + kx of plane kx), every other row -- pad columns, margins of the shifted planes -- stays zero.
-        for (int i = tid; i < (A_BYTES + G_BYTES + PAD_BYTES) / 16; i += NPROD) reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0u, 0u, 0u, 0u);
+        // Both operand stages are cleared ONCE: every tile writes the same rows (activation planes: the 8x16 interior; gradient
+        // planes: rows kx .. 179 + kx of plane kx), every other row -- pad columns, margins of the shifted planes -- stays zero.
+        for (int i = tid; i < (2 * STAGE + PAD_BYTES) / 16; i += NPROD) reinterpret_cast<uint4*>(smem + OP_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
         asm volatile("bar.sync 1, 512;" ::: "memory");
 
-        // ---- gradient halo tile, dense / upsampled modes: (8 + 2) x 34 pixels x two 8-channel halves = 680 items; a thread owns
-        //      item tid and, if tid < 168, item 512 + tid.  The loads of tile it + 1 are issued after tile it has been written.
-        const int q_a = tid >= A_ROWS ? tid - A_ROWS : tid, hf_a = tid >= A_ROWS ? 1 : 0;
-        const int q_b = (NPROD + tid) - A_ROWS, hf_b = 1;                       // second item (valid when tid < 2 * A_ROWS - NPROD)
-        const bool has_b = tid < 2 * A_ROWS - NPROD;
-        float4 ga[2], xa4[2], gb[2], xb4[2];
-        bool ok_a = false, ok_b = false;
-        auto g_issue = [&](int t) {
-            int b, y0, x0;
-            tile_origin(t, b, y0, x0);
-            const size_t img = (size_t)b * A.H * A.W;
-            {
-                const int r = q_a / PITCH, cc = q_a - r * PITCH;
+        // ---- gradient halo tile, dense / upsampled modes: (8 + 2) x 18 pixels x two 8-channel halves = 360 items, one per thread
+        //      (tid < 360).  g and x of the item travel by cp.async into a two-deep ring of thread-private slots, requested one
+        //      tile AHEAD (commit groups, not scoreboards, track them: registers prefetched across the loop edge stalled the loop
+        //      top for 55 % of the tile period, clock64 trace r2).
+        const bool g_thread = tid < GITEMS && !A.one;
+        const int gq = tid % H_ROWS, ghf = tid / H_ROWS;
+        auto g_issue = [&](int it) {                                            // tile t_begin + it -> ring[it & 1]
+            if (g_thread && it < ntiles) {
+                int b, y0, x0;
+                tile_origin(t_begin + it, b, y0, x0);
+                const int r = gq / PITCH, cc = gq - r * PITCH;
                 const int y = y0 + r - 1, x = x0 + cc - 1;
-                ok_a = (y >= 0) && (y < A.H) && (x >= 0) && (x < A.W);
-                const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + hf_a * 8;
+                const bool ok = (y >= 0) && (y < A.H) && (x >= 0) && (x < A.W);
+                const size_t oo = ok ? (((size_t)b * A.H + y) * A.W + x) * A.C + A.out_off + ghf * 8 : 0;
+                unsigned char* slot = gring + (it & 1) * GRING_BYTES + (size_t)tid * 16;
 #pragma unroll
                 for (int h4 = 0; h4 < 2; ++h4) {
-                    ga[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xa4[h4] = ga[h4];
-                    if (ok_a && hf_a * 8 + h4 * 4 < A.Cout) {
-                        ga[h4] = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
-                        xa4[h4] = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
-                    }
+                    const uint32_t nb = (ok && ghf * 8 + h4 * 4 < A.Cout) ? 16u : 0u;      // 0 bytes = zero fill
+                    tc::cp_async16(slot + (size_t)h4 * GITEMS * 16, A.g + oo + (nb ? h4 * 4 : 0), nb);
+                    tc::cp_async16(slot + (size_t)(2 + h4) * GITEMS * 16, A.x + oo + (nb ? h4 * 4 : 0), nb);
                 }
             }
-            if (has_b) {
-                const int r = q_b / PITCH, cc = q_b - r * PITCH;
-                const int y = y0 + r - 1, x = x0 + cc - 1;
-                ok_b = (y >= 0) && (y < A.H) && (x >= 0) && (x < A.W);
-                const size_t oo = (img + (size_t)y * A.W + x) * A.C + A.out_off + hf_b * 8;
-#pragma unroll
-                for (int h4 = 0; h4 < 2; ++h4) {
-                    gb[h4] = make_float4(0.f, 0.f, 0.f, 0.f); xb4[h4] = gb[h4];
-                    if (ok_b && hf_b * 8 + h4 * 4 < A.Cout) {
-                        gb[h4] = __ldg(reinterpret_cast<const float4*>(A.g + oo + h4 * 4));
-                        xb4[h4] = __ldg(reinterpret_cast<const float4*>(A.x + oo + h4 * 4));
-                    }
-                }
-            }
+            tc::cp_async_commit();                                              // one group per tile, empty or not
         };
-        auto g_store = [&](int g, int q, int hf, bool ok, const float4 (&gq)[2], const float4 (&xq)[2]) {
-            float v[8];
-            const float* abp = A.ab + ((size_t)g * A.C + A.out_off + hf * 8) * 2;
-#pragma unroll
-            for (int h4 = 0; h4 < 2; ++h4) {
-                if (ok && hf * 8 + h4 * 4 < A.Cout) {
-                    const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
-                    const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
-                    v[h4 * 4 + 0] = gq[h4].x + fmaf(c0.y, xq[h4].x, c0.x); v[h4 * 4 + 1] = gq[h4].y + fmaf(c0.w, xq[h4].y, c0.z);
-                    v[h4 * 4 + 2] = gq[h4].z + fmaf(c1.y, xq[h4].z, c1.x); v[h4 * 4 + 3] = gq[h4].w + fmaf(c1.w, xq[h4].w, c1.z);
-                } else {
-                    v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
-                }
-            }
-            const uint4 o = ok ? make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]))
-                               : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-                *reinterpret_cast<uint4*>(g_s + (kx * 2 + hf) * PLANE_BYTES + (size_t)(q + kx) * 16) = o;
-        };
-        if (!A.one && ntiles > 0) g_issue(t_begin);
+        g_issue(0);
 
         const int grp = tid & 7;
         const int ch = ci0 + grp * 8;
@@ -160,21 +139,27 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
         const bool hi_ok = ch + 4 < A.Cin;
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1;
+            unsigned char* a_s = smem + OP_OFF + s * STAGE;
+            unsigned char* g_s = a_s + A_BYTES;
             int b, y0, x0;
             tile_origin(t_begin + it, b, y0, x0);
             const int g = b / (A.B / A.G);
+            if (tid == 0) WG_TRACE(16 + 8 * it + 0);
+            g_issue(it + 1);                                                    // next tile's gradient rows: in flight from here
             tc::mbar_wait(raw_full + s, (it >> 1) & 1);                         // the TMA box of this tile has landed
-            if (it >= 1) tc::mbar_wait(op_empty, (it - 1) & 1);                 // the MMAs of the previous tile are done with the planes
+            if (tid == 0) WG_TRACE(16 + 8 * it + 1);
+            if (it >= 2) tc::mbar_wait(op_empty + s, ((it >> 1) - 1) & 1);      // the MMAs of tile it - 2 are done with this stage
+            if (tid == 0) WG_TRACE(16 + 8 * it + 2);
             // ---- activations: raw fp32 (shared) -> BN + ReLU -> bf16 planes.  Item = (interior pixel, 8-channel group).
             {
                 const float4* kt = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ktab) + (g * 8 + grp) * 144);
                 const float4 k0 = kt[0], k1 = kt[1], k2 = kt[2], k3 = kt[3], k4 = kt[4], k5 = kt[5], k6 = kt[6], k7 = kt[7];
                 const unsigned char* raw = smem + s * RAW_BYTES + grp * 32;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ip = (tid >> 3) + 64 * j;              // interior pixel 0 .. 255
-                    const int ry = ip >> 5, rx = ip & 31;
-                    const int px = (1 + ry) * PITCH + 1 + rx;        // row of the pitch-34 plane
+                for (int j = 0; j < 2; ++j) {
+                    const int ip = (tid >> 3) + 64 * j;              // interior pixel 0 .. 127
+                    const int ry = ip >> 4, rx = ip & 15;
+                    const int px = (1 + ry) * PITCH + 1 + rx;        // row of the pitch-18 plane
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);
                     if (ch_ok && y0 + ry < A.H && x0 + rx < A.W) {   // (TMA zero-fills outside the image, but relu(bn(0)) != 0)
                         const int sp = sh ? ((ry >> 1) * (TW >> 1) + (rx >> 1)) : ip;
@@ -193,61 +178,91 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
                     *reinterpret_cast<uint4*>(a_s + grp * PLANE_BYTES + (size_t)px * 16) = o;
                 }
             }
+            if (tid == 0) WG_TRACE(16 + 8 * it + 3);
             tc::mbar_arrive(raw_empty + s);                                     // this thread has read its part of the raw tile
             // ---- output gradient
             if (A.one) {
                 // 1x1 mode (TransitionDown): interior only, 48 channels in three rounds of 16: the max-pool-routed gradient of the
-                // NEXT level (argmax word + g + x); plane (sub, half) row q + 1
-                const int gpix = tid & 255, half = tid >> 8;
-                const int r = 1 + (gpix >> 5), cc = 1 + (gpix & 31);
-                const int y = y0 + r - 1, x = x0 + cc - 1;
-                const bool ok = (y < A.H) && (x < A.W);
-                const unsigned pos = (unsigned)(((y & 1) << 1) | (x & 1));
-                const size_t pp = ok ? ((size_t)(b * A.cH + (y >> 1)) * A.cW + (x >> 1)) : 0;
-                const int q = r * PITCH + cc;
-                unsigned am[3][2];
-                float4 gq[3][2], xq[3][2];
+                // NEXT level (argmax word + g + x); plane (sub, half) row q + 1.  128 pixels x 2 halves = threads 0 .. 255.
+                if (tid < 256) {
+                    const int gpix = tid & 127, half = tid >> 7;
+                    const int r = 1 + (gpix >> 4), cc = 1 + (gpix & 15);
+                    const int y = y0 + r - 1, x = x0 + cc - 1;
+                    const bool ok = (y < A.H) && (x < A.W);
+                    const unsigned pos = (unsigned)(((y & 1) << 1) | (x & 1));
+                    const size_t pp = ok ? ((size_t)(b * A.cH + (y >> 1)) * A.cW + (x >> 1)) : 0;
+                    const int q = r * PITCH + cc;
+                    unsigned am[3][2];
+                    float4 gv[3][2], xv[3][2];
 #pragma unroll
-                for (int sub = 0; sub < 3; ++sub) {                              // all loads of the three rounds first
-                    const int cbase = A.out_off + sub * 16 + half * 8;
+                    for (int sub = 0; sub < 3; ++sub) {                              // all loads of the three rounds first
+                        const int cbase = A.out_off + sub * 16 + half * 8;
 #pragma unroll
-                    for (int h4 = 0; h4 < 2; ++h4) {
-                        am[sub][h4] = 0xffffffffu; gq[sub][h4] = make_float4(0.f, 0.f, 0.f, 0.f); xq[sub][h4] = gq[sub][h4];
-                        if (ok && cbase + h4 * 4 < A.Cout) {
-                            am[sub][h4] = __ldg(reinterpret_cast<const unsigned*>(A.argmax + pp * A.Cout + cbase + h4 * 4));
-                            gq[sub][h4] = __ldg(reinterpret_cast<const float4*>(A.gc + pp * A.cC + A.c_off + cbase + h4 * 4));
-                            xq[sub][h4] = __ldg(reinterpret_cast<const float4*>(A.xc + pp * A.cC + A.c_off + cbase + h4 * 4));
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            am[sub][h4] = 0xffffffffu; gv[sub][h4] = make_float4(0.f, 0.f, 0.f, 0.f); xv[sub][h4] = gv[sub][h4];
+                            if (ok && cbase + h4 * 4 < A.Cout) {
+                                am[sub][h4] = __ldg(reinterpret_cast<const unsigned*>(A.argmax + pp * A.Cout + cbase + h4 * 4));
+                                gv[sub][h4] = __ldg(reinterpret_cast<const float4*>(A.gc + pp * A.cC + A.c_off + cbase + h4 * 4));
+                                xv[sub][h4] = __ldg(reinterpret_cast<const float4*>(A.xc + pp * A.cC + A.c_off + cbase + h4 * 4));
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int sub = 0; sub < 3; ++sub) {
-                    const int cbase = A.out_off + sub * 16 + half * 8;
-                    float v[8];
+                    for (int sub = 0; sub < 3; ++sub) {
+                        const int cbase = A.out_off + sub * 16 + half * 8;
+                        float v[8];
 #pragma unroll
-                    for (int h4 = 0; h4 < 2; ++h4) {
-                        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-                        if (cbase + h4 * 4 < A.Cout) {
-                            const float* abp = A.abc + ((size_t)g * A.cC + A.c_off + cbase + h4 * 4) * 2;
-                            c0 = __ldg(reinterpret_cast<const float4*>(abp)); c1 = __ldg(reinterpret_cast<const float4*>(abp + 4));
+                        for (int h4 = 0; h4 < 2; ++h4) {
+                            float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+                            if (cbase + h4 * 4 < A.Cout) {
+                                const float* abp = A.abc + ((size_t)g * A.cC + A.c_off + cbase + h4 * 4) * 2;
+                                c0 = __ldg(reinterpret_cast<const float4*>(abp)); c1 = __ldg(reinterpret_cast<const float4*>(abp + 4));
+                            }
+                            const unsigned a_ = am[sub][h4];
+                            v[h4 * 4 + 0] = ((a_ & 0xffu) == pos) ? gv[sub][h4].x + fmaf(c0.y, xv[sub][h4].x, c0.x) : 0.f;
+                            v[h4 * 4 + 1] = (((a_ >> 8) & 0xffu) == pos) ? gv[sub][h4].y + fmaf(c0.w, xv[sub][h4].y, c0.z) : 0.f;
+                            v[h4 * 4 + 2] = (((a_ >> 16) & 0xffu) == pos) ? gv[sub][h4].z + fmaf(c1.y, xv[sub][h4].z, c1.x) : 0.f;
+                            v[h4 * 4 + 3] = ((a_ >> 24) == pos) ? gv[sub][h4].w + fmaf(c1.w, xv[sub][h4].w, c1.z) : 0.f;
                         }
-                        const unsigned a_ = am[sub][h4];
-                        v[h4 * 4 + 0] = ((a_ & 0xffu) == pos) ? gq[sub][h4].x + fmaf(c0.y, xq[sub][h4].x, c0.x) : 0.f;
-                        v[h4 * 4 + 1] = (((a_ >> 8) & 0xffu) == pos) ? gq[sub][h4].y + fmaf(c0.w, xq[sub][h4].y, c0.z) : 0.f;
-                        v[h4 * 4 + 2] = (((a_ >> 16) & 0xffu) == pos) ? gq[sub][h4].z + fmaf(c1.y, xq[sub][h4].z, c1.x) : 0.f;
-                        v[h4 * 4 + 3] = ((a_ >> 24) == pos) ? gq[sub][h4].w + fmaf(c1.w, xq[sub][h4].w, c1.z) : 0.f;
+                        const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                        *reinterpret_cast<uint4*>(g_s + (sub * 2 + half) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? o : make_uint4(0u, 0u, 0u, 0u);
                     }
-                    const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                    *reinterpret_cast<uint4*>(g_s + (sub * 2 + half) * PLANE_BYTES + (size_t)(q + 1) * 16) = ok ? o : make_uint4(0u, 0u, 0u, 0u);
                 }
             } else {
-                g_store(g, q_a, hf_a, ok_a, ga, xa4);
-                if (has_b) g_store(g, q_b, hf_b, ok_b, gb, xb4);
+                tc::cp_async_wait<1>();                                         // this thread's copies of tile `it` have landed
+                if (g_thread) {
+                    const unsigned char* slot = gring + s * GRING_BYTES + (size_t)tid * 16;
+                    float v[8];
+                    const float* abp = A.ab + ((size_t)g * A.C + A.out_off + ghf * 8) * 2;
+#pragma unroll
+                    for (int h4 = 0; h4 < 2; ++h4) {
+                        if (ghf * 8 + h4 * 4 < A.Cout) {
+                            const float4 gv = *reinterpret_cast<const float4*>(slot + (size_t)h4 * GITEMS * 16);
+                            const float4 xv = *reinterpret_cast<const float4*>(slot + (size_t)(2 + h4) * GITEMS * 16);
+                            const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
+                            const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
+                            v[h4 * 4 + 0] = gv.x + fmaf(c0.y, xv.x, c0.x); v[h4 * 4 + 1] = gv.y + fmaf(c0.w, xv.y, c0.z);
+                            v[h4 * 4 + 2] = gv.z + fmaf(c1.y, xv.z, c1.x); v[h4 * 4 + 3] = gv.w + fmaf(c1.w, xv.w, c1.z);
+                        } else {
+                            v[h4 * 4 + 0] = v[h4 * 4 + 1] = v[h4 * 4 + 2] = v[h4 * 4 + 3] = 0.f;
+                        }
+                    }
+                    // a pixel outside the image: g and x were zero-filled, but the lazy BatchNorm term A_c is not zero
+                    const int r = gq / PITCH, cc = gq - r * PITCH;
+                    const int y = y0 + r - 1, x = x0 + cc - 1;
+                    const bool ok = (y >= 0) && (y < A.H) && (x >= 0) && (x < A.W);
+                    const uint4 o = ok ? make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]))
+                                       : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        *reinterpret_cast<uint4*>(g_s + (kx * 2 + ghf) * PLANE_BYTES + (size_t)(gq + kx) * 16) = o;
+                }
             }
             tc::fence_proxy_async();
-            tc::mbar_arrive(op_full);
-            if (!A.one && it + 1 < ntiles) g_issue(t_begin + it + 1);           // one batch in flight while the MMAs of this tile run
+            tc::mbar_arrive(op_full + s);
+            if (tid == 0) WG_TRACE(16 + 8 * it + 4);
         }
+        tc::cp_async_wait<0>();
         // ---- epilogue: D_ky[ci][kx*16 + co] -> atomicAdd into OIHW
         tc::mbar_wait(accum, 0);
         tc::tc_fence_after();
@@ -297,20 +312,22 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
         // ---------------------------------------------------------------- MMA issuer: convergent; one elected lane issues
         const uint32_t tmem_b = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         const uint32_t idesc = tc::instr_desc(tc::FMT_BF16, 128, NB, 1, 1);
-        const uint32_t a_base = tc::smem_u32(a_s), g_base = tc::smem_u32(g_s);
         // MN-major: LBO = 8-pixel groups (128 B), SBO = 8-channel groups (planes)
         const uint64_t d_hi = tc::smem_desc(0, 128, PLANE_BYTES);
-        const uint64_t a_d0 = d_hi | (uint64_t)(a_base >> 4), b_d0 = d_hi | (uint64_t)((g_base + 16u) >> 4);
         for (int it = 0; it < ntiles; ++it) {
-            tc::mbar_wait(op_full, it & 1);
+            const int s = it & 1;
+            tc::mbar_wait(op_full + s, (it >> 1) & 1);
             tc::tc_fence_after();
+            if (lane == 0) WG_TRACE(16 + 8 * it + 5);
+            const uint32_t a_base = tc::smem_u32(smem + OP_OFF + s * STAGE), g_base = a_base + A_BYTES;
+            const uint64_t a_d0 = d_hi | (uint64_t)(a_base >> 4), b_d0 = d_hi | (uint64_t)((g_base + 16u) >> 4);
             // consecutive K-steps rotate over three accumulator sets (9 independent chains): an MMA that accumulates into the
             // tile its predecessor wrote waits ~266 cycles for it
             if (A.one) {
 #pragma unroll 1
                 for (int k16 = 0; k16 < KPX / 16; ++k16)
                     tc::mma_f16_w(tmem_b + (k16 % 9) * NB, a_d0 + (uint64_t)(PITCH + k16 * 16), b_d0 + (uint64_t)(PITCH + k16 * 16), idesc,
-                                (uint32_t)(it != 0 || k16 >= 9));
+                                (uint32_t)(it != 0));
             } else {
 #pragma unroll 1
                 for (int k16 = 0; k16 < KPX / 16; ++k16) {
@@ -322,7 +339,8 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
                         tc::mma_f16_w(tmem_b + (set * 3 + ky) * NB, ad, b_d0 + (uint64_t)(PITCH + k16 * 16 - (ky - 1) * PITCH), idesc, acc);
                 }
             }
-            tc::tc_commit_w(op_empty);
+            tc::tc_commit_w(op_empty + s);
+            if (lane == 0) WG_TRACE(16 + 8 * it + 6);
         }
         tc::tc_commit_w(accum);
     } else {
@@ -338,6 +356,7 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
                 tc::mbar_expect_tx(raw_full + s, box_bytes);
                 tma::load_4d(smem + s * RAW_BYTES, &xmap, A.in_off + ci0, x0 >> sh, y0 >> sh, b, raw_full + s);
                 tc::mbar_arrive(raw_full + s);
+                WG_TRACE(16 + 8 * it + 7);
             }
         }
     }
