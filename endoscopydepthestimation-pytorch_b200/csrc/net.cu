@@ -386,10 +386,12 @@ static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
     CUtensorMap xmap;
     if (!tma::make_nhwc_map(&xmap, t.xa, t.B, t.H >> sh, t.W >> sh, t.xa_C, tcwgrad::MCH, tcwgrad2::TW >> sh, tcwgrad2::TR >> sh))
         return ENDO_ERR_CUDA;
-    ENDO_SET_MAX_SMEM(tcwgrad2::dense_wgrad_tma_kernel, tcwgrad2::SMEM_BYTES);
+    ENDO_SET_MAX_SMEM(tcwgrad2::dense_wgrad_tma_kernel, 227 * 1024);
+    const size_t smem = tcwgrad2::smem_bytes(t.Cout, t.one);
+    if (smem > 227 * 1024) return ENDO_ERR_CONFIG;
     dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
     ProfScope prof(cat, s);
-    tcwgrad2::dense_wgrad_tma_kernel<<<grid, tcwgrad2::NTHREADS, tcwgrad2::SMEM_BYTES, s>>>(t, xmap);
+    tcwgrad2::dense_wgrad_tma_kernel<<<grid, tcwgrad2::NTHREADS, smem, s>>>(t, xmap);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }

@@ -39,31 +39,39 @@ constexpr int KPX = TR * PITCH;                          // 144 pixels = 9 K-ste
 constexpr int H_ROWS = (TR + 2) * PITCH;                 // 180 pixels of the gradient halo tile
 constexpr int PLANE_BYTES = 185 * 16;                    // 2,960 (= 16 mod 128: the 8 channel groups of a pixel spread over all banks)
 constexpr int RAW_BYTES = TR * TW * MCH * 4;             // 32,768: [8][16][64] fp32
-constexpr int NRAW = 2;
 constexpr int A_BYTES = (MCH / 8) * PLANE_BYTES;         // 23,680
 constexpr int G_BYTES = 6 * PLANE_BYTES;                 // 17,760
 constexpr int STAGE = A_BYTES + G_BYTES;                 // 41,440
-constexpr int OP_OFF = NRAW * RAW_BYTES;                 // 65,536
 constexpr int PAD_BYTES = 2 * PLANE_BYTES;               // the M = 128 read of the A operand runs 16 planes far (stage 1: past its end)
 constexpr int GITEMS = 2 * H_ROWS;                       // (halo pixel, 8-channel half) items of the gradient tile
-constexpr int GRING_OFF = OP_OFF + 2 * STAGE + PAD_BYTES;
-constexpr int GRING_BYTES = 4 * GITEMS * 16;             // per tile: [g lo, g hi, x lo, x hi][item][16 B] = 23,040
-constexpr int KTAB_OFF = GRING_OFF + 2 * GRING_BYTES;
 constexpr int KTAB_BYTES = 2 * 8 * 144;
-constexpr int BAR_OFF = KTAB_OFF + KTAB_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + 256;                // 202,976
 constexpr int NPROD = 512;
 constexpr int NTHREADS = NPROD + 64;                     // + MMA warp + TMA warp
+// Shared-memory layout, raw-ring depth chosen per mode (the TMA latency, ~4.5 k cycles, spans more than one ~3.5 k-cycle tile
+// period: with two raw slots the consumers waited ~1.1 k cycles per tile for the box, clock64 trace r2):
+//   [raw ring: nraw x 32 KB][operand stages 2 x 41,440 + pad][coefficient table][barriers][gradient ring 2 x gstage]
+//   dense layers (Cout <= 12): the second channel quad of the upper half never exists -> compact gradient slots, nraw = 3
+//   TransitionUp passes / growth 16 (Cout = 16): full slots, nraw = 2;   1x1 mode: no gradient ring, nraw = 4
+__host__ __device__ inline int raw_depth(int Cout, int one) { return one ? 4 : (Cout <= 12 ? 3 : 2); }
+__host__ __device__ inline int g_hi_items(int Cout) { return Cout <= 12 ? H_ROWS : GITEMS; }       // items that own a second quad
+__host__ __device__ inline int g_stage_bytes(int Cout, int one) { return one ? 0 : (2 * GITEMS + 2 * g_hi_items(Cout)) * 16; }
+__host__ inline size_t smem_bytes(int Cout, int one) {
+    return (size_t)raw_depth(Cout, one) * RAW_BYTES + 2 * STAGE + PAD_BYTES + KTAB_BYTES + 256 + 2 * (size_t)g_stage_bytes(Cout, one);
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char* gring = smem + GRING_OFF;
-    float* ktab = reinterpret_cast<float*>(smem + KTAB_OFF);                    // [G <= 2][8 groups][8 x float4 + pad]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-    uint64_t* raw_full = bars; uint64_t* raw_empty = bars + 2; uint64_t* op_full = bars + 4; uint64_t* op_empty = bars + 6;
-    uint64_t* accum = bars + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const int NRAW = raw_depth(A.Cout, A.one);
+    const int OP_OFF = NRAW * RAW_BYTES;
+    float* ktab = reinterpret_cast<float*>(smem + OP_OFF + 2 * STAGE + PAD_BYTES);   // [G <= 2][8 groups][8 x float4 + pad]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OP_OFF + 2 * STAGE + PAD_BYTES + KTAB_BYTES);
+    uint64_t* raw_full = bars; uint64_t* raw_empty = bars + 4; uint64_t* op_full = bars + 8; uint64_t* op_empty = bars + 10;
+    uint64_t* accum = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    unsigned char* gring = smem + OP_OFF + 2 * STAGE + PAD_BYTES + KTAB_BYTES + 256;
+    const int GRING_BYTES = g_stage_bytes(A.Cout, A.one);
+    const int ghi = g_hi_items(A.Cout);                      // slot regions of a gradient stage: g lo [GITEMS], g hi [ghi], x lo, x hi
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ci0 = blockIdx.y * MCH;
@@ -82,10 +90,8 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
         *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ktab) + (gi * 8 + (cl >> 3)) * 144 + (cl & 7) * 16) = e;
     }
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, NPROD);
-            tc::mbar_init(op_full + i, NPROD); tc::mbar_init(op_empty + i, 1);
-        }
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, NPROD); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(op_full + i, NPROD); tc::mbar_init(op_empty + i, 1); }
         tc::mbar_init(accum, 1);
         tc::fence_mbar_init();
     }
@@ -124,9 +130,11 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
                 unsigned char* slot = gring + (it & 1) * GRING_BYTES + (size_t)tid * 16;
 #pragma unroll
                 for (int h4 = 0; h4 < 2; ++h4) {
-                    const uint32_t nb = (ok && ghf * 8 + h4 * 4 < A.Cout) ? 16u : 0u;      // 0 bytes = zero fill
-                    tc::cp_async16(slot + (size_t)h4 * GITEMS * 16, A.g + oo + (nb ? h4 * 4 : 0), nb);
-                    tc::cp_async16(slot + (size_t)(2 + h4) * GITEMS * 16, A.x + oo + (nb ? h4 * 4 : 0), nb);
+                    if (ghf * 8 + h4 * 4 < A.Cout) {                             // (compact slots: the quad does not exist otherwise)
+                        const uint32_t nb = ok ? 16u : 0u;                       // 0 bytes = zero fill
+                        tc::cp_async16(slot + (size_t)(h4 ? GITEMS : 0) * 16, A.g + oo + (nb ? h4 * 4 : 0), nb);
+                        tc::cp_async16(slot + (size_t)(GITEMS + ghi + (h4 ? GITEMS : 0)) * 16, A.x + oo + (nb ? h4 * 4 : 0), nb);
+                    }
                 }
             }
             tc::cp_async_commit();                                              // one group per tile, empty or not
@@ -139,6 +147,7 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
         const bool hi_ok = ch + 4 < A.Cin;
         for (int it = 0; it < ntiles; ++it) {
             const int s = it & 1;
+            const int rs = it % NRAW, rph = (it / NRAW) & 1;                    // raw-ring slot and its phase
             unsigned char* a_s = smem + OP_OFF + s * STAGE;
             unsigned char* g_s = a_s + A_BYTES;
             int b, y0, x0;
@@ -146,7 +155,7 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
             const int g = b / (A.B / A.G);
             if (tid == 0) WG_TRACE(16 + 8 * it + 0);
             g_issue(it + 1);                                                    // next tile's gradient rows: in flight from here
-            tc::mbar_wait(raw_full + s, (it >> 1) & 1);                         // the TMA box of this tile has landed
+            tc::mbar_wait(raw_full + rs, rph);                                  // the TMA box of this tile has landed
             if (tid == 0) WG_TRACE(16 + 8 * it + 1);
             if (it >= 2) tc::mbar_wait(op_empty + s, ((it >> 1) - 1) & 1);      // the MMAs of tile it - 2 are done with this stage
             if (tid == 0) WG_TRACE(16 + 8 * it + 2);
@@ -154,7 +163,7 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
             {
                 const float4* kt = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ktab) + (g * 8 + grp) * 144);
                 const float4 k0 = kt[0], k1 = kt[1], k2 = kt[2], k3 = kt[3], k4 = kt[4], k5 = kt[5], k6 = kt[6], k7 = kt[7];
-                const unsigned char* raw = smem + s * RAW_BYTES + grp * 32;
+                const unsigned char* raw = smem + rs * RAW_BYTES + grp * 32;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int ip = (tid >> 3) + 64 * j;              // interior pixel 0 .. 127
@@ -179,7 +188,7 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
                 }
             }
             if (tid == 0) WG_TRACE(16 + 8 * it + 3);
-            tc::mbar_arrive(raw_empty + s);                                     // this thread has read its part of the raw tile
+            tc::mbar_arrive(raw_empty + rs);                                    // this thread has read its part of the raw tile
             // ---- output gradient
             if (A.one) {
                 // 1x1 mode (TransitionDown): interior only, 48 channels in three rounds of 16: the max-pool-routed gradient of the
@@ -237,8 +246,8 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
 #pragma unroll
                     for (int h4 = 0; h4 < 2; ++h4) {
                         if (ghf * 8 + h4 * 4 < A.Cout) {
-                            const float4 gv = *reinterpret_cast<const float4*>(slot + (size_t)h4 * GITEMS * 16);
-                            const float4 xv = *reinterpret_cast<const float4*>(slot + (size_t)(2 + h4) * GITEMS * 16);
+                            const float4 gv = *reinterpret_cast<const float4*>(slot + (size_t)(h4 ? GITEMS : 0) * 16);
+                            const float4 xv = *reinterpret_cast<const float4*>(slot + (size_t)(GITEMS + ghi + (h4 ? GITEMS : 0)) * 16);
                             const float4 c0 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8));
                             const float4 c1 = __ldg(reinterpret_cast<const float4*>(abp + h4 * 8 + 4));
                             v[h4 * 4 + 0] = gv.x + fmaf(c0.y, xv.x, c0.x); v[h4 * 4 + 1] = gv.y + fmaf(c0.w, xv.y, c0.z);
@@ -349,8 +358,8 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
             tma::prefetch_map(&xmap);
             const uint32_t box_bytes = (uint32_t)(MCH * (TW >> sh) * (TR >> sh) * 4);
             for (int it = 0; it < ntiles; ++it) {
-                const int s = it & 1;
-                if (it >= NRAW) tc::mbar_wait(raw_empty + s, ((it >> 1) - 1) & 1);
+                const int s = it % NRAW;
+                if (it >= NRAW) tc::mbar_wait(raw_empty + s, ((it / NRAW) - 1) & 1);
                 int b, y0, x0;
                 tile_origin(t_begin + it, b, y0, x0);
                 tc::mbar_expect_tx(raw_full + s, box_bytes);
