@@ -9,6 +9,7 @@
 #include "net_tc.cuh"
 #include "net_pw.cuh"
 #include "net_wgrad2.cuh"
+#include "net_fwd2.cuh"
 
 namespace endo {
 
@@ -289,6 +290,27 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         t.H = a.oh; t.W = a.ow; t.B = a.B; t.G = a.G; t.stats_C = a.stats_C; t.up = 0; t.dbg = tc_debug_mask(); t.one = 0;
         t.x3 = x3_mode(c.math);
         t.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + d.wp_off);   // packed by pack_dense_weights_fwd()
+        // 3xTF32 at the high-resolution levels: the persistent TMA-fed kernel of net_fwd2.cuh (ENDO_TC_DISABLE bit 32768: round-1 kernel)
+        {
+            const int tx2 = cdiv(t.W, tcfwd2::TW), ty2 = cdiv(t.H, tcfwd2::TH);
+            const int n2 = tx2 * ty2 * t.B;
+            if (t.x3 == 1 && n2 >= 4 * kNumSMs && t.K <= tcfwd2::COEF_MAX && t.N <= tcfwd2::OUT_MAXN && (t.N & 3) == 0 &&
+                !(tc_disable_mask() & 32768)) {
+                tcfwd2::Args f;
+                f.coef = t.coef; f.bias = t.bias; f.wpack = t.wpack; f.stats = t.stats;
+                f.in_off = t.in_off; f.K = t.K; f.out_off = t.out_off; f.N = t.N; f.H = t.H; f.W = t.W; f.B = t.B; f.G = t.G;
+                f.stats_C = t.stats_C; f.tiles_x = tx2; f.tiles_y = ty2; f.n_tiles = n2;
+                CUtensorMap in_map, out_map;
+                if (!tma::make_nhwc_map(&in_map, t.in, t.B, t.H, t.W, t.in_C, 8, tcfwd2::PITCH, tcfwd2::TH + 2) ||
+                    !tma::make_nhwc_map(&out_map, t.out, t.B, t.H, t.W, t.out_C, t.N, tcfwd2::TW, tcfwd2::TH))
+                    return ENDO_ERR_CUDA;
+                ENDO_SET_MAX_SMEM(tcfwd2::dense_fwd_x3_persistent_kernel, tcfwd2::SMEM_BYTES);
+                ProfScope prof(PC_CONV_DENSE_FWD, c.s);
+                tcfwd2::dense_fwd_x3_persistent_kernel<<<n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s>>>(f, in_map, out_map);
+                ENDO_CHECK_LAUNCH();
+                return ENDO_OK;
+            }
+        }
         ENDO_SET_MAX_SMEM(tcconv::dense_fwd_tf32_kernel, tcconv::SMEM_BYTES);
         // Low-resolution levels: a CTA per 32x32 tile over ALL input channels leaves most SMs idle behind a long serial
         // channel loop.  Split the channel chunks over blockIdx.y (raw partial sums to scratch, splitk_finish_kernel adds
