@@ -232,7 +232,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
         }
     } else {
         // ======================================================================== epilogue warps 18-21: TMEM lane quadrant q
-        const int q = warp - 18, et = tid - 18 * 32;                 // 0 .. 127
+        const int q = warp & 3, et = tid - 18 * 32;                   // a warp reads the TMEM lanes 32 (warp % 4) .. + 31; et = 0 .. 127
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         float s1[16], s2[16];
 #pragma unroll
