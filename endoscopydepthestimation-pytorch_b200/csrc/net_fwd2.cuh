@@ -8,8 +8,8 @@
 //
 //   * one CTA per SM walks over 32 x 16 tiles; the accumulators (5 M-blocks x 48 columns) are DOUBLE-BUFFERED in TMEM, so the
 //     epilogue of tile k overlaps the channel loop of tile k + 1;
-//   * warp 17 (one lane) streams the UNTRANSFORMED (8 channels, 34 x 18 pixels) boxes of the NHWC level buffer with
-//     cp.async.bulk.tensor into a 4-deep raw ring -- zero-filled outside the image, up to four chunks (78 KB) in flight per SM,
+//   * warp 17 (one lane) streams the UNTRANSFORMED (16 channels, 34 x 18 pixels) boxes of the NHWC level buffer with
+//     cp.async.bulk.tensor into a 2-deep raw ring -- zero-filled outside the image, four chunks (78 KB) in flight per SM,
 //     across tile boundaries -- and the weight stage images travel by TMA bulk copy;
 //   * warps 0-15 turn raw fp32 into the operand planes (BatchNorm + ReLU from a shared coefficient table, exact hi/lo split);
 //   * warp 16 issues 30 MMAs per chunk; warps 18-21 (one per TMEM lane quadrant) drain finished accumulators: horizontal taps,
@@ -36,8 +36,11 @@ constexpr int A_STAGE = 4 * PLANE_BYTES;                 // 45,696: hi0 | hi1 | 
 constexpr int NB = 48;
 constexpr int B_BLOCK = 2 * NB * 16;                     // 1,536
 constexpr int B_STAGE = 6 * B_BLOCK;                     // 9,216 = one packed weight chunk (pack_w_fwd_all_kernel, mode 1)
-constexpr int RAW_BYTES = HALO_ROWS * 32;                // 19,584 = 153 * 128: [18][34][8] fp32
-constexpr int NRAW = 4;
+constexpr int RAW_CH = 16;                               // channels per TMA box = two 8-channel chunks: 64-byte rows (a box of 8
+                                                         // channels is 612 rows of 32 bytes, and the TMA unit, not DRAM, bounded the
+                                                         // kernel at ~2.5 k cycles per chunk: ncu r2, DRAM 25 %, tensor pipe 34 %)
+constexpr int RAW_BYTES = HALO_ROWS * RAW_CH * 4;        // 39,168 = 306 * 128: [18][34][16] fp32
+constexpr int NRAW = 2;
 constexpr int COEF_MAX = 384;
 constexpr int OUT_MAXN = 16;
 constexpr int NUNITS = MBLK * 4;
@@ -114,6 +117,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
         const int quad = tid & 1;                                   // 4-channel group inside the 8-channel chunk
         int cur_g = -1;
         int j = 0;                                                  // running chunk number of this CTA (all tiles)
+        int jb = 0;                                                 // running box number (a box = two chunks)
         for (int k = 0; k < my_tiles; ++k) {
             int b, y0, x0;
             tile_origin(k, b, y0, x0);
@@ -136,7 +140,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 if (px < HALO_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) pixok |= 1u << r3;
             }
             for (int c = 0; c < nchunks; ++c, ++j) {
-                const int rs = j & (NRAW - 1), s = j & 1;
+                const int rs = jb & (NRAW - 1), s = j & 1, half = c & 1;
                 const int ch = c * 8 + quad * 4;
                 const bool ch_ok = ch < A.K;
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
@@ -145,13 +149,13 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     k0 = *reinterpret_cast<const float4*>(cf); k1 = *reinterpret_cast<const float4*>(cf + 4);
                     k2 = *reinterpret_cast<const float4*>(cf + 8); k3 = *reinterpret_cast<const float4*>(cf + 12);
                 }
-                tc::mbar_wait(raw_full + rs, (j >> 2) & 1);                        // the box of this chunk has landed
+                if (half == 0) tc::mbar_wait(raw_full + rs, (jb >> 1) & 1);        // the box of this chunk pair has landed
                 if (j >= 2) tc::mbar_wait(op_empty + s, ((j >> 1) - 1) & 1);       // the MMAs of chunk j - 2 are done with the stage
                 if (tid == 0) {                                                    // weights of this chunk: TMA bulk copy of the stage image
                     tc::mbar_expect_tx(op_full + s, (uint32_t)B_STAGE);
                     tc::bulk_g2s(smem + B_OFF + s * B_STAGE, A.wpack + (size_t)c * (B_STAGE / 4), (uint32_t)B_STAGE, op_full + s);
                 }
-                const unsigned char* raw = smem + RAW_OFF + rs * RAW_BYTES;
+                const unsigned char* raw = smem + RAW_OFF + rs * RAW_BYTES + half * 32 + quad * 16;
                 unsigned char* a_s = smem + A_OFF + s * A_STAGE;
 #pragma unroll
                 for (int r3 = 0; r3 < 3; ++r3) {
@@ -161,7 +165,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                         float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
                         uint2 lo = make_uint2(0u, 0u), xb = lo;
                         if ((pixok & (1u << r3)) && ch_ok) {
-                            float4 v = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
+                            float4 v = *reinterpret_cast<const float4*>(raw + (size_t)px * (RAW_CH * 4));
                             v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
                             v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
                             hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
@@ -173,7 +177,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                         *reinterpret_cast<uint2*>(a_s + 3 * PLANE_BYTES + (size_t)px * 16 + quad * 8) = xb;
                     }
                 }
-                tc::mbar_arrive(raw_empty + rs);
+                if (half == 1 || c == nchunks - 1) { tc::mbar_arrive(raw_empty + rs); ++jb; }    // both chunks of the box consumed
                 tc::fence_proxy_async();
                 tc::mbar_arrive(op_full + s);
             }
@@ -217,15 +221,16 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
         // ======================================================================== TMA issuer: up to NRAW chunks ahead, across tiles
         if (lane == 0) {
             tma::prefetch_map(&in_map);
-            int j = 0;
+            int jb = 0;
+            const int nboxes = (nchunks + 1) >> 1;
             for (int k = 0; k < my_tiles; ++k) {
                 int b, y0, x0;
                 tile_origin(k, b, y0, x0);
-                for (int c = 0; c < nchunks; ++c, ++j) {
-                    const int rs = j & (NRAW - 1);
-                    if (j >= NRAW) tc::mbar_wait(raw_empty + rs, ((j >> 2) - 1) & 1);
+                for (int cp = 0; cp < nboxes; ++cp, ++jb) {
+                    const int rs = jb & (NRAW - 1);
+                    if (jb >= NRAW) tc::mbar_wait(raw_empty + rs, ((jb >> 1) - 1) & 1);
                     tc::mbar_expect_tx(raw_full + rs, (uint32_t)RAW_BYTES);
-                    tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + c * 8, x0 - 1, y0 - 1, b, raw_full + rs);
+                    tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + cp * RAW_CH, x0 - 1, y0 - 1, b, raw_full + rs);
                     tc::mbar_arrive(raw_full + rs);
                 }
             }
