@@ -64,7 +64,12 @@ struct Args {
     const float* coef; const float* bias; const float* wpack; double* stats;
     int in_off, K, out_off, N, H, W, B, G, stats_C;
     int tiles_x, tiles_y, n_tiles;
+    int dbg;                                             // ENDO_TC_DEBUG bit 16: clock64 trace of CTA 0 (tools/trace_fwd2.py)
 };
+// trace slots: [0] = chunks per tile, [1] = start, [2] = tiles; per running chunk j: 16 + 8 j + {0 top, 1 raw landed, 2 stage free,
+// 3 planes written (transform thread 0); 4 operands ready, 5 MMAs issued (MMA warp); 6 box issued (TMA thread)};
+// per tile k: 1600 + 4 k + {0 accumulators ready, 1 TMEM drained, 2 store issued} (epilogue thread 0)
+#define F2_TRACE(slot) do { if ((A.dbg & 16) && blockIdx.x == 0 && (slot) < 2048) g_tc_trace[(slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
@@ -89,6 +94,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
     const int per_img = A.tiles_x * A.tiles_y;
     const int per_group = A.B / A.G;
 
+    if (tid == 0 && (A.dbg & 16) && blockIdx.x == 0) { g_tc_trace[0] = nchunks; g_tc_trace[1] = clock64(); g_tc_trace[2] = my_tiles; }
     if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
     if (tid < 16) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;
     if (tid == 0) {
@@ -197,6 +203,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 const int s = j & 1;
                 tc::mbar_wait(op_full + s, (j >> 1) & 1);
                 tc::tc_fence_after();
+                if (lane == 0) F2_TRACE(16 + 8 * j + 4);
                 const uint32_t a_base = tc::smem_u32(smem + A_OFF + s * A_STAGE);
                 const uint32_t b_base = tc::smem_u32(smem + B_OFF + s * B_STAGE);
 #pragma unroll 1
@@ -214,6 +221,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32_w(d0 + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
                 }
                 tc::tc_commit_w(op_empty + s);
+                if (lane == 0) F2_TRACE(16 + 8 * j + 5);
             }
             tc::tc_commit_w(acc_full + buf);
         }
@@ -274,6 +282,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
             const uint32_t d0 = tmem + lane_base + (uint32_t)(buf * MBLK * NB);
             tc::mbar_wait(acc_full + buf, (k >> 1) & 1);
             tc::tc_fence_after();
+            if (et == 0) F2_TRACE(1600 + 4 * k + 0);
             // the staging block of the previous tile must have been read by its TMA store before it is overwritten
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             // pass 1: publish the values the neighbouring 32-lane units need
@@ -316,6 +325,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     if (mb == MBLK - 1 && h8 == 8) {                       // last TMEM read of this tile: tile k + 2 may overwrite the buffer
                         tc::tc_fence_before();
                         tc::mbar_arrive(acc_empty + buf);
+                        if (et == 0) F2_TRACE(1600 + 4 * k + 1);
                     }
                     float o[8];
 #pragma unroll
@@ -352,6 +362,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                              "r"(A.out_off), "r"(x0), "r"(y0), "r"(b), "r"(tc::smem_u32(out_s))
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                F2_TRACE(1600 + 4 * k + 2);
             }
         }
         if (cur_g >= 0) flush_stats(cur_g);
