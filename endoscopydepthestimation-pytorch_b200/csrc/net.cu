@@ -301,7 +301,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
                 f.in_off = t.in_off; f.K = t.K; f.out_off = t.out_off; f.N = t.N; f.H = t.H; f.W = t.W; f.B = t.B; f.G = t.G;
                 f.stats_C = t.stats_C; f.tiles_x = tx2; f.tiles_y = ty2; f.n_tiles = n2; f.dbg = tc_debug_mask();
                 CUtensorMap in_map, out_map;
-                if (!tma::make_nhwc_map(&in_map, t.in, t.B, t.H, t.W, t.in_C, tcfwd2::RAW_CH, tcfwd2::PITCH, tcfwd2::TH + 2) ||
+                if (!tma::make_nhwc_map(&in_map, t.in, t.B, t.H, t.W, t.in_C, 8, tcfwd2::PITCH, tcfwd2::TH + 2) ||
                     !tma::make_nhwc_map(&out_map, t.out, t.B, t.H, t.W, t.out_C, t.N, tcfwd2::TW, tcfwd2::TH))
                     return ENDO_ERR_CUDA;
                 ENDO_SET_MAX_SMEM(tcfwd2::dense_fwd_x3_persistent_kernel, tcfwd2::SMEM_BYTES);

@@ -8,8 +8,8 @@
 //
 //   * one CTA per SM walks over 32 x 16 tiles; the accumulators (5 M-blocks x 48 columns) are DOUBLE-BUFFERED in TMEM, so the
 //     epilogue of tile k overlaps the channel loop of tile k + 1;
-//   * warp 17 (one lane) streams the UNTRANSFORMED (16 channels, 34 x 18 pixels) boxes of the NHWC level buffer with
-//     cp.async.bulk.tensor into a 2-deep raw ring -- zero-filled outside the image, four chunks (78 KB) in flight per SM,
+//   * warp 17 (one lane) streams the UNTRANSFORMED (8 channels, 34 x 18 pixels) boxes of the NHWC level buffer with
+//     cp.async.bulk.tensor into a 4-deep raw ring -- zero-filled outside the image, up to four chunks (78 KB) in flight per SM,
 //     across tile boundaries -- and the weight stage images travel by TMA bulk copy;
 //   * warps 0-15 turn raw fp32 into the operand planes (BatchNorm + ReLU from a shared coefficient table, exact hi/lo split);
 //   * warp 16 issues 30 MMAs per chunk; warps 18-21 (one per TMEM lane quadrant) drain finished accumulators: horizontal taps,
@@ -36,11 +36,8 @@ constexpr int A_STAGE = 4 * PLANE_BYTES;                 // 45,696: hi0 | hi1 | 
 constexpr int NB = 48;
 constexpr int B_BLOCK = 2 * NB * 16;                     // 1,536
 constexpr int B_STAGE = 6 * B_BLOCK;                     // 9,216 = one packed weight chunk (pack_w_fwd_all_kernel, mode 1)
-constexpr int RAW_CH = 16;                               // channels per TMA box = two 8-channel chunks: 64-byte rows (a box of 8
-                                                         // channels is 612 rows of 32 bytes, and the TMA unit, not DRAM, bounded the
-                                                         // kernel at ~2.5 k cycles per chunk: ncu r2, DRAM 25 %, tensor pipe 34 %)
-constexpr int RAW_BYTES = HALO_ROWS * RAW_CH * 4;        // 39,168 = 306 * 128: [18][34][16] fp32
-constexpr int NRAW = 2;
+constexpr int RAW_BYTES = HALO_ROWS * 32;                // 19,584 = 153 * 128: [18][34][8] fp32
+constexpr int NRAW = 4;
 constexpr int COEF_MAX = 384;
 constexpr int OUT_MAXN = 16;
 constexpr int NUNITS = MBLK * 4;
@@ -66,10 +63,10 @@ struct Args {
     int tiles_x, tiles_y, n_tiles;
     int dbg;                                             // ENDO_TC_DEBUG bit 16: clock64 trace of CTA 0 (tools/trace_fwd2.py)
 };
-// trace slots: [0] = chunks per tile, [1] = start, [2] = tiles; per running chunk j: 16 + 8 j + {0 top, 1 raw landed, 2 stage free,
-// 3 planes written (transform thread 0); 4 operands ready, 5 MMAs issued (MMA warp); 6 box issued (TMA thread)};
-// per tile k: 1600 + 4 k + {0 accumulators ready, 1 TMEM drained, 2 store issued} (epilogue thread 0)
-#define F2_TRACE(slot) do { if ((A.dbg & 16) && blockIdx.x == 0 && (slot) < 2048) g_tc_trace[(slot)] = clock64(); } while (0)
+// trace slots (first 3 tiles): [0] = chunks per tile, [1] = start, [2] = tiles; per running chunk j < 70: 16 + 8 j + {0 top, 1 raw landed,
+// 2 stage free, 3 planes written (transform thread 0); 4 operands ready, 5 MMAs issued (MMA warp); 6 box issued (TMA thread)};
+// per tile k < 8: 1900 + 4 k + {0 accumulators ready, 1 TMEM drained, 2 store issued} (epilogue thread 0)
+#define F2_TRACE(slot) do { if ((A.dbg & 16) && blockIdx.x == 0) g_tc_trace[(slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
@@ -123,7 +120,6 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
         const int quad = tid & 1;                                   // 4-channel group inside the 8-channel chunk
         int cur_g = -1;
         int j = 0;                                                  // running chunk number of this CTA (all tiles)
-        int jb = 0;                                                 // running box number (a box = two chunks)
         for (int k = 0; k < my_tiles; ++k) {
             int b, y0, x0;
             tile_origin(k, b, y0, x0);
@@ -146,7 +142,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 if (px < HALO_ROWS && y >= 0 && y < A.H && x >= 0 && x < A.W) pixok |= 1u << r3;
             }
             for (int c = 0; c < nchunks; ++c, ++j) {
-                const int rs = jb & (NRAW - 1), s = j & 1, half = c & 1;
+                const int rs = j & (NRAW - 1), s = j & 1;
                 const int ch = c * 8 + quad * 4;
                 const bool ch_ok = ch < A.K;
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
@@ -155,13 +151,16 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     k0 = *reinterpret_cast<const float4*>(cf); k1 = *reinterpret_cast<const float4*>(cf + 4);
                     k2 = *reinterpret_cast<const float4*>(cf + 8); k3 = *reinterpret_cast<const float4*>(cf + 12);
                 }
-                if (half == 0) tc::mbar_wait(raw_full + rs, (jb >> 1) & 1);        // the box of this chunk pair has landed
+                if (tid == 0 && j < 70) F2_TRACE(16 + 8 * j + 0);
+                tc::mbar_wait(raw_full + rs, (j >> 2) & 1);                        // the box of this chunk has landed
+                if (tid == 0 && j < 70) F2_TRACE(16 + 8 * j + 1);
                 if (j >= 2) tc::mbar_wait(op_empty + s, ((j >> 1) - 1) & 1);       // the MMAs of chunk j - 2 are done with the stage
+                if (tid == 0 && j < 70) F2_TRACE(16 + 8 * j + 2);
                 if (tid == 0) {                                                    // weights of this chunk: TMA bulk copy of the stage image
                     tc::mbar_expect_tx(op_full + s, (uint32_t)B_STAGE);
                     tc::bulk_g2s(smem + B_OFF + s * B_STAGE, A.wpack + (size_t)c * (B_STAGE / 4), (uint32_t)B_STAGE, op_full + s);
                 }
-                const unsigned char* raw = smem + RAW_OFF + rs * RAW_BYTES + half * 32 + quad * 16;
+                const unsigned char* raw = smem + RAW_OFF + rs * RAW_BYTES;
                 unsigned char* a_s = smem + A_OFF + s * A_STAGE;
 #pragma unroll
                 for (int r3 = 0; r3 < 3; ++r3) {
@@ -171,7 +170,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                         float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
                         uint2 lo = make_uint2(0u, 0u), xb = lo;
                         if ((pixok & (1u << r3)) && ch_ok) {
-                            float4 v = *reinterpret_cast<const float4*>(raw + (size_t)px * (RAW_CH * 4));
+                            float4 v = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
                             v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
                             v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
                             hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
@@ -183,9 +182,10 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                         *reinterpret_cast<uint2*>(a_s + 3 * PLANE_BYTES + (size_t)px * 16 + quad * 8) = xb;
                     }
                 }
-                if (half == 1 || c == nchunks - 1) { tc::mbar_arrive(raw_empty + rs); ++jb; }    // both chunks of the box consumed
+                tc::mbar_arrive(raw_empty + rs);
                 tc::fence_proxy_async();
                 tc::mbar_arrive(op_full + s);
+                if (tid == 0 && j < 70) F2_TRACE(16 + 8 * j + 3);
             }
         }
     } else if (warp == 16) {
@@ -203,7 +203,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 const int s = j & 1;
                 tc::mbar_wait(op_full + s, (j >> 1) & 1);
                 tc::tc_fence_after();
-                if (lane == 0) F2_TRACE(16 + 8 * j + 4);
+                if (lane == 0 && j < 70) F2_TRACE(16 + 8 * j + 4);
                 const uint32_t a_base = tc::smem_u32(smem + A_OFF + s * A_STAGE);
                 const uint32_t b_base = tc::smem_u32(smem + B_OFF + s * B_STAGE);
 #pragma unroll 1
@@ -221,7 +221,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     for (int mb = 0; mb < MBLK; ++mb) tc::mma_tf32_w(d0 + mb * NB, ahi + (uint64_t)(mb * 128), bhi, idesc, 1u);
                 }
                 tc::tc_commit_w(op_empty + s);
-                if (lane == 0) F2_TRACE(16 + 8 * j + 5);
+                if (lane == 0 && j < 70) F2_TRACE(16 + 8 * j + 5);
             }
             tc::tc_commit_w(acc_full + buf);
         }
@@ -229,17 +229,17 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
         // ======================================================================== TMA issuer: up to NRAW chunks ahead, across tiles
         if (lane == 0) {
             tma::prefetch_map(&in_map);
-            int jb = 0;
-            const int nboxes = (nchunks + 1) >> 1;
+            int j = 0;
             for (int k = 0; k < my_tiles; ++k) {
                 int b, y0, x0;
                 tile_origin(k, b, y0, x0);
-                for (int cp = 0; cp < nboxes; ++cp, ++jb) {
-                    const int rs = jb & (NRAW - 1);
-                    if (jb >= NRAW) tc::mbar_wait(raw_empty + rs, ((jb >> 1) - 1) & 1);
+                for (int c = 0; c < nchunks; ++c, ++j) {
+                    const int rs = j & (NRAW - 1);
+                    if (j >= NRAW) tc::mbar_wait(raw_empty + rs, ((j >> 2) - 1) & 1);
                     tc::mbar_expect_tx(raw_full + rs, (uint32_t)RAW_BYTES);
-                    tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + cp * RAW_CH, x0 - 1, y0 - 1, b, raw_full + rs);
+                    tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + c * 8, x0 - 1, y0 - 1, b, raw_full + rs);
                     tc::mbar_arrive(raw_full + rs);
+                    if (j < 70) F2_TRACE(16 + 8 * j + 6);
                 }
             }
         }
@@ -282,7 +282,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
             const uint32_t d0 = tmem + lane_base + (uint32_t)(buf * MBLK * NB);
             tc::mbar_wait(acc_full + buf, (k >> 1) & 1);
             tc::tc_fence_after();
-            if (et == 0) F2_TRACE(1600 + 4 * k + 0);
+            if (et == 0 && k < 8) F2_TRACE(1900 + 4 * k + 0);
             // the staging block of the previous tile must have been read by its TMA store before it is overwritten
             if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             // pass 1: publish the values the neighbouring 32-lane units need
@@ -325,7 +325,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     if (mb == MBLK - 1 && h8 == 8) {                       // last TMEM read of this tile: tile k + 2 may overwrite the buffer
                         tc::tc_fence_before();
                         tc::mbar_arrive(acc_empty + buf);
-                        if (et == 0) F2_TRACE(1600 + 4 * k + 1);
+                        if (et == 0 && k < 8) F2_TRACE(1900 + 4 * k + 1);
                     }
                     float o[8];
 #pragma unroll
@@ -362,7 +362,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                              "r"(A.out_off), "r"(x0), "r"(y0), "r"(b), "r"(tc::smem_u32(out_s))
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                F2_TRACE(1600 + 4 * k + 2);
+                if (k < 8) F2_TRACE(1900 + 4 * k + 2);
             }
         }
         if (cur_g >= 0) flush_stats(cur_g);

@@ -20,7 +20,7 @@ nch, t0, ntl = int(t[0]), t[1], int(t[2])
 print(f"chunks per tile {nch}, tiles of CTA 0: {ntl}")
 print("  j | top->raw landed | ->stage free | ->planes written | period || mma: ready rel top, issue time | tma issued rel top")
 prev = None
-for j in range(min(3 * nch, 190)):
+for j in range(min(3 * nch, 70)):
     b = 16 + 8 * j
     top, raw, free, done, mrdy, miss, tma = t[b:b + 7]
     per = top - prev if prev else 0
@@ -30,6 +30,6 @@ for j in range(min(3 * nch, 190)):
 print("tile | acc ready (abs) | drained - ready | store issued - ready | tile period")
 prev = None
 for k in range(min(ntl, 8)):
-    a, d, s = t[1600 + 4 * k: 1600 + 4 * k + 3]
+    a, d, s = t[1900 + 4 * k: 1900 + 4 * k + 3]
     print(f"{k:3d} | {a - t0:9d} | {d - a:6d} | {s - a:6d} | {(a - prev) if prev else 0}")
     prev = a
