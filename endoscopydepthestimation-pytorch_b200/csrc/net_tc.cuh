@@ -758,10 +758,8 @@ constexpr int W_BYTES = 9 * 2 * WBLK_BYTES;               // 36,864
 constexpr int TB_PITCH = NC * 4 + 16;                     // 272 B per pixel row (bank spread)
 constexpr int TB_BYTES = 128 * TB_PITCH;                  // 34,816
 constexpr int NBUF = 8;                                   // TMEM accumulator buffers (8 x 64 = 512 columns)
-constexpr int NEPI = 512;                                 // 16 staging / epilogue warps (round 1: 8 -- two warps per scheduler could not
-                                                          // cover the latencies of the memory-bound epilogue: warps active 14 %, ncu)
-constexpr int SMEM_BYTES = G_BYTES + W_BYTES + TB_BYTES + NC * 4 * 4 + 16 * NC * 2 * 4 + 256;
-constexpr int NTHREADS = NEPI + 32;
+constexpr int SMEM_BYTES = G_BYTES + W_BYTES + 2 * TB_BYTES + NC * 4 * 4 + 8 * NC * 2 * 4 + 256;
+constexpr int NTHREADS = 288;
 
 struct Args {
     const float* g; const float* x; const float* ab;      // gradient buffer, activation buffer, lazy correction [G][C][2]
@@ -784,10 +782,11 @@ dense_dgrad_tf32_kernel(const Args A) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* g_s = smem;
     unsigned char* w_s = smem + G_BYTES;
-    unsigned char* tb = smem + G_BYTES + W_BYTES;
-    float* ctab = reinterpret_cast<float*>(tb + TB_BYTES);                 // [NC][4] a, beta, mean, invstd
-    float* red = ctab + NC * 4;                                            // [16][NC][2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16 * NC * 2);       // w_full, acc_full[8], acc_empty[8]
+    unsigned char* tb0 = smem + G_BYTES + W_BYTES;                          // transposed epilogue tile, DOUBLE-BUFFERED: one barrier per
+                                                                           // unit instead of two (r2 ncu: 18 % of the stall samples were barriers)
+    float* ctab = reinterpret_cast<float*>(tb0 + 2 * TB_BYTES);            // [NC][4] a, beta, mean, invstd
+    float* red = ctab + NC * 4;                                            // [8][NC][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * NC * 2);        // w_full, acc_full[8], acc_empty[8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NBUF);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -802,9 +801,9 @@ dense_dgrad_tf32_kernel(const Args A) {
     const int c_begin = gridDim.y > 1 ? (int)blockIdx.y : 0;
     const int c_end = gridDim.y > 1 ? c_begin + 1 : nchunks;
 
-    if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
+    if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        tc::mbar_init(bars + 0, NEPI);
+        tc::mbar_init(bars + 0, 256);
         for (int i = 0; i < NBUF; ++i) { tc::mbar_init(bars + 1 + i, 1); tc::mbar_init(bars + 1 + NBUF + i, 128); }
         tc::fence_mbar_init();
     }
@@ -813,7 +812,7 @@ dense_dgrad_tf32_kernel(const Args A) {
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 16) {
+    if (warp < 8) {
         // ---------------------------------------------------------------- stage the output-gradient tile once
         {
             const int grp = tid & 3;
@@ -828,12 +827,12 @@ dense_dgrad_tf32_kernel(const Args A) {
             const size_t img = (size_t)b * A.H * A.W;
             float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int part = 0; part < 1; ++part) {                    // 10 pixels per thread, one batch (2 loads each)
+            for (int part = 0; part < 2; ++part) {                    // 19 pixels per thread in two batches of 10 (2 loads each)
                 float4 gq[10], xq[10];
                 unsigned okmask = 0u;
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
-                    const int px = (tid >> 2) + 128 * (part * 10 + j);
+                    const int px = (tid >> 2) + 64 * (part * 10 + j);
                     const int r = px / PITCH, cc = px - r * PITCH;
                     const int y = y0 + r - 1, x = x0 + cc - 1;
                     gq[j] = make_float4(0.f, 0.f, 0.f, 0.f); xq[j] = gq[j];
@@ -846,7 +845,7 @@ dense_dgrad_tf32_kernel(const Args A) {
                 }
 #pragma unroll
                 for (int j = 0; j < 10; ++j) {
-                    const int px = (tid >> 2) + 128 * (part * 10 + j);
+                    const int px = (tid >> 2) + 64 * (part * 10 + j);
                     if (px < REAL_ROWS) {
                         const int r = px / PITCH, cc = px - r * PITCH;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -871,15 +870,19 @@ dense_dgrad_tf32_kernel(const Args A) {
                 atomicAdd(A.db + ch + 2, bs.z); atomicAdd(A.db + ch + 3, bs.w);
             }
         }
-        const int q = warp & 3, csub = warp >> 2;             // TMEM lane quadrant, column quarter (16 columns)
+        const int q = warp & 3, chalf = warp >> 2;            // TMEM lane quadrant, column half (32 columns)
         const int quad = lane & 15, psub = lane >> 4;         // phase-2 mapping: channel quad, pixel parity
         int unit = 0;
         for (int c = c_begin; c < c_end; ++c) {
             const int ci0 = c * NC;
             // ------------------------------------------------------------ weights + BN table of this ci chunk
-            if (tid == 0) {   // 36,864-byte weight image of this chunk: TMA bulk copy, completing on w_full as a transaction count
-                tc::mbar_expect_tx(bars + 0, (uint32_t)W_BYTES);
-                tc::bulk_g2s(w_s, A.wpack + (size_t)c * 9216, (uint32_t)W_BYTES, bars + 0);
+            {   // 36,864-byte weight image of this chunk, copied verbatim (9 x 16 B per thread, all loads first)
+                const float4* src = reinterpret_cast<const float4*>(A.wpack + (size_t)c * 9216);
+                float4 wq[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) wq[j] = __ldg(src + tid + 256 * j);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) *reinterpret_cast<float4*>(w_s + (size_t)(tid + 256 * j) * 16) = wq[j];
             }
             if (tid < NC) {
                 const int ci = ci0 + tid;
@@ -889,7 +892,7 @@ dense_dgrad_tf32_kernel(const Args A) {
             }
             tc::fence_proxy_async();
             tc::mbar_arrive(bars + 0);                         // w_full: phase c
-            asm volatile("bar.sync 1, 512;" ::: "memory");     // ctab visible to all epilogue threads
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // ctab visible to all epilogue threads
             // per-lane constants for the 4 channels this lane owns in phase 2
             float ca[4], cb[4], cm[4], cs[4];
 #pragma unroll
@@ -901,15 +904,16 @@ dense_dgrad_tf32_kernel(const Args A) {
             float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
             for (int mb = 0; mb < MBLK; ++mb, ++unit) {
                 const int buf = unit % NBUF;
+                unsigned char* tb = tb0 + (unit & 1) * TB_BYTES;
                 // the activations / gradient rows this lane will update (phase 2) do not depend on the accumulator: request them
                 // first, so that they travel while the MMAs finish, the accumulator is drained and the warps meet at the barrier
-                float4 xv[4];
+                float4 xv[8];
                 unsigned okmask = 0u;
-                size_t off[4];
+                size_t off[8];
                 if (quad_ok) {
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {                     // all 4 loads of this unit in flight at once
-                        const int p = warp * 8 + it * 2 + psub;
+                    for (int it = 0; it < 8; ++it) {                     // all 8 loads of this unit in flight at once
+                        const int p = warp * 16 + it * 2 + psub;
                         const int L = PITCH + mb * 128 + p;
                         const int r = L / PITCH, cc = L - r * PITCH;
                         const int y = y0 + r - 1, x = x0 + cc - 1;
@@ -929,24 +933,28 @@ dense_dgrad_tf32_kernel(const Args A) {
                 tc::tc_fence_after();
                 // phase 1: TMEM -> registers -> transposed shared tile [pixel][channel]
                 {
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * NC + csub * 16;
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * NC + chalf * 32;
                     float v[16];
-                    unsigned char* row = tb + (size_t)(q * 32 + lane) * TB_PITCH + csub * 64;
+                    unsigned char* row = tb + (size_t)(q * 32 + lane) * TB_PITCH + chalf * 128;
                     tc::tmem_ld16(taddr, v);
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
                         *reinterpret_cast<float4*>(row + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    tc::tmem_ld16(taddr + 16, v);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(row + 64 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
                 tc::tc_fence_before();
-                asm volatile("bar.sync 1, 512;" ::: "memory");               // all 16 warps have drained their TMEM part
-                if (csub == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);       // 128 arrivals: accumulator buffer free again
+                asm volatile("bar.sync 1, 256;" ::: "memory");               // all 8 warps have drained their TMEM part
+                if (chalf == 0) tc::mbar_arrive(bars + 1 + NBUF + buf);      // 128 arrivals: accumulator buffer free again
                 // phase 2: lane = (pixel parity, channel quad); 16 pixels per warp
                 if (quad_ok) {
                     if (A.plain) {
 #pragma unroll
-                        for (int it = 0; it < 4; ++it) {
+                        for (int it = 0; it < 8; ++it) {
                             if (okmask & (1u << it)) {
-                                const int p = warp * 8 + it * 2 + psub;
+                                const int p = warp * 16 + it * 2 + psub;
                                 const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
                                 if (A.first) *reinterpret_cast<float4*>(A.po + off[it]) = d;
                                 else tcconv::red_add_v4(A.po + off[it], d.x, d.y, d.z, d.w);
@@ -954,9 +962,9 @@ dense_dgrad_tf32_kernel(const Args A) {
                         }
                     } else
 #pragma unroll
-                    for (int it = 0; it < 4; ++it) {
+                    for (int it = 0; it < 8; ++it) {
                         if (okmask & (1u << it)) {
-                            const int p = warp * 8 + it * 2 + psub;
+                            const int p = warp * 16 + it * 2 + psub;
                             const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
                             const float4 xq = xv[it];
                             const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
@@ -973,7 +981,8 @@ dense_dgrad_tf32_kernel(const Args A) {
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 512;" ::: "memory");           // transposed tile free for the next unit
+                // (no barrier here: the next unit writes the OTHER transposed tile; this one is rewritten two units later, after the
+                // barrier of the next unit, which every thread reaches only when it has finished reading this one)
             }
             // ------------------------------------------------------------ BN-backward sums of this chunk
 #pragma unroll
@@ -985,20 +994,20 @@ dense_dgrad_tf32_kernel(const Args A) {
                     red[(warp * NC + quad * 4 + e) * 2 + 1] = s2[e];
                 }
             }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < 2 * NC) {
                 const int j = tid >> 1, which = tid & 1;
                 if (ci0 + j < A.Cin && !A.plain) {
                     double sum = 0.0;
 #pragma unroll
-                    for (int wq = 0; wq < 16; ++wq) sum += (double)red[(wq * NC + j) * 2 + which];
+                    for (int wq = 0; wq < 8; ++wq) sum += (double)red[(wq * NC + j) * 2 + which];
                     atomicAdd(A.red + ((size_t)g * A.red_C + ci0 + j) * 2 + which, sum);
                 }
             }
-            asm volatile("bar.sync 1, 512;" ::: "memory");               // red / ctab / weights reusable
+            asm volatile("bar.sync 1, 256;" ::: "memory");               // red / ctab / weights reusable
         }
     } else {
-        // -------------------------------------------------------------------- MMA issuer: warp 16, convergent; one elected lane issues
+        // -------------------------------------------------------------------- MMA issuer: warp 8, convergent; one elected lane issues
         const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
         const uint32_t idesc = tc::instr_desc(tc::FMT_TF32, 128, NC);
         const uint32_t g_base = tc::smem_u32(g_s), w_base = tc::smem_u32(w_s);
@@ -1037,7 +1046,7 @@ dense_dgrad_tf32_kernel(const Args A) {
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 8) {
         __syncwarp();
         tc::tmem_dealloc(tmem, 512);
     }
