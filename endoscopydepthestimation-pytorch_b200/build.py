@@ -16,6 +16,8 @@ STAMP = os.path.join(HERE, "csrc", ".build_stamp")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
           "-Xptxas", "-v"]
+if os.environ.get("ENDO_BUILD_TRACE") == "1":      # clock64 trace points in the persistent kernels (tools/trace_*.py)
+    COMMON.append("-DENDO_TRACE_BUILD")
 # per-file extra flags: the geometric kernels follow the reference's fp32 operation order
 # (bit-exact thresholded masks), so FMA contraction is switched off there; they are HBM-bound.
 PER_FILE = {"geometry.cu": ["-fmad=false"], "losses.cu": ["-fmad=false"]}

@@ -30,7 +30,11 @@ namespace tcwgrad2 {
 
 // trace slots: [0] = tiles, [1] = start; producers (thread 0) 16 + 8 it + {0 loop top, 1 raw landed, 2 planes free, 3 activations
 // written, 4 gradient written / arrived}; MMA warp 16 + 8 it + {5 operands ready, 6 issued}; TMA thread 16 + 8 it + 7 = issued
+#ifdef ENDO_TRACE_BUILD
 #define WG_TRACE(slot) do { if ((A.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0 && (slot) < 2048) g_tc_trace[(slot)] = clock64(); } while (0)
+#else
+#define WG_TRACE(slot) do { } while (0)
+#endif
 
 using tcwgrad::Args; using tcwgrad::MCH; using tcwgrad::NB; using tcwgrad::pack_bf16;
 

@@ -1,6 +1,6 @@
 """clock64 trace of CTA 0 of the LAST persistent forward launch (denseBlocksUp.4.layers.3, Cin 180, 16 x 256x320):
    python tools/trace_fwd2.py"""
-import ctypes, os, sys, torch
+import ctypes, os, sys, torch   # needs a trace build: ENDO_BUILD_TRACE=1 python -m endo_b200.build --force
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["ENDO_TC_DEBUG"] = "16"

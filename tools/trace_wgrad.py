@@ -1,6 +1,6 @@
 """clock64 trace of CTA (0,0) of the FIRST weight-gradient launch of a backward (denseBlocksUp.4.layers.3, Cin 180, 256x320 x16):
    ENDO_TC_DEBUG=8 ENDO_TC_DISABLE=8192 python tools/trace_wgrad.py"""
-import ctypes, os, sys, torch
+import ctypes, os, sys, torch   # needs a trace build: ENDO_BUILD_TRACE=1 python -m endo_b200.build --force
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["ENDO_TC_DEBUG"] = "8"
