@@ -299,7 +299,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
                 tcfwd2::Args f;
                 f.coef = t.coef; f.bias = t.bias; f.wpack = t.wpack; f.stats = t.stats;
                 f.in_off = t.in_off; f.K = t.K; f.out_off = t.out_off; f.N = t.N; f.H = t.H; f.W = t.W; f.B = t.B; f.G = t.G;
-                f.stats_C = t.stats_C; f.tiles_x = tx2; f.tiles_y = ty2; f.n_tiles = n2; f.dbg = tc_debug_mask();
+                f.stats_C = t.stats_C; f.tiles_x = tx2; f.tiles_y = ty2; f.n_tiles = n2; f.up = 0; f.dbg = tc_debug_mask();
                 CUtensorMap in_map, out_map;
                 if (!tma::make_nhwc_map(&in_map, t.in, t.B, t.H, t.W, t.in_C, 8, tcfwd2::PITCH, tcfwd2::TH + 2) ||
                     !tma::make_nhwc_map(&out_map, t.out, t.B, t.H, t.W, t.out_C, t.N, tcfwd2::TW, tcfwd2::TH))
@@ -635,7 +635,27 @@ static int trans_up_fwd(const Ctx& c, int i) {
     if (is_tc(c.math) && !(tc_disable_mask() & 8)) {
         // tcgen05: the DenseLayer forward kernel with the upsampling loader, 16 output channels per pass
         ENDO_SET_MAX_SMEM(tcconv::dense_fwd_tf32_kernel, tcconv::SMEM_BYTES);
-        for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
+        const int tx2 = cdiv(a.ow, tcfwd2::TW), ty2 = cdiv(a.oh, tcfwd2::TH), n2 = tx2 * ty2 * a.B;
+        const bool use2 = x3_mode(c.math) == 1 && n2 >= 4 * kNumSMs && !(a.oh & 1) && !(a.ow & 1) && !(tc_disable_mask() & 32768);
+        for (int co0 = 0; co0 < (use2 ? t.conv.cout : 0); co0 += 16) {
+            // persistent TMA-fed kernel (net_fwd2.cuh) with the upsampling transform, 16 output channels per pass
+            tcfwd2::Args f;
+            f.coef = nullptr; f.bias = a.bias + co0; f.stats = a.stats;
+            f.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + t.wp_off[co0 / 16]);
+            f.in_off = a.in_off; f.K = a.K; f.out_off = a.out_off + co0; f.N = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
+            f.H = a.oh; f.W = a.ow; f.B = a.B; f.G = a.G; f.stats_C = a.stats_C; f.tiles_x = tx2; f.tiles_y = ty2; f.n_tiles = n2;
+            f.up = 1; f.dbg = 0;
+            if (f.N & 3) return ENDO_ERR_CONFIG;
+            CUtensorMap in_map, out_map;
+            if (!tma::make_nhwc_map(&in_map, a.in, a.B, a.oh >> 1, a.ow >> 1, a.in_C, 8, tcfwd2::UP_W, tcfwd2::UP_H) ||
+                !tma::make_nhwc_map(&out_map, a.out, a.B, a.oh, a.ow, a.out_C, f.N, tcfwd2::TW, tcfwd2::TH))
+                return ENDO_ERR_CUDA;
+            ENDO_SET_MAX_SMEM(tcfwd2::dense_fwd_x3_persistent_kernel, tcfwd2::SMEM_BYTES);
+            ProfScope prof(PC_CONV_TRANS_FWD, c.s);
+            tcfwd2::dense_fwd_x3_persistent_kernel<<<n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s>>>(f, in_map, out_map);
+            ENDO_CHECK_LAUNCH();
+        }
+        for (int co0 = 0; co0 < (use2 ? 0 : t.conv.cout); co0 += 16) {
             tcconv::FwdArgs f;
             f.in = a.in; f.coef = nullptr; f.w = a.w + (size_t)co0 * t.cin * 9; f.bias = a.bias + co0; f.out = a.out; f.stats = a.stats;
             f.in_C = a.in_C; f.in_off = a.in_off; f.K = a.K; f.out_C = a.out_C; f.out_off = a.out_off + co0;

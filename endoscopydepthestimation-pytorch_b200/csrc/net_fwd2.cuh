@@ -37,6 +37,8 @@ constexpr int NB = 48;
 constexpr int B_BLOCK = 2 * NB * 16;                     // 1,536
 constexpr int B_STAGE = 6 * B_BLOCK;                     // 9,216 = one packed weight chunk (pack_w_fwd_all_kernel, mode 1)
 constexpr int RAW_BYTES = HALO_ROWS * 32;                // 19,584 = 153 * 128: [18][34][8] fp32
+constexpr int UP_W = TW / 2 + 2, UP_H = TH / 2 + 2;      // half-resolution box of the upsampling mode: 18 x 10 pixels
+constexpr int RAW_BYTES_UP = UP_W * UP_H * 32;           // 5,760
 constexpr int NRAW = 4;
 constexpr int COEF_MAX = 384;
 constexpr int OUT_MAXN = 16;
@@ -61,6 +63,8 @@ struct Args {
     const float* coef; const float* bias; const float* wpack; double* stats;
     int in_off, K, out_off, N, H, W, B, G, stats_C;
     int tiles_x, tiles_y, n_tiles;
+    int up;                                              // 1: TransitionUp (models.py:70-80): the operand is the half-resolution buffer,
+                                                         // nearest-upsampled x2, no BatchNorm / ReLU; the TMA box is (8, 18, 10) of it
     int dbg;                                             // ENDO_TC_DEBUG bit 16: clock64 trace of CTA 0 (tools/trace_fwd2.py)
 };
 // trace slots (first 3 tiles): [0] = chunks per tile, [1] = start, [2] = tiles; per running chunk j < 70: 16 + 8 j + {0 top, 1 raw landed,
@@ -130,7 +134,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
             int b, y0, x0;
             tile_origin(k, b, y0, x0);
             const int g = b / per_group;
-            if (g != cur_g) {
+            if (g != cur_g && !A.up) {
                 // (a, beta, mean, invstd) of every input channel of this statistic group.  The table is only read by these 512
                 // threads, between their own barriers: safe to rewrite when the group changes (tiles are visited in image order).
                 asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -152,7 +156,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 const int ch = c * 8 + quad * 4;
                 const bool ch_ok = ch < A.K;
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
-                if (ch_ok) {
+                if (ch_ok && !A.up) {
                     const float* cf = coef_s + ch * 4;
                     k0 = *reinterpret_cast<const float4*>(cf); k1 = *reinterpret_cast<const float4*>(cf + 4);
                     k2 = *reinterpret_cast<const float4*>(cf + 8); k3 = *reinterpret_cast<const float4*>(cf + 12);
@@ -176,9 +180,16 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                         float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
                         uint2 lo = make_uint2(0u, 0u), xb = lo;
                         if ((pixok & (1u << r3)) && ch_ok) {
-                            float4 v = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
-                            v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
-                            v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
+                            float4 v;
+                            if (A.up) {                                  // fine pixel (r, cc) of the halo tile <- half-resolution box pixel
+                                const int r = px / PITCH, cc = px - r * PITCH;
+                                const int sp = (((r - 1) >> 1) + 1) * UP_W + ((cc - 1) >> 1) + 1;
+                                v = *reinterpret_cast<const float4*>(raw + (size_t)sp * 32 + quad * 16);
+                            } else {
+                                v = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
+                                v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
+                                v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
+                            }
                             hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
                             lo = make_uint2(bf16x2_rn(v.x - hi.x, v.y - hi.y), bf16x2_rn(v.z - hi.z, v.w - hi.w));
                             xb = make_uint2(bf16x2_rn(v.x, v.y), bf16x2_rn(v.z, v.w));
@@ -242,8 +253,9 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 for (int c = 0; c < nchunks; ++c, ++j) {
                     const int rs = j & (NRAW - 1);
                     if (j >= NRAW) tc::mbar_wait(raw_empty + rs, ((j >> 2) - 1) & 1);
-                    tc::mbar_expect_tx(raw_full + rs, (uint32_t)RAW_BYTES);
-                    tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + c * 8, x0 - 1, y0 - 1, b, raw_full + rs);
+                    tc::mbar_expect_tx(raw_full + rs, (uint32_t)(A.up ? RAW_BYTES_UP : RAW_BYTES));
+                    if (A.up) tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + c * 8, (x0 >> 1) - 1, (y0 >> 1) - 1, b, raw_full + rs);
+                    else tma::load_4d(smem + RAW_OFF + rs * RAW_BYTES, &in_map, A.in_off + c * 8, x0 - 1, y0 - 1, b, raw_full + rs);
                     tc::mbar_arrive(raw_full + rs);
                     if (j < 70) F2_TRACE(16 + 8 * j + 6);
                 }
