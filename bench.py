@@ -471,13 +471,13 @@ def kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg=N
     achieved_tf = work_flops[dominant] / (dom_ms * 1e-3) / 1e12
     kind = {"fp32": "fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe)",
             "tf32": "tcgen05 kernels, tf32 / bf16 operands, fp32 accumulate in TMEM",
-            "tf32x3": "tcgen05 kernels: 3xTF32 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM",
+            "tf32x3": "tcgen05 kernels: 3xTF32 forward (persistent, TMA-fed), tf32 data gradient, bf16 weight gradient (TMA-fed), fp32 accumulate in TMEM",
             "bf16": "tcgen05 kernels: bf16 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM",
             "bf16x3": "tcgen05 kernels: bf16x3 forward, tf32 data gradient, bf16 weight gradient, fp32 accumulate in TMEM"}[math_mode]
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
                 "launches_per_step": dom_launches, "avg_launch_ms": dom_ms / dom_launches,
-                "algorithmic_bytes_per_launch": work_bytes[dominant] / dom_launches,
+                "algorithmic_bytes_per_launch_avg": work_bytes[dominant] / dom_launches,
                 "tensor": {"achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": achieved_tf / peaks["bf16_tflops_sustained"],
                            "note": "algorithmic conv FLOPs of the class over the same time, against the measured dense bf16 peak"},
@@ -492,7 +492,10 @@ def kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg=N
         with open(tpath) as fh:
             table = json.load(fh)
         if dominant in table:
+            # `traffic` and `traffic_launch_algorithmic_bytes` refer to the SAME launch (the class's largest one, named in
+            # traffic_of.launch); algorithmic_bytes_per_launch_avg above is the average over the class's launches of a step
             roofline["traffic"] = table[dominant]["dram_bytes"]
+            roofline["traffic_launch_algorithmic_bytes"] = table[dominant]["algorithmic_bytes"]
             roofline["traffic_of"] = table[dominant]
     kernels = {k: {"ms_per_step": round(v, 4), "launch_sites": cat_n[k]} for k, v in cat_ms.items()}
     for k, byts in work_bytes.items():
