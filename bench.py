@@ -585,7 +585,8 @@ def main():
     # NEXT step's 16 input tensors (copy stream, overlapping this step's compute), the device-to-device hand-over into the
     # graph's inputs, one graph launch, and the D2H read of the loss (train.py:317 / :330).
     e2e = None
-    if not args.no_e2e:
+    skip = os.environ.get("ENDO_BENCH_SKIP", "").split(",")          # debugging aid: e2e, modules, breakdown, c3, c5
+    if not args.no_e2e and "e2e" not in skip:
         model2 = new_model(math_mode)
         g2 = train_step.GraphedTrainStep(model2, h, w, resident, lr=1e-4, momentum=0.9, max_norm=10.0, dcl_weight=5.0,
                                          sfl_weight=20.0, pair=True, process_group=pg, warmup=2)
@@ -648,7 +649,7 @@ def main():
         del model2, opt, stack
 
     # ------------------------------------------------------------------ per-kernel-class timing (roofline)
-    roofline, kernels = kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg)
+    roofline, kernels = ({}, {}) if "breakdown" in skip else kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg)
 
     # ------------------------------------------------------------------ extra arms (single GPU only)
     other_arms, warp_layer, cpu = {}, None, None
@@ -659,7 +660,7 @@ def main():
         del fused, model
         torch.cuda.empty_cache()
         for name, mode in (("c3", "bf16"), ("c5", "tf32x3")):
-            if name == args.config:
+            if name == args.config or name in skip:
                 continue
             b3, h3, w3, _, d3 = CONFIGS[name]
             hb = endo_b200.synthetic.make_batch(b3, h3, w3, seed=10085 + rank)

@@ -145,9 +145,15 @@ _ws_cache = {}
 
 
 def workspace(device, nbytes: int) -> torch.Tensor:
-    """Per (device, stream) scratch with a zeroed, self-resetting counter header (see endo_b200.h)."""
+    """Per (device, stream) scratch with a zeroed, self-resetting counter header (see endo_b200.h).
+
+    While the current stream is being CAPTURED into a CUDA graph the scratch is a fresh allocation from the graph's
+    private memory pool (its zero-fill is captured with it and replayed): a cached tensor would belong to the pool of
+    whichever graph was captured first and be shared by every later graph of the process."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros(max(nbytes, 1 << 12), dtype=torch.uint8, device=device)
     key = (device.index if device.index is not None else torch.cuda.current_device(),
-           torch.cuda.current_stream(device).cuda_stream, torch.cuda.is_current_stream_capturing())
+           torch.cuda.current_stream(device).cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)

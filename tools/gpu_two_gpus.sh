@@ -1,7 +1,11 @@
 #!/bin/bash
+# 2-GPU run of the bench exactly as the driver launches it (torchrun, one rank per GPU, NCCL)
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 exit $?"
-tail -2 gpurun_out/bench_n2.err
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_n2.json').read().strip().splitlines()[-1]); print({k:d[k] for k in ('value','n_gpus','ms_per_step','scaling','e2e','clocks','gpu_launches')})"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_n2_ref.json 2>> gpurun_out/bench_n2.err; echo "ref n2 exit $?"; cut -c1-160 gpurun_out/bench_n2_ref.json
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err; echo "n2 exit $?"; tail -5 gpurun_out/r2_bench_n2.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2_bench_n2.json'))
+print('n_gpus',d['n_gpus'],'value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'modules',d['e2e']['modules_as_train_py']['value'],'loss',d['config']['loss'])
+print('other_configs',{k:(v['value'],v['ms_per_step']) for k,v in d['other_configs'].items()})
+PY
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | cut -c1-300
