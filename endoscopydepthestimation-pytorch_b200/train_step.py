@@ -121,7 +121,7 @@ class GraphedTrainStep:
     On several GPUs the gradient all-reduce runs between two graphs (forward + backward | optimiser tail)."""
 
     def __init__(self, net, height, width, example_batch, lr=1.0e-3, momentum=0.9, max_norm=10.0, dcl_weight=5.0,
-                 sfl_weight=20.0, epsilon=1.0e-8, pair=True, process_group=None, warmup=3):
+                 sfl_weight=20.0, epsilon=1.0e-8, pair=True, process_group=None, warmup=3, split_graphs=None):
         from .synthetic import BATCH_KEYS_H2D
         self.keys = [k for k in BATCH_KEYS_H2D if k in example_batch]
         dev = next(net.parameters()).device
@@ -130,6 +130,9 @@ class GraphedTrainStep:
         self.inner = TrainStep(net, height, width, lr=lr, momentum=momentum, max_norm=max_norm, dcl_weight=dcl_weight,
                                sfl_weight=sfl_weight, epsilon=epsilon, pair=pair, process_group=process_group)
         self.world, self.pg = self.inner.world, process_group
+        # two graphs (forward + backward | optimiser tail) around the gradient all-reduce on several GPUs; `split_graphs=True`
+        # forces that shape on one GPU (tests)
+        self.split = (self.world > 1) if split_graphs is None else bool(split_graphs)
         self.static = {k: example_batch[k].to(dev, copy=True) for k in self.keys}
         self.staging = {k: torch.empty_like(v) for k, v in self.static.items()}
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
@@ -152,10 +155,10 @@ class GraphedTrainStep:
         self.g_main = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_main):
             self._eager_fwd_bwd()
-            if self.world == 1:
+            if not self.split:
                 self._eager_tail()
         self.g_tail = None
-        if self.world > 1:
+        if self.split:
             self.g_tail = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_tail):
                 self._eager_tail()
@@ -177,9 +180,10 @@ class GraphedTrainStep:
 
     def replay(self):
         self.g_main.replay()
-        if self.world > 1:
-            from . import ddp
-            ddp.allreduce_gradients(self.net, self.finite, self.pg)
+        if self.split:
+            if self.world > 1:
+                from . import ddp
+                ddp.allreduce_gradients(self.net, self.finite, self.pg)
             self.g_tail.replay()
         return self.loss, self.dcl, self.sfl
 

@@ -306,3 +306,27 @@ def test_cuda_graph_step_equals_eager_step():
     l4, _, _ = graphed.replay()
     l4e, _, _ = eager.step(cb)
     assert abs(float(l4) - float(l4e)) / abs(float(l4e)) < 1e-5
+
+
+def test_successive_graphed_steps_in_one_process():
+    """Two GraphedTrainStep objects one after the other (the first deleted, cache emptied), in the two-graph shape the
+    multi-GPU path uses: round 2 found a crash here on N > 1 GPUs (a cached workspace living in the first graph's pool)."""
+    import gc
+    g, (b, h, w, stride), state, cb = _fixture_setup("step_b")
+    losses = []
+    for _ in range(2):
+        m = endo_b200.models.FCDenseNet57(n_classes=1, math="tf32x3")
+        m.load_state_dict(state)
+        m.cuda().train()
+        ts = endo_b200.train_step.GraphedTrainStep(m, h, w, cb, lr=1e-3, pair=True, split_graphs=True)
+        m.load_state_dict(state)
+        ts.inner.opt.buf.zero_()
+        l0, _, _ = ts.replay()
+        l1, _, _ = ts.replay()
+        torch.cuda.synchronize()
+        losses.append((float(l0), float(l1)))
+        del ts, m
+        gc.collect()
+        torch.cuda.empty_cache()
+    assert abs(losses[0][0] - g["loss"][0]) / g["loss"][0] < LOSS_TOL and abs(losses[0][1] - g["loss"][1]) / g["loss"][1] < LOSS_TOL
+    assert abs(losses[1][0] - losses[0][0]) < 1e-5 and abs(losses[1][1] - losses[0][1]) < 1e-5, losses
