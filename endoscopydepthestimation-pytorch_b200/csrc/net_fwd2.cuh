@@ -172,28 +172,40 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 }
                 const unsigned char* raw = smem + RAW_OFF + rs * RAW_BYTES;
                 unsigned char* a_s = smem + A_OFF + s * A_STAGE;
+                // BRANCH-FREE item loop (the three items of a thread interleave in the instruction stream: the transform, not the MMA
+                // issue or the TMA stream, bounded this kernel -- clock64 trace r2): loads are unconditional (clamped index), invalid
+                // items become zeros through a mask, only the stores of the partial third round are predicated.  The tf32 "hi" part is
+                // round-to-nearest-ties-away done on the integer pipe ((bits + 0x1000) & ~0x1fff == cvt.rna.tf32.f32 for finite
+                // normal values), and the bf16 copy of x that multiplies w_lo (2^-12 of the product) is the upper half of hi.
+                float4 v3[3];
+#pragma unroll
+                for (int r3 = 0; r3 < 3; ++r3) {
+                    const int i = min(tid + NPROD * r3, 2 * HALO_ROWS - 1);
+                    if (A.up) {                                          // fine pixel (r, cc) of the halo tile <- half-resolution box pixel
+                        const int px = i >> 1, r = px / PITCH, cc = px - r * PITCH;
+                        const int sp = (((r - 1) >> 1) + 1) * UP_W + ((cc - 1) >> 1) + 1;
+                        v3[r3] = *reinterpret_cast<const float4*>(raw + (size_t)sp * 32 + quad * 16);
+                    } else {
+                        v3[r3] = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
+                    }
+                }
 #pragma unroll
                 for (int r3 = 0; r3 < 3; ++r3) {
                     const int i = tid + NPROD * r3;
                     const int px = i >> 1;
-                    if (px < HALO_ROWS) {
-                        float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
-                        uint2 lo = make_uint2(0u, 0u), xb = lo;
-                        if ((pixok & (1u << r3)) && ch_ok) {
-                            float4 v;
-                            if (A.up) {                                  // fine pixel (r, cc) of the halo tile <- half-resolution box pixel
-                                const int r = px / PITCH, cc = px - r * PITCH;
-                                const int sp = (((r - 1) >> 1) + 1) * UP_W + ((cc - 1) >> 1) + 1;
-                                v = *reinterpret_cast<const float4*>(raw + (size_t)sp * 32 + quad * 16);
-                            } else {
-                                v = *reinterpret_cast<const float4*>(raw + (size_t)i * 16);
-                                v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
-                                v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
-                            }
-                            hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                            lo = make_uint2(bf16x2_rn(v.x - hi.x, v.y - hi.y), bf16x2_rn(v.z - hi.z, v.w - hi.w));
-                            xb = make_uint2(bf16x2_rn(v.x, v.y), bf16x2_rn(v.z, v.w));
-                        }
+                    float4 v = v3[r3];
+                    if (!A.up) {
+                        v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
+                        v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
+                    }
+                    const bool live = (pixok & (1u << r3)) && ch_ok;
+                    v.x = live ? v.x : 0.f; v.y = live ? v.y : 0.f; v.z = live ? v.z : 0.f; v.w = live ? v.w : 0.f;
+                    const uint32_t hx = (__float_as_uint(v.x) + 0x1000u) & 0xffffe000u, hy = (__float_as_uint(v.y) + 0x1000u) & 0xffffe000u;
+                    const uint32_t hz = (__float_as_uint(v.z) + 0x1000u) & 0xffffe000u, hw = (__float_as_uint(v.w) + 0x1000u) & 0xffffe000u;
+                    const float4 hi = make_float4(__uint_as_float(hx), __uint_as_float(hy), __uint_as_float(hz), __uint_as_float(hw));
+                    const uint2 lo = make_uint2(bf16x2_rn(v.x - hi.x, v.y - hi.y), bf16x2_rn(v.z - hi.z, v.w - hi.w));
+                    const uint2 xb = make_uint2(__byte_perm(hx, hy, 0x7632), __byte_perm(hz, hw, 0x7632));   // bf16(x) ~ upper halves of hi
+                    if (r3 < 2 || px < HALO_ROWS) {
                         *reinterpret_cast<float4*>(a_s + quad * PLANE_BYTES + (size_t)px * 16) = hi;
                         *reinterpret_cast<uint2*>(a_s + 2 * PLANE_BYTES + (size_t)px * 16 + quad * 8) = lo;
                         *reinterpret_cast<uint2*>(a_s + 3 * PLANE_BYTES + (size_t)px * 16 + quad * 8) = xb;
