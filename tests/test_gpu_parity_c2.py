@@ -321,10 +321,10 @@ def test_successive_graphed_steps_in_one_process():
         ts = endo_b200.train_step.GraphedTrainStep(m, h, w, cb, lr=1e-3, pair=True, split_graphs=True)
         m.load_state_dict(state)
         ts.inner.opt.buf.zero_()
-        l0, _, _ = ts.replay()
-        l1, _, _ = ts.replay()
+        l0 = float(ts.replay()[0])            # (the returned tensors are the graph's static outputs: read before the next replay)
+        l1 = float(ts.replay()[0])
         torch.cuda.synchronize()
-        losses.append((float(l0), float(l1)))
+        losses.append((l0, l1))
         del ts, m
         gc.collect()
         torch.cuda.empty_cache()
