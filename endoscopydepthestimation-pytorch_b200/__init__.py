@@ -13,7 +13,7 @@ __version__ = "0.1.0"
 
 def __getattr__(name):
     # heavy submodules are imported on first use so that `import endo_b200` stays cheap
-    if name in ("models", "losses", "functional", "optim", "ddp", "_lib", "build", "engine", "train_step"):
+    if name in ("models", "losses", "functional", "optim", "ddp", "_lib", "build", "engine", "train_step", "utils"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -20,7 +20,7 @@ if os.environ.get("ENDO_BUILD_TRACE") == "1":      # clock64 trace points in the
     COMMON.append("-DENDO_TRACE_BUILD")
 # per-file extra flags: the geometric kernels follow the reference's fp32 operation order
 # (bit-exact thresholded masks), so FMA contraction is switched off there; they are HBM-bound.
-PER_FILE = {"geometry.cu": ["-fmad=false"], "losses.cu": ["-fmad=false"]}
+PER_FILE = {"geometry.cu": ["-fmad=false"], "losses.cu": ["-fmad=false"], "export.cu": ["-fmad=false"]}
 
 
 def _sources():

@@ -231,6 +231,18 @@ int endo_tc_probe(const float* A, const float* B, float* D, int a_rows, int N, i
                   int a_mn_major, int b_mn_major, int swizzle, int reps, long long* cycles, int rotate,
                   endo_stream_t stream);   /* rotate > 1 (timing only): reps cycle over that many accumulator tiles */
 
+/* ------------------------------------------------------------------------------------------------
+ * utils.point_cloud_from_depth (utils.py:825-852; evaluate.py:337-341): depth map [H,W] + BGR uint8 image [H,W,3] + mask [H,W]
+ * -> points[N][6] = (x, y, z, r, g, b) of the pixels with h % downsampling == 0, w % downsampling == 0, mask > 0.5 (and, if
+ * use_threshold, max(r,g,b) >= max_threshold and min(r,g,b) <= min_threshold), in ROW-MAJOR order like the reference's loop;
+ * count[0] = N.  `points` must hold H*W rows.  x = (w - cx) / fx * z in fp32, the reference's operation order.
+ * ---------------------------------------------------------------------------------------------- */
+size_t endo_point_cloud_workspace_bytes(int H, int W);
+int endo_point_cloud_from_depth(const float* depth, const unsigned char* color_bgr, const float* mask, float fx, float fy,
+                                float cx, float cy, int H, int W, int downsampling, int use_threshold, float min_threshold,
+                                float max_threshold, float* points, int* count, void* ws, size_t ws_bytes,
+                                endo_stream_t stream);
+
 /* TMA bring-up probe (tests only): out[box_h][box_w][box_c] = the box of the NHWC fp32 buffer src[B][H][W][C] at channel c0,
  * column x0, row y0 (either may be negative or overhang: zero fill) of image b, loaded by one cp.async.bulk.tensor. */
 int endo_tma_probe(const float* src, int B, int H, int W, int C, int box_c, int box_w, int box_h, int c0, int x0,

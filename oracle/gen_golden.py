@@ -35,7 +35,41 @@ def np32(t):
     return t.detach().cpu().numpy().astype(np.float32)
 
 
+def reference_function(name, path=REF + "/utils.py"):
+    """Execute ONE function of a reference file that cannot be imported as a module here (utils.py needs plyfile /
+    matplotlib): its FunctionDef is cut out of the unmodified source with `ast` and run against numpy."""
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def record_export():
+    """utils.point_cloud_from_depth (utils.py:825-852) on a seeded 48 x 64 case, with and without the colour thresholds."""
+    fn = reference_function("point_cloud_from_depth")
+    rs = np.random.RandomState(77)
+    h, w = 48, 64
+    depth = (0.3 + 1.2 * rs.rand(h, w)).astype(np.float32)
+    color = rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    mask = (((yy - h / 2) ** 2 + (xx - w / 2) ** 2) < (0.45 * w) ** 2).astype(np.float32)
+    k = np.array([[677.171 / 8, 0, w / 2.0], [0, 677.171 / 8, h / 2.0], [0, 0, 1]], dtype=np.float32)
+    out = dict(depth=depth, color=color, mask=mask, k=k)
+    out["pc_all"] = fn(depth, color, mask, k, 1)
+    out["pc_ds2"] = fn(depth, color, mask, k, 2)
+    out["pc_thr"] = fn(depth, color, mask, k, 1, min_threshold=60, max_threshold=200)
+    np.savez_compressed(os.path.join(OUT, "export_a.npz"), **out)
+    print("export_a", {k_: v.shape for k_, v in out.items()})
+
+
 def main(only=None):
+    if only and "export_a" in only:
+        record_export()
+        only = [t for t in only if t != "export_a"]
+        if not only:
+            return
     if only:                                    # regenerate selected step fixtures only: python -m oracle.gen_golden step_d
         ref_models, ref_losses = load_reference()
         torch.set_num_threads(8)
@@ -139,6 +173,7 @@ def main(only=None):
     np.savez_compressed(os.path.join(OUT, "net_a.npz"), meta=np.array([b, h, w, seed]), **out)
     print("net_a", y.shape, float(y.mean()))
 
+    record_export()
     # ---------------------------------------------------------------- one full train step (train.py:272-328)
     record_step(ref_models, ref_losses, "step_a", 2, 64, 64, 404, perturb=False, conditioned=False)
     # well-conditioned variants (oracle.net.condition_state): the bounds that matter -- 1e-4 on every loss term

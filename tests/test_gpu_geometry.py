@@ -23,7 +23,8 @@ def _cuda(batch):
     return {k: v.cuda() for k, v in batch.items()}
 
 
-CASES = [(2, 64, 96, 101, False), (3, 32, 64, 202, True), (1, 37, 53, 5, False), (8, 256, 320, 10085, False)]
+CASES = [(2, 64, 96, 101, False), (3, 32, 64, 202, True), (1, 37, 53, 5, False), (8, 256, 320, 10085, False),
+         (2, 512, 640, 50085, False)]          # the last one: BASELINE config 5 resolution (downsampling 2.0)
 
 
 def _mask_mismatch(got, ref, margin_values, thr, tol=1e-5):

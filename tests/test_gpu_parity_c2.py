@@ -330,3 +330,27 @@ def test_successive_graphed_steps_in_one_process():
         torch.cuda.empty_cache()
     assert abs(losses[0][0] - g["loss"][0]) / g["loss"][0] < LOSS_TOL and abs(losses[0][1] - g["loss"][1]) / g["loss"][1] < LOSS_TOL
     assert abs(losses[1][0] - losses[0][0]) < 1e-5 and abs(losses[1][1] - losses[0][1]) < 1e-5, losses
+
+
+@pytest.mark.parametrize("math_mode", ["tf32x3"])
+def test_config5_network_forward_512x640(math_mode):
+    """BASELINE config 5 resolution (512x640, downsampling 2.0): forward of the pair network against the fp32 CPU oracle
+    (the persistent TMA-fed kernels then run levels 0-2, 5,120 tiles per image pair at level 0)."""
+    cfg = onet.FCDENSENET57
+    b, h, w, seed = 1, 512, 640, 50085
+    state = onet.condition_state(onet.init_state(cfg, seed=seed, perturb=True))
+    batch = endo_b200.synthetic.make_batch(b, h, w, seed=seed)
+    x1 = batch["boundaries"] * batch["colors_1"]
+    x2 = batch["boundaries"] * batch["colors_2"]
+    with torch.no_grad():
+        y1_ref = onet.forward(state, x1, cfg, True, {})
+        y2_ref = onet.forward(state, x2, cfg, True, {})
+    model = endo_b200.models.FCDenseNet57(n_classes=1, math=math_mode)
+    model.load_state_dict(state)
+    model.cuda().train()
+    p1, p2 = model.forward_pair(x1.cuda(), x2.cuda())
+    e1, e2 = rel_err(p1, y1_ref), rel_err(p2, y2_ref)
+    print(f"{math_mode} forward_pair 512x640 vs fp32 oracle: {e1:.2e} {e2:.2e}")
+    assert e1 < DEPTH_TOL and e2 < DEPTH_TOL
+    (p1.sum() + p2.sum()).backward()
+    assert bool(torch.isfinite(model.flat_grads).all())
