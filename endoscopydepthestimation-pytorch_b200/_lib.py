@@ -62,6 +62,8 @@ _SIGNATURES = {
     "endo_point_cloud_workspace_bytes": (c_size_t, [c_int, c_int]),
     "endo_point_cloud_from_depth": (c_int, [_P, _P, _P, c_float, c_float, c_float, c_float, c_int, c_int, c_int, c_int, c_float,
                                             c_float, _P, _P, _P, c_size_t, _P]),
+    "endo_rasterize_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "endo_rasterize_pair": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "endo_tma_probe": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "endo_sgd_workspace_bytes": (c_size_t, [c_longlong]),
     "endo_sgd_clip_step": (c_int, [_P, _P, _P, c_longlong, c_float, c_float, c_float, c_int, _P, _P, _P, c_size_t,

@@ -107,3 +107,104 @@ extern "C" int endo_point_cloud_from_depth(const float* depth, const unsigned ch
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
+
+// =====================================================================================================
+// Sparse SfM rasteriser (reference utils.get_torch_training_data, utils.py:460-612): the step BEFORE the hot path.
+// Projects the M (a few hundred) SfM points of a sequence into the two views of a pair and scatters the sparse depth,
+// depth-mask, flow and flow-mask images the loss stack consumes; the reference does it with numpy on the CPU per sample
+// and the DataLoader then copies ten H x W images to the GPU (train.py:255-270).  Here the images are produced on the
+// device.  Semantics kept exactly: float64 projection, np.round (half to even), `a[idx] = v` with duplicate indices =
+// the LAST point (in point order) wins, flow normalised in float32, |flow| > 5 outliers cleared (utils.py:567-574).
+// =====================================================================================================
+namespace endo {
+
+struct RasterArgs {
+    const double* pts;            // [M][4] homogeneous points
+    const double* P;              // [2][3][4] projection matrices of the two views
+    const double* E;              // [2][4][4] extrinsic matrices
+    const float* vis;             // [2][M] visibility of each point in each view (> 0.5 = visible)
+    const float* clean;           // [M] inlier flags or nullptr (utils.py:505-508)
+    const unsigned char* mask;    // [H][W] boundary mask, 255 = inside
+    int M, H, W;
+    int* winner;                  // [2][H*W], -1 = empty
+    double* uvz;                  // [2][M][3] rounded pixel position (u, v) and camera-space depth
+    float* depth_mask; float* depth; float* flow_mask; float* flow;    // [2][H][W][1|2] like the reference's return values
+};
+
+__global__ void raster_project_kernel(const RasterArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * A.M) return;
+    const int view = i / A.M, m = i - view * A.M;
+    const double* X = A.pts + (size_t)m * 4;
+    const double* P = A.P + view * 12;
+    const double* E = A.E + view * 16;
+    double p[3], c[4];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) p[r] = ((P[r * 4] * X[0] + P[r * 4 + 1] * X[1]) + P[r * 4 + 2] * X[2]) + P[r * 4 + 3] * X[3];   // einsum order (:483)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) c[r] = ((E[r * 4] * X[0] + E[r * 4 + 1] * X[1]) + E[r * 4 + 2] * X[2]) + E[r * 4 + 3] * X[3];
+    const double u = rint(p[0] / p[2]), v = rint(p[1] / p[2]);      // np.round: half to even (:484)
+    const double z = c[2] / c[3];                                   // :486
+    double* o = A.uvz + ((size_t)view * A.M + m) * 3;
+    o[0] = u; o[1] = v; o[2] = z;
+    const bool visible = A.vis[(size_t)view * A.M + m] > 0.5f && (!A.clean || A.clean[m] > 0.5f);      // :503-515
+    if (visible && u <= (double)(A.W - 1) && u >= 0.0 && v <= (double)(A.H - 1) && v >= 0.0 && z > 0.0) {   // :521-525
+        const int loc = (int)(u + v * (double)A.W);                 // :527-529
+        if (A.mask[loc] == 255) atomicMax(A.winner + (size_t)view * A.H * A.W + loc, m);   // :530-533; last point wins
+    }
+}
+
+__global__ void raster_write_kernel(const RasterArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * A.M) return;
+    const int view = i / A.M, m = i - view * A.M;
+    const double* mine = A.uvz + ((size_t)view * A.M + m) * 3;
+    const double* other = A.uvz + ((size_t)(1 - view) * A.M + m) * 3;
+    const double u = mine[0], v = mine[1], z = mine[2];
+    const bool visible = A.vis[(size_t)view * A.M + m] > 0.5f && (!A.clean || A.clean[m] > 0.5f);
+    if (!(visible && u <= (double)(A.W - 1) && u >= 0.0 && v <= (double)(A.H - 1) && v >= 0.0 && z > 0.0)) return;
+    const int loc = (int)(u + v * (double)A.W);
+    const size_t img = (size_t)view * A.H * A.W;
+    if (A.mask[loc] != 255 || A.winner[img + loc] != m) return;
+    // flow = position in the other view - position in this view (:548-557), stored as float32, then normalised (:559-562)
+    float fx = (float)(other[0] - u), fy = (float)(other[1] - v);
+    fx = fx / (float)A.W; fy = fy / (float)A.H;
+    const bool outlier = fabsf(fx) > 5.0f || fabsf(fy) > 5.0f;      // :564-574
+    A.flow[(img + loc) * 2] = outlier ? 0.f : fx;
+    A.flow[(img + loc) * 2 + 1] = outlier ? 0.f : fy;
+    A.flow_mask[img + loc] = outlier ? 0.f : 1.f;
+    A.depth[img + loc] = (float)z;                                  // :585-590
+    A.depth_mask[img + loc] = 1.f;
+}
+
+}  // namespace endo
+
+extern "C" size_t endo_rasterize_workspace_bytes(int M, int H, int W) {
+    if (M < 0 || H <= 0 || W <= 0) return 0;
+    return sizeof(int) * 2 * (size_t)H * W + sizeof(double) * 6 * (size_t)(M > 0 ? M : 1) + 64;
+}
+
+extern "C" int endo_rasterize_pair(const double* points, const double* projections, const double* extrinsics, const float* visibility,
+                                   const float* clean, const unsigned char* mask_boundary, int M, int H, int W, float* depth_mask,
+                                   float* depth, float* flow_mask, float* flow, void* ws, size_t ws_bytes, endo_stream_t stream) {
+    if (M < 0 || H <= 0 || W <= 0) return ENDO_ERR_BAD_SHAPE;
+    if (!projections || !extrinsics || !mask_boundary || !depth_mask || !depth || !flow_mask || !flow || (M > 0 && (!points || !visibility)))
+        return ENDO_ERR_BAD_POINTER;
+    if (!ws || ws_bytes < endo_rasterize_workspace_bytes(M, H, W) || (reinterpret_cast<uintptr_t>(ws) & 7u)) return ENDO_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t hw = (size_t)H * W;
+    endo::RasterArgs A{points, projections, extrinsics, visibility, clean, mask_boundary, M, H, W,
+                       nullptr, reinterpret_cast<double*>(ws), depth_mask, depth, flow_mask, flow};
+    A.winner = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + sizeof(double) * 6 * (size_t)(M > 0 ? M : 1));
+    ENDO_CUDA(cudaMemsetAsync(A.winner, 0xff, sizeof(int) * 2 * hw, s));
+    ENDO_CUDA(cudaMemsetAsync(depth_mask, 0, sizeof(float) * 2 * hw, s));
+    ENDO_CUDA(cudaMemsetAsync(depth, 0, sizeof(float) * 2 * hw, s));
+    ENDO_CUDA(cudaMemsetAsync(flow_mask, 0, sizeof(float) * 2 * hw, s));
+    ENDO_CUDA(cudaMemsetAsync(flow, 0, sizeof(float) * 4 * hw, s));
+    if (M == 0) return ENDO_OK;
+    endo::raster_project_kernel<<<endo::cdiv(2 * M, 256), 256, 0, s>>>(A);
+    ENDO_CHECK_LAUNCH();
+    endo::raster_write_kernel<<<endo::cdiv(2 * M, 256), 256, 0, s>>>(A);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}

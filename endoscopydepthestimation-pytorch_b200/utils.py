@@ -41,3 +41,41 @@ def point_cloud_from_depth(depth_map, color_img, mask_img, intrinsic_matrix, poi
                 "point_cloud_from_depth")
     out = points[: int(count.item())]
     return out if return_tensor else out.cpu().numpy()
+
+
+def get_torch_training_data(pair_extrinsics, pair_projections, pair_indexes, point_cloud, mask_boundary,
+                            view_indexes_per_point, clean_point_list, visible_view_indexes, device=None, return_tensor=False):
+    """`utils.get_torch_training_data` (utils.py:460-612) on the GPU: same arguments, same four return values
+    (pair_depth_mask_imgs [2,H,W,1], pair_depth_imgs [2,H,W,1], pair_flow_mask_imgs [2,H,W,1], pair_flow_imgs [2,H,W,2],
+    float32).  With `return_tensor=True` they stay on the device (the DataLoader's ten H2D image copies per pair,
+    train.py:255-270, disappear)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("endo_b200.utils.get_torch_training_data runs on a CUDA device only (there is no CPU fallback)")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    mask_np = np.asarray(mask_boundary)
+    h, w = mask_np.shape[0], mask_np.shape[1]
+    pts = np.asarray(point_cloud, dtype=np.float64).reshape((-1, 4))
+    m = pts.shape[0]
+    vis = np.asarray(view_indexes_per_point)
+    cols = [visible_view_indexes.index(pair_indexes[0]), visible_view_indexes.index(pair_indexes[1])]     # utils.py:501, 509
+    vis2 = np.stack([np.asarray(vis[:, c]).reshape(-1) for c in cols]).astype(np.float32)
+    clean = None if len(clean_point_list) == 0 else np.asarray(clean_point_list, dtype=np.float32).reshape(-1)
+    proj = np.stack([np.asarray(p, dtype=np.float64).reshape(3, 4) for p in pair_projections[:2]])
+    extr = np.stack([np.asarray(e, dtype=np.float64).reshape(4, 4) for e in pair_extrinsics[:2]])
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
+    d_pts, d_proj, d_extr, d_vis = t(pts, torch.float64), t(proj, torch.float64), t(extr, torch.float64), t(vis2, torch.float32)
+    d_clean = None if clean is None else t(clean, torch.float32)
+    d_mask = t(mask_np.reshape(h, w), torch.uint8)
+    depth_mask = torch.empty((2, h, w, 1), dtype=torch.float32, device=device)
+    depth = torch.empty((2, h, w, 1), dtype=torch.float32, device=device)
+    flow_mask = torch.empty((2, h, w, 1), dtype=torch.float32, device=device)
+    flow = torch.empty((2, h, w, 2), dtype=torch.float32, device=device)
+    lib = L.lib()
+    ws = torch.empty(lib.endo_rasterize_workspace_bytes(m, h, w), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        L.check(lib.endo_rasterize_pair(d_pts.data_ptr(), d_proj.data_ptr(), d_extr.data_ptr(), d_vis.data_ptr(), L.ptr(d_clean),
+                                        d_mask.data_ptr(), m, h, w, depth_mask.data_ptr(), depth.data_ptr(), flow_mask.data_ptr(),
+                                        flow.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(device)), "rasterize_pair")
+    out = (depth_mask, depth, flow_mask, flow)
+    return out if return_tensor else tuple(o.cpu().numpy() for o in out)

@@ -243,6 +243,18 @@ int endo_point_cloud_from_depth(const float* depth, const unsigned char* color_b
                                 float max_threshold, float* points, int* count, void* ws, size_t ws_bytes,
                                 endo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * utils.get_torch_training_data (utils.py:460-612): sparse SfM rasteriser of one image pair.  points[M][4] homogeneous
+ * (double), projections[2][3][4], extrinsics[2][4][4] (double), visibility[2][M] (the two columns of view_indexes_per_point,
+ * > 0.5 = visible), clean[M] or NULL, mask_boundary[H][W] uint8 (255 = inside) -> the four pairs of images the reference
+ * returns: depth_mask[2][H][W], depth[2][H][W], flow_mask[2][H][W], flow[2][H][W][2].  float64 projection, np.round,
+ * last-point-wins scatter, float32 flow normalisation and the |flow| > 5 outlier rule exactly as in the reference.
+ * ---------------------------------------------------------------------------------------------- */
+size_t endo_rasterize_workspace_bytes(int M, int H, int W);
+int endo_rasterize_pair(const double* points, const double* projections, const double* extrinsics, const float* visibility,
+                        const float* clean, const unsigned char* mask_boundary, int M, int H, int W, float* depth_mask,
+                        float* depth, float* flow_mask, float* flow, void* ws, size_t ws_bytes, endo_stream_t stream);
+
 /* TMA bring-up probe (tests only): out[box_h][box_w][box_c] = the box of the NHWC fp32 buffer src[B][H][W][C] at channel c0,
  * column x0, row y0 (either may be negative or overhang: zero fill) of image b, loaded by one cp.async.bulk.tensor. */
 int endo_tma_probe(const float* src, int B, int H, int W, int C, int box_c, int box_w, int box_h, int c0, int x0,

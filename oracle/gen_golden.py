@@ -64,12 +64,28 @@ def record_export():
     print("export_a", {k_: v.shape for k_, v in out.items()})
 
 
+def record_raster():
+    """utils.get_torch_training_data (utils.py:460-612) on the seeded scene above, with and without the inlier list."""
+    fn = reference_function("get_torch_training_data")
+    from oracle.export import raster_scene
+    sc = raster_scene()
+    out = dict(sc)
+    args = ([sc["extr"][0], sc["extr"][1]], [sc["proj"][0], sc["proj"][1]], list(sc["pair_indexes"]), [list(p) for p in sc["pts"]],
+            sc["mask"], sc["vis"])
+    for tag, clean in (("clean", sc["clean"]), ("noclean", [])):
+        dm, d, fm, fl = fn(*args, clean, list(sc["visible_view_indexes"]))
+        out.update({f"{tag}_depth_mask": dm, f"{tag}_depth": d, f"{tag}_flow_mask": fm, f"{tag}_flow": fl})
+        print("raster_a", tag, "points drawn per view", dm.sum(axis=(1, 2, 3)), "flow points", fm.sum(axis=(1, 2, 3)))
+    np.savez_compressed(os.path.join(OUT, "raster_a.npz"), **out)
+
+
 def main(only=None):
-    if only and "export_a" in only:
-        record_export()
-        only = [t for t in only if t != "export_a"]
-        if not only:
-            return
+    for tag, rec in (("export_a", record_export), ("raster_a", record_raster)):
+        if only and tag in only:
+            rec()
+            only = [t for t in only if t != tag]
+            if not only:
+                return
     if only:                                    # regenerate selected step fixtures only: python -m oracle.gen_golden step_d
         ref_models, ref_losses = load_reference()
         torch.set_num_threads(8)

@@ -42,3 +42,64 @@ def test_cuda_point_cloud_is_bit_exact():
     assert np.array_equal(got, ref)
     with pytest.raises(RuntimeError):
         endo_b200.utils.point_cloud_from_depth(depth[:10], color, mask, k, 1)
+
+
+# ------------------------------------------------------------------ sparse rasteriser (utils.get_torch_training_data, utils.py:460-612)
+def _raster_args(g, clean):
+    return ([g["extr"][0], g["extr"][1]], [g["proj"][0], g["proj"][1]], list(g["pair_indexes"]), [list(p) for p in g["pts"]],
+            g["mask"], g["vis"], (g["clean"] if clean else []), list(g["visible_view_indexes"]))
+
+
+RASTER_KEYS = ("depth_mask", "depth", "flow_mask", "flow")
+
+
+def test_raster_fixture_exercises_duplicates_and_outliers():
+    g = load_golden("raster_a")
+    dm, fm = g["noclean_depth_mask"], g["noclean_flow_mask"]
+    assert fm.sum() < dm.sum()                                     # |flow| > 5 outliers were cleared (utils.py:564-574)
+    out = oexp.get_torch_training_data(*_raster_args(g, False))
+    # several points land on one pixel: more valid points than drawn pixels
+    uv = np.round((g["pts"] @ g["proj"][0].T) / (g["pts"] @ g["proj"][0].T)[:, 2:3])
+    loc = uv[:, 0] + uv[:, 1] * g["mask"].shape[1]
+    assert len(np.unique(loc)) < len(loc)
+    assert out[0].shape == dm.shape
+
+
+@pytest.mark.parametrize("clean", [True, False])
+def test_raster_oracle_matches_reference_fixture(clean):
+    g = load_golden("raster_a")
+    out = oexp.get_torch_training_data(*_raster_args(g, clean))
+    for key, o in zip(RASTER_KEYS, out):
+        want = g[("clean_" if clean else "noclean_") + key]
+        assert o.dtype == want.dtype and o.shape == want.shape
+        assert np.array_equal(o, want), key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clean", [True, False])
+def test_cuda_rasteriser_is_bit_exact(clean):
+    g = load_golden("raster_a")
+    out = endo_b200.utils.get_torch_training_data(*_raster_args(g, clean))
+    for key, o in zip(RASTER_KEYS, out):
+        want = g[("clean_" if clean else "noclean_") + key]
+        assert o.dtype == want.dtype and o.shape == want.shape
+        assert np.array_equal(o, want), key
+    dev = endo_b200.utils.get_torch_training_data(*_raster_args(g, clean), return_tensor=True)
+    assert all(t.is_cuda for t in dev)
+
+
+@pytest.mark.gpu
+def test_cuda_rasteriser_empty_point_cloud_and_larger_image():
+    g = load_golden("raster_a")
+    a = list(_raster_args(g, False))
+    a[3] = []
+    a[5] = np.zeros((0, g["vis"].shape[1]), np.float32)
+    out = endo_b200.utils.get_torch_training_data(*a)
+    assert all(float(np.abs(o).sum()) == 0.0 for o in out)
+    # a second, seeded 256 x 320 scene against the oracle
+    sc = oexp.raster_scene(seed=5, h=256, w=320, m=3000)
+    args = _raster_args(sc, True)
+    want = oexp.get_torch_training_data(*args)
+    got = endo_b200.utils.get_torch_training_data(*args)
+    for key, o, wnt in zip(RASTER_KEYS, got, want):
+        assert np.array_equal(o, wnt), key
