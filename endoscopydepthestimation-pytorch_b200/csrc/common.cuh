@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include "../../include/endo_b200.h"
 
 namespace endo {
@@ -52,6 +53,32 @@ struct ProfScope {
             endo_cfg_mask_ |= 1ull << endo_dev_;                                                           \
         }                                                                                                  \
     } while (0)
+
+// Programmatic dependent launch (griddepcontrol): a kernel launched through launch_pdl() may become resident while its
+// predecessor on the stream is still draining; it must run pdl_wait() BEFORE its first access to global memory (reads AND
+// writes: the predecessor may still be reading what this kernel overwrites) and may do on-chip set-up (barrier init, TMEM
+// allocation, descriptor prefetch) ahead of it.  pdl_trigger() at the top of a kernel lets ITS successor do the same as soon
+// as every CTA of this kernel has started.  ENDO_PDL=0 launches everything with full stream serialisation (A/B switch).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ENDO_PDL"); v = e ? (atoi(e) != 0) : 1; }
+    return v != 0;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -10,6 +10,7 @@
 #include "net_pw.cuh"
 #include "net_wgrad2.cuh"
 #include "net_fwd2.cuh"
+#include "net_pwwgrad.cuh"
 
 namespace endo {
 
@@ -23,7 +24,7 @@ static int launch_conv(const ConvArgs& a, cudaStream_t s) {
     dim3 grid(tiles, cdiv(a.N, CO), a.B);
     ProfScope prof(WM == WM_DGRAD ? ((LM == LM_GRADPOOL || EM == EM_DGRAD_UP) ? PC_DGRAD_TRANS : PC_DGRAD)
                                   : ((LM == LM_BNRELU && EM == EM_STORE) ? PC_CONV_DENSE_FWD : PC_CONV_TRANS_FWD), s);
-    kern<<<grid, NW * 32, smem, s>>>(a);
+    launch_pdl(kern, grid, NW * 32, smem, s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -38,7 +39,7 @@ static int launch_conv_pf(const ConvArgs& a, cudaStream_t s) {
     if (a.K > kMaxK) return ENDO_ERR_BAD_SHAPE;
     dim3 grid(cdiv(a.ow, 32) * cdiv(a.oh, 4 * PX), cdiv(a.N, CO), a.B);
     ProfScope prof(PC_CONV_DENSE_FWD, s);
-    kern<<<grid, 128, base + 16 * (size_t)a.K, s>>>(a);
+    launch_pdl(kern, grid, 128, base + 16 * (size_t)a.K, s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -50,7 +51,7 @@ static int launch_conv_splitk(const ConvArgs& a, cudaStream_t s) {
     ENDO_SET_MAX_SMEM(kern, (int)smem);
     dim3 grid(cdiv(a.ow, 32) * cdiv(a.oh, NW * PX), a.ksplit, a.B);
     ProfScope prof(PC_CONV_DENSE_FWD, s);
-    kern<<<grid, NW * 32, smem, s>>>(a);
+    launch_pdl(kern, grid, NW * 32, smem, s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -68,7 +69,7 @@ static int launch_wgrad(WgradArgs a, cudaStream_t s) {
     a.tiles_per_cta = cdiv(a.n_tiles, want);
     dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
     ProfScope prof((KS == 3 && LMA == LM_BNRELU) ? PC_WGRAD : PC_WGRAD_TRANS, s);
-    kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
+    launch_pdl(kern, grid, KS * NCG * NPS * 32, smem, s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -87,7 +88,7 @@ static int launch_wgrad2(WgradArgs a, cudaStream_t s) {
     a.tiles_per_cta = cdiv(a.n_tiles, want);
     dim3 grid(cdiv(a.n_tiles, a.tiles_per_cta), ychunks, zchunks);
     ProfScope prof((KS == 3 && LMA == LM_BNRELU) ? PC_WGRAD : PC_WGRAD_TRANS, s);
-    kern<<<grid, KS * NCG * NPS * 32, smem, s>>>(a);
+    launch_pdl(kern, grid, KS * NCG * NPS * 32, smem, s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -197,7 +198,7 @@ static int bn_prepare(const Ctx& c, const BnP& bn, int level, int ch_off) {
     a.C = bn.c; a.Ctot = c.P.Ctot[level]; a.ch_off = ch_off; a.G = c.P.G; a.training = c.training;
     a.count = c.count(level);
     ProfScope prof(PC_BN, c.s);
-    bn_prepare_kernel<<<cdiv(bn.c, 128), 128, 0, c.s>>>(a);
+    launch_pdl(bn_prepare_kernel, cdiv(bn.c, 128), 128, 0, c.s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -212,9 +213,9 @@ static int launch_pw(const tcpw::Args& a, int G, cudaStream_t s, int cat) {
     ENDO_SET_MAX_SMEM(tcpw::pw_gemm_kernel, 227 * 1024);
     const size_t smem = tcpw::smem_bytes(a.Npad, a.K, a.mode);
     if (smem > 227 * 1024) return ENDO_ERR_CONFIG;
-    dim3 grid(cdiv(a.per_group, tcpw::MT), G, 1);
+    dim3 grid(cdiv(a.per_group, a.mode == 2 ? tcpw::MT / 4 : tcpw::MT), G, 1);
     ProfScope prof(cat, s);
-    tcpw::pw_gemm_kernel<<<grid, tcpw::NTHREADS, smem, s>>>(a);
+    launch_pdl(tcpw::pw_gemm_kernel, grid, tcpw::NTHREADS, smem, s, a);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -241,7 +242,7 @@ static int pack_all(const Ctx& c, bool bwd, int per, int mode, K kern, unsigned 
     auto flush = [&]() -> int {
         if (T.n == 0) return ENDO_OK;
         ProfScope prof(PC_BN, c.s);
-        kern<<<T.total_chunks, 256, 0, c.s>>>(c.params, region, T);
+        launch_pdl(kern, T.total_chunks, 256, 0, c.s, c.params, region, T);
         ENDO_CHECK_LAUNCH();
         T.n = 0; T.total_chunks = 0;
         return ENDO_OK;
@@ -306,7 +307,7 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
                     return ENDO_ERR_CUDA;
                 ENDO_SET_MAX_SMEM(tcfwd2::dense_fwd_x3_persistent_kernel, tcfwd2::SMEM_BYTES);
                 ProfScope prof(PC_CONV_DENSE_FWD, c.s);
-                tcfwd2::dense_fwd_x3_persistent_kernel<<<n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s>>>(f, in_map, out_map);
+                launch_pdl(tcfwd2::dense_fwd_x3_persistent_kernel, n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s, f, in_map, out_map);
                 ENDO_CHECK_LAUNCH();
                 return ENDO_OK;
             }
@@ -332,13 +333,13 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
         if (ksplit > 1) { t.partial = reinterpret_cast<float*>(c.acts + P.tdtmp_off); t.ksplit = ksplit; }
         dim3 grid(cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH), ksplit, t.B);
         ProfScope prof(PC_CONV_DENSE_FWD, c.s);
-        tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(t);
+        launch_pdl(tcconv::dense_fwd_tf32_kernel, grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s, t);
         ENDO_CHECK_LAUNCH();
         if (ksplit > 1) {
             const int per_group = (int)(pixels / t.G);
             int fblocks = cdiv(per_group, 64);
             if (fblocks > 4 * kNumSMs) fblocks = 4 * kNumSMs;
-            splitk_finish_kernel<16><<<dim3(fblocks, t.G), 256, 0, c.s>>>(t.partial, t.bias, t.out, t.stats, ksplit, pixels, per_group,
+            launch_pdl(splitk_finish_kernel<16>, dim3(fblocks, t.G), 256, 0, c.s, t.partial, t.bias, t.out, t.stats, ksplit, pixels, per_group,
                                                                         t.N, t.out_C, t.out_off, t.stats_C);
             ENDO_CHECK_LAUNCH();
         }
@@ -362,12 +363,12 @@ static int dense_layer_fwd(const Ctx& c, const DenseLayerP& d) {
             if (d.conv.cout == 12) {
                 ENDO_TRY((launch_conv_splitk<3, 2, 12, 4, LM_BNRELU>(a, c.s)));
                 ProfScope prof(PC_CONV_DENSE_FWD, c.s);
-                splitk_finish_kernel<12><<<dim3(fblocks, a.G), 256, 0, c.s>>>(a.partial, a.bias, a.out, a.stats, ksplit, pixels, per_group,
+                launch_pdl(splitk_finish_kernel<12>, dim3(fblocks, a.G), 256, 0, c.s, a.partial, a.bias, a.out, a.stats, ksplit, pixels, per_group,
                                                                             a.N, a.out_C, a.out_off, a.stats_C);
             } else {
                 ENDO_TRY((launch_conv_splitk<3, 2, 16, 4, LM_BNRELU>(a, c.s)));
                 ProfScope prof(PC_CONV_DENSE_FWD, c.s);
-                splitk_finish_kernel<16><<<dim3(fblocks, a.G), 256, 0, c.s>>>(a.partial, a.bias, a.out, a.stats, ksplit, pixels, per_group,
+                launch_pdl(splitk_finish_kernel<16>, dim3(fblocks, a.G), 256, 0, c.s, a.partial, a.bias, a.out, a.stats, ksplit, pixels, per_group,
                                                                             a.N, a.out_C, a.out_off, a.stats_C);
             }
             ENDO_CHECK_LAUNCH();
@@ -413,7 +414,7 @@ static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
     if (smem > 227 * 1024) return ENDO_ERR_CONFIG;
     dim3 grid(cdiv(t.n_tiles, t.tiles_per_cta), yblocks, 1);
     ProfScope prof(cat, s);
-    tcwgrad2::dense_wgrad_tma_kernel<<<grid, tcwgrad2::NTHREADS, smem, s>>>(t, xmap);
+    launch_pdl(tcwgrad2::dense_wgrad_tma_kernel, grid, tcwgrad2::NTHREADS, smem, s, t, xmap);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -435,7 +436,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     if (tc_d) w.db = nullptr;
     if (tc_w && !tc_d) {
         ProfScope prof(PC_WGRAD, c.sw);
-        bias_grad_kernel<<<kNumSMs, 256, 0, c.sw>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + d.conv.b, P.Ctot[l], d.out_off, d.conv.cout,
+        launch_pdl(bias_grad_kernel, kNumSMs, 256, 0, c.sw, c.GX(l), c.X(l), c.AB(l), c.gparams + d.conv.b, P.Ctot[l], d.out_off, d.conv.cout,
                                                   (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
         ENDO_CHECK_LAUNCH();
     }
@@ -472,7 +473,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         const int ysplit = (tiles * t.B < 4 * kNumSMs && !(tc_disable_mask() & 128)) ? cdiv(t.Cin, tcdgrad::NC) : 1;
         dim3 grid(tiles, ysplit, t.B);
         ProfScope prof(PC_DGRAD, c.s);
-        tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(t);
+        launch_pdl(tcdgrad::dense_dgrad_tf32_kernel, grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s, t);
         ENDO_CHECK_LAUNCH();
     } else {
         // all 12 (16) output-gradient channels in ONE staging step (no padded K), 32 input channels per CTA so that two
@@ -485,7 +486,7 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     b.dgamma = c.gparams + d.bn.gamma; b.dbeta = c.gparams + d.bn.beta;
     b.C = d.cin; b.Ctot = P.Ctot[l]; b.ch_off = d.in_off; b.G = P.G; b.count = c.count(l);
     ProfScope prof(PC_BN, c.s);
-    bn_bwd_finalize_kernel<<<cdiv(d.cin, 128), 128, 0, c.s>>>(b);
+    launch_pdl(bn_bwd_finalize_kernel, cdiv(d.cin, 128), 128, 0, c.s, b);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -507,15 +508,21 @@ static int trans_down_fwd(const Ctx& c, int l) {
         float* tmp = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
         const int npad = (cs + 15) / 16 * 16;
         const bool pw = npad <= 512 && !(tc_disable_mask() & 512);
+        const bool fused_pool = pw && !(a.oh & 1) && !(a.ow & 1) && !(cs & 3) && !(tc_disable_mask() & 65536);
         if (pw) {
             // one GEMM over all output channels per 128-pixel tile (net_pw.cuh): the input is read once
             tcpw::Args q{};
             q.in = a.in; q.in_C = a.in_C; q.in_off = a.in_off; q.coef = a.coef; q.wpack = c.WPACK(); q.bias = a.bias;
             q.out = tmp; q.out_C = cs; q.out_off = 0; q.K = cs; q.N = cs; q.Npad = npad;
             q.per_group = (long long)(P.B / P.G) * a.oh * a.ow; q.mode = 0; q.x3 = x3_mode(c.math) == 1 || x3_mode(c.math) == 2;   // plain tf32 / bf16 modes: tf32 operands
+            if (fused_pool) {
+                // max-pool, argmax and statistics in the GEMM epilogue: the full-resolution conv output never reaches HBM
+                q.out = a.out; q.out_C = a.out_C; q.out_off = a.out_off; q.argmax_out = a.argmax_out; q.red = a.stats; q.red_C = a.stats_C;
+                q.H = a.oh; q.W = a.ow; q.per_group = (long long)(P.B / P.G) * (a.oh / 2) * (a.ow / 2); q.mode = 2;
+            }
             {
                 ProfScope prof(PC_BN, c.s);
-                tcpw::pack_w_pw_kernel<<<cdiv(cs, q.x3 ? 8 : 16), 256, 0, c.s>>>(a.w, cs, npad, q.x3, 0, c.WPACK());
+                launch_pdl(tcpw::pack_w_pw_kernel, cdiv(cs, q.x3 ? 8 : 16), 256, 0, c.s, a.w, cs, npad, q.x3, 0, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }
             ENDO_TRY(launch_pw(q, P.G, c.s, PC_CONV_TRANS_FWD));
@@ -528,23 +535,23 @@ static int trans_down_fwd(const Ctx& c, int l) {
             f.x3 = x3_mode(c.math); f.partial = nullptr; f.ksplit = 1; f.pixels = 0;
             {
                 ProfScope prof(PC_BN, c.s);
-                if (f.x3 == 1) tcconv::pack_w_1x1_x3_kernel<<<cdiv(cs, 8), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
-                else if (f.x3 >= 2) tcconv::pack_w_1x1_b3_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, reinterpret_cast<uint32_t*>(c.WPACK()));
-                else tcconv::pack_w_1x1_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(a.w, cs, cs, co0, c.WPACK());
+                if (f.x3 == 1) launch_pdl(tcconv::pack_w_1x1_x3_kernel, cdiv(cs, 8), 256, 0, c.s, a.w, cs, cs, co0, c.WPACK());
+                else if (f.x3 >= 2) launch_pdl(tcconv::pack_w_1x1_b3_kernel, cdiv(cs, 16), 256, 0, c.s, a.w, cs, cs, co0, reinterpret_cast<uint32_t*>(c.WPACK()));
+                else launch_pdl(tcconv::pack_w_1x1_kernel, cdiv(cs, 16), 256, 0, c.s, a.w, cs, cs, co0, c.WPACK());
                 ENDO_CHECK_LAUNCH();
             }
             dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
             ProfScope prof(PC_CONV_TRANS_FWD, c.s);
-            tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(f);
+            launch_pdl(tcconv::dense_fwd_tf32_kernel, grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s, f);
             ENDO_CHECK_LAUNCH();
         }
-        {
+        if (!fused_pool) {
             const long long pixels = (long long)(P.B / P.G) * (a.oh / 2) * (a.ow / 2);
             int blocks = (int)((pixels + 7) / 8);
             if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
             if (blocks < 1) blocks = 1;
             ProfScope prof(PC_CONV_TRANS_FWD, c.s);
-            tcconv::td_pool_kernel<<<dim3(blocks, P.G), 256, sizeof(float) * 16 * cs, c.s>>>(tmp, a.out, a.argmax_out, a.stats, P.B, a.oh, a.ow, cs,
+            launch_pdl(tcconv::td_pool_kernel, dim3(blocks, P.G), 256, sizeof(float) * 16 * cs, c.s, tmp, a.out, a.argmax_out, a.stats, P.B, a.oh, a.ow, cs,
                                                                                           a.out_C, a.out_off, P.G, a.stats_C);
             ENDO_CHECK_LAUNCH();
         }
@@ -564,13 +571,18 @@ static int trans_down_bwd(const Ctx& c, int l) {
     w.g_off = P.offIn[l + 1]; w.g_K = cs; w.g_h = P.h[l + 1]; w.g_w = P.w[l + 1];
     w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + t.conv.w; w.db = c.gparams + t.conv.b; w.w_cin = cs;
-    ENDO_TRY(c.fork());
-    if (is_tc(c.math) && !(tc_disable_mask() & 32)) {
+    const int npad = (cs + 15) / 16 * 16;
+    const bool dgrad_pw = is_tc(c.math) && npad <= 512 && !(tc_disable_mask() & 1024);
+    // weight gradient as one C x C GEMM over the bf16 by-products of the data-gradient kernel (net_pwwgrad.cuh): runs AFTER it
+    const bool wgrad_gemm = dgrad_pw && !(cs & 15) && !(tc_disable_mask() & 32) && !(tc_disable_mask() & 131072);
+    if (!wgrad_gemm) ENDO_TRY(c.fork());
+    if (wgrad_gemm) {
+    } else if (is_tc(c.math) && !(tc_disable_mask() & 32)) {
         // tcgen05 (bf16): the weight-gradient kernel in 1x1 mode, 48 output channels per launch; bias gradient = sum of the
         // routed (= of the pooled) gradient, reduced over the coarse buffer
         {
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
-            bias_grad_kernel<<<dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.sw>>>(c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
+            launch_pdl(bias_grad_kernel, dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.sw, c.GX(l + 1), c.X(l + 1), c.AB(l + 1), c.gparams + t.conv.b,
                                                                              P.Ctot[l + 1], P.offIn[l + 1], cs,
                                                                              (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
             ENDO_CHECK_LAUNCH();
@@ -595,8 +607,7 @@ static int trans_down_bwd(const Ctx& c, int l) {
     a.out = c.GX(l); a.out_C = P.Ctot[l]; a.out_off = P.offIn[l]; a.N = cs; a.oh = P.h[l]; a.ow = P.w[l];
     a.stats = c.BNRED(); a.stats_C = P.maxC;
     a.x = c.X(l); a.ep_coef = c.COEF(t.bn);
-    const int npad = (cs + 15) / 16 * 16;
-    if (is_tc(c.math) && npad <= 512 && !(tc_disable_mask() & 1024)) {
+    if (dgrad_pw) {
         // tcgen05 (tf32): routed-gradient GEMM over all input channels per 128-pixel tile, BN-backward epilogue (net_pw.cuh)
         tcpw::Args q{};
         q.argmax = am; q.gc = c.GX(l + 1); q.xc = c.X(l + 1); q.abc = c.AB(l + 1); q.cC = P.Ctot[l + 1]; q.c_off = P.offIn[l + 1];
@@ -604,21 +615,62 @@ static int trans_down_bwd(const Ctx& c, int l) {
         q.out = c.GX(l); q.out_C = P.Ctot[l]; q.out_off = P.offIn[l]; q.x = c.X(l); q.ep_coef = c.COEF(t.bn);
         q.red = c.BNRED(); q.red_C = P.maxC; q.K = cs; q.N = cs; q.Npad = npad;
         q.per_group = (long long)(P.B / P.G) * P.h[l] * P.w[l]; q.mode = 1; q.x3 = 0;
+        if (wgrad_gemm) {
+            q.r16 = reinterpret_cast<unsigned short*>(c.scratch + t.r16);
+            q.a16 = reinterpret_cast<unsigned short*>(c.scratch + t.a16);
+        }
         {
             ProfScope prof(PC_BN, c.s);
-            tcpw::pack_w_pw_kernel<<<cdiv(cs, 16), 256, 0, c.s>>>(t.conv.w + c.params, cs, npad, 0, 1, c.WPACK_BWD());
+            launch_pdl(tcpw::pack_w_pw_kernel, cdiv(cs, 16), 256, 0, c.s, t.conv.w + c.params, cs, npad, 0, 1, c.WPACK_BWD());
             ENDO_CHECK_LAUNCH();
         }
         ENDO_TRY(launch_pw(q, P.G, c.s, PC_DGRAD_TRANS));
     } else {
         ENDO_TRY((launch_conv<1, 2, 48, 8, LM_GRADPOOL, EM_DGRAD_BN, WM_DGRAD, false>(a, c.s)));
     }
+    if (wgrad_gemm) {
+        ENDO_TRY(c.fork());                                  // the by-products are complete: the GEMM overlaps what follows
+        {
+            ProfScope prof(PC_WGRAD_TRANS, c.sw);
+            launch_pdl(bias_grad_kernel, dim3(kNumSMs / 4, cdiv(cs, 16)), 256, 0, c.sw, c.GX(l + 1), c.X(l + 1), c.AB(l + 1),
+                       c.gparams + t.conv.b, P.Ctot[l + 1], P.offIn[l + 1], cs, (long long)(P.B / P.G) * P.h[l + 1] * P.w[l + 1], P.G);
+            ENDO_CHECK_LAUNCH();
+        }
+        tcpww::Args g{};
+        g.dw = c.gparams + t.conv.w; g.C = cs;
+        const int mblocks = (cs + 127) / 128;
+        int ny = 1;
+        g.Nper = cs;
+        while (mblocks * g.Nper > 512 || g.Nper > 256) { ++ny; g.Nper = (cdiv(cs, ny) + 15) / 16 * 16; }
+        g.sets = 512 / (mblocks * g.Nper);
+        if (g.sets > 4) g.sets = 4;
+        g.KT = 128;
+        if (tcpww::smem_bytes(cs, g.Nper, 128, 2) > (size_t)tcpww::SMEM_LIMIT) g.KT = 64;
+        g.nstages = 1;
+        while (g.nstages < tcpww::MAX_STAGES && tcpww::smem_bytes(cs, g.Nper, g.KT, g.nstages + 1) <= (size_t)tcpww::SMEM_LIMIT) ++g.nstages;
+        const size_t smem = tcpww::smem_bytes(cs, g.Nper, g.KT, g.nstages);
+        if (smem > (size_t)tcpww::SMEM_LIMIT) return ENDO_ERR_CONFIG;
+        const long long pix = (long long)P.B * P.h[l] * P.w[l];
+        g.n_tiles = cdiv(pix, g.KT);
+        int ctas = kNumSMs / ny;
+        if (ctas > g.n_tiles) ctas = g.n_tiles;
+        if (ctas < 1) ctas = 1;
+        g.tiles_per_cta = cdiv(g.n_tiles, ctas);
+        CUtensorMap amap, rmap;
+        if (!tcpww::make_planes_map(&amap, c.scratch + t.a16, pix, cs, g.KT, cs / 8) ||
+            !tcpww::make_planes_map(&rmap, c.scratch + t.r16, pix, cs, g.KT, g.Nper / 8))
+            return ENDO_ERR_CUDA;
+        ENDO_SET_MAX_SMEM(tcpww::pw_wgrad_kernel, tcpww::SMEM_LIMIT);
+        ProfScope prof(PC_WGRAD_TRANS, c.sw);
+        launch_pdl(tcpww::pw_wgrad_kernel, dim3(cdiv(g.n_tiles, g.tiles_per_cta), ny), tcpww::NTHREADS, smem, c.sw, g, amap, rmap);
+        ENDO_CHECK_LAUNCH();
+    }
     BnBwdArgs b;
     b.red = c.BNRED(); b.red_C = P.maxC; b.coef = c.COEF(t.bn); b.mi = c.MI(l); b.ab = c.AB(l);
     b.dgamma = c.gparams + t.bn.gamma; b.dbeta = c.gparams + t.bn.beta;
     b.C = cs; b.Ctot = P.Ctot[l]; b.ch_off = P.offIn[l]; b.G = P.G; b.count = c.count(l);
     ProfScope prof(PC_BN, c.s);
-    bn_bwd_finalize_kernel<<<cdiv(cs, 128), 128, 0, c.s>>>(b);
+    launch_pdl(bn_bwd_finalize_kernel, cdiv(cs, 128), 128, 0, c.s, b);
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
@@ -652,7 +704,7 @@ static int trans_up_fwd(const Ctx& c, int i) {
                 return ENDO_ERR_CUDA;
             ENDO_SET_MAX_SMEM(tcfwd2::dense_fwd_x3_persistent_kernel, tcfwd2::SMEM_BYTES);
             ProfScope prof(PC_CONV_TRANS_FWD, c.s);
-            tcfwd2::dense_fwd_x3_persistent_kernel<<<n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s>>>(f, in_map, out_map);
+            launch_pdl(tcfwd2::dense_fwd_x3_persistent_kernel, n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s, f, in_map, out_map);
             ENDO_CHECK_LAUNCH();
         }
         for (int co0 = 0; co0 < (use2 ? 0 : t.conv.cout); co0 += 16) {
@@ -665,7 +717,7 @@ static int trans_up_fwd(const Ctx& c, int i) {
             f.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + t.wp_off[co0 / 16]);    // packed by pack_dense_weights_fwd()
             dim3 grid(cdiv(f.W, tcconv::TW) * cdiv(f.H, tcconv::TH), 1, f.B);
             ProfScope prof(PC_CONV_TRANS_FWD, c.s);
-            tcconv::dense_fwd_tf32_kernel<<<grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s>>>(f);
+            launch_pdl(tcconv::dense_fwd_tf32_kernel, grid, tcconv::NTHREADS, tcconv::SMEM_BYTES, c.s, f);
             ENDO_CHECK_LAUNCH();
         }
         return ENDO_OK;
@@ -691,7 +743,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
         // the bias gradient comes from the small dedicated reduction
         if (!dgrad_tc) {                                  // otherwise the data-gradient passes below produce the bias gradient
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
-            bias_grad_kernel<<<dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.sw>>>(c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
+            launch_pdl(bias_grad_kernel, dim3(kNumSMs / 2, cdiv(t.conv.cout, 16)), 256, 0, c.sw, c.GX(l), c.X(l), c.AB(l), c.gparams + t.conv.b, P.Ctot[l], 0,
                                                                                        t.conv.cout, (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
             ENDO_CHECK_LAUNCH();
         }
@@ -725,14 +777,14 @@ static int trans_up_bwd(const Ctx& c, int i) {
             q.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + t.wpb_off[co0 / 16]);   // packed by pack_dense_weights_bwd()
             dim3 grid(cdiv(q.W, tcconv::TW) * cdiv(q.H, tcconv::TH), 1, q.B);
             ProfScope prof(PC_DGRAD_TRANS, c.s);
-            tcdgrad::dense_dgrad_tf32_kernel<<<grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s>>>(q);
+            launch_pdl(tcdgrad::dense_dgrad_tf32_kernel, grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s, q);
             ENDO_CHECK_LAUNCH();
         }
         const long long items = (long long)P.B * P.h[ls] * P.w[ls] * (t.cin / 4);
         int blocks = (int)((items + 255) / 256);
         if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
         ProfScope prof(PC_DGRAD_TRANS, c.s);
-        tcdgrad::up_sum_kernel<<<blocks, 256, 0, c.s>>>(tmp, t.cin, c.GX(ls), P.Ctot[ls], t.src_off, P.B, P.h[ls], P.w[ls], t.cin);
+        launch_pdl(tcdgrad::up_sum_kernel, blocks, 256, 0, c.s, tmp, t.cin, c.GX(ls), P.Ctot[ls], t.src_off, P.B, P.h[ls], P.w[ls], t.cin);
         ENDO_CHECK_LAUNCH();
         return ENDO_OK;
     }
@@ -814,7 +866,7 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
         const long long npix = (long long)B * H * W;
         float* pre = reinterpret_cast<float*>(c.acts + P.pre_off);
         ProfScope prof(PC_FINAL, c.s);
-        final_fwd_kernel<<<cdiv(npix * 8, 256), 256, 0, c.s>>>(c.X(0), params + P.final_.w, params + P.final_.b, pre, y,
+        launch_pdl(final_fwd_kernel, cdiv(npix * 8, 256), 256, 0, c.s, c.X(0), params + P.final_.w, params + P.final_.b, pre, y,
                                                                npix, P.Ctot[0]);
         ENDO_CHECK_LAUNCH();
     }
@@ -859,8 +911,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         const float* pre = reinterpret_cast<const float*>(c.acts + P.pre_off);
         const int ppc = (int)((npix + 2 * kNumSMs - 1) / (2 * kNumSMs));
         ProfScope prof(PC_FINAL, c.s);
-        final_bwd_kernel<<<cdiv(npix, ppc), 256, sizeof(float) * P.Ctot[0], c.s>>>(
-            g_y, pre, c.X(0), params + P.final_.w, c.GX(0), g_params + P.final_.w, g_params + P.final_.b, npix, P.Ctot[0], ppc);
+        launch_pdl(final_bwd_kernel, cdiv(npix, ppc), 256, sizeof(float) * P.Ctot[0], c.s, g_y, pre, c.X(0), params + P.final_.w, c.GX(0), g_params + P.final_.w, g_params + P.final_.b, npix, P.Ctot[0], ppc);
         ENDO_CHECK_LAUNCH();
     }
     if (is_tc(math)) ENDO_TRY(pack_dense_weights_bwd(c));
@@ -882,7 +933,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         ENDO_TRY(c.fork());
         if (cfg->in_channels == 3 && P.first.cout == 48 && !(tc_disable_mask() & 4096)) {
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
-            first_wgrad_kernel<<<4 * kNumSMs, FW_THREADS, 0, c.sw>>>(w);
+            launch_pdl(first_wgrad_kernel, 4 * kNumSMs, FW_THREADS, 0, c.sw, w);
             ENDO_CHECK_LAUNCH();
         } else {
             ENDO_TRY((launch_wgrad<3, 12, 4, 1, LM_NCHW, LM_GRAD, false>(w, c.sw)));

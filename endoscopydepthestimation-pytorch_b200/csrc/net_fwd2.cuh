@@ -101,9 +101,8 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
     const int per_img = A.tiles_x * A.tiles_y;
     const int per_group = A.B / A.G;
 
-    if (tid == 0 && (A.dbg & 16) && blockIdx.x == 0) { g_tc_trace[0] = nchunks; g_tc_trace[1] = clock64(); g_tc_trace[2] = my_tiles; }
+    pdl_trigger();
     if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
-    if (tid < 16) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;
     if (tid == 0) {
         for (int i = 0; i < NRAW; ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, NPROD); }
         for (int i = 0; i < 2; ++i) {
@@ -112,6 +111,10 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
         }
         tc::fence_mbar_init();
     }
+    if (warp == 17 && lane == 0) { tma::prefetch_map(&in_map); tma::prefetch_map(&out_map); }
+    pdl_wait();                                              // on-chip set-up above; global memory from here on
+    if (tid == 0 && (A.dbg & 16) && blockIdx.x == 0) { g_tc_trace[0] = nchunks; g_tc_trace[1] = clock64(); g_tc_trace[2] = my_tiles; }
+    if (tid < 16) s_bias[tid] = (tid < A.N) ? __ldg(A.bias + tid) : 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();

@@ -121,6 +121,7 @@ struct ConvTile {
 template <int KS, int PX, int CO, int NW, int LM, int EM, int WM, bool UP, int KCT = KC, int MINB = 1, bool PF = false>
 __global__ void __launch_bounds__(NW * 32, MINB)
 conv_kernel(const ConvArgs A) {
+    pdl_enter();
     using T = ConvTile<KS, PX, NW>;
     constexpr int PAD = T::PAD, TR = T::TR, TRP = T::TRP, TWP = T::TWP, PLANE = T::PLANE, TAPS = KS * KS;
     constexpr int NT = NW * 32;
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ partial, const float* __restrict__ bias, float* __restrict__ out,
                      double* __restrict__ stats, int ksplit, long long pixels, int per_group, int N, int out_C, int out_off,
                      int stats_C) {
+    pdl_enter();
     constexpr int NQ = CO / 4;
     __shared__ float red[8][CO][2];
     const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -559,6 +561,7 @@ struct WgradArgs {
 template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
 __global__ void __launch_bounds__(KS * NCG * NPS * 32)
 wgrad_kernel(const WgradArgs A) {
+    pdl_enter();
     constexpr int PAD = KS / 2, TR = 8, TRP = TR + 2 * PAD, TWP = 32 + 2 * PAD, COT = CW * NCG;
     constexpr int NT = KS * NCG * NPS * 32;
     extern __shared__ __align__(16) float smem[];
@@ -699,6 +702,7 @@ wgrad_kernel(const WgradArgs A) {
 template <int KS, int CW, int NCG, int NPS, int LMA, int LMG, bool UP>
 __global__ void __launch_bounds__(KS * NCG * NPS * 32)
 wgrad2_kernel(const WgradArgs A) {
+    pdl_enter();
     static_assert(LMA == LM_BNRELU || LMA == LM_PLAIN, "activation loader");
     static_assert(LMG == LM_GRAD || LMG == LM_GRADPOOL, "gradient loader");
     constexpr int PAD = KS / 2, TR = 8, TRP = TR + 2 * PAD, TWP = 32 + 2 * PAD, COT = CW * NCG;
@@ -903,6 +907,7 @@ struct BnPrepArgs {
 };
 
 __global__ void bn_prepare_kernel(const BnPrepArgs A) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= A.C) return;
     const float gam = A.gamma[c], bet = A.beta[c];
@@ -948,6 +953,7 @@ struct BnBwdArgs {
 };
 
 __global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= A.C) return;
     double dg = 0.0, db = 0.0;
@@ -977,6 +983,7 @@ __global__ void bn_bwd_finalize_kernel(const BnBwdArgs A) {
 constexpr int FW_STREAMS = 5, FW_THREADS = FW_STREAMS * 48, FW_ROWS = 4, FW_PX = FW_ROWS * 32, FW_PR = FW_ROWS + 2;
 __global__ void __launch_bounds__(FW_THREADS)
 first_wgrad_kernel(const WgradArgs A) {
+    pdl_enter();
     __shared__ __align__(16) float g_s[FW_PX * 48];
     __shared__ float in_s[3 * FW_PR * 34];
     const int tid = threadIdx.x;
@@ -1059,6 +1066,7 @@ first_wgrad_kernel(const WgradArgs A) {
 __global__ void __launch_bounds__(256)
 bias_grad_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ ab, float* __restrict__ db,
                  int C, int off, int Cout, long long npix_per_group, int G) {
+    pdl_enter();
     // blockIdx.y selects a group of 16 output channels
     off += 16 * blockIdx.y; db += 16 * blockIdx.y; Cout -= 16 * blockIdx.y;
     if (Cout > 16) Cout = 16;
@@ -1098,6 +1106,7 @@ bias_grad_kernel(const float* __restrict__ g, const float* __restrict__ x, const
 __global__ void __launch_bounds__(256)
 final_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ pre, float* __restrict__ y, long long npix, int C) {
+    pdl_enter();
     const int sub = threadIdx.x & 7;
     const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     float s = 0.f;
@@ -1124,6 +1133,7 @@ __global__ void __launch_bounds__(256)
 final_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ pre, const float* __restrict__ x,
                  const float* __restrict__ w, float* __restrict__ gx, float* __restrict__ dw, float* __restrict__ db,
                  long long npix, int C, int pix_per_cta) {
+    pdl_enter();
     extern __shared__ __align__(16) float sm[];     // [C] dW partial
     for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = 0.f;
     __syncthreads();

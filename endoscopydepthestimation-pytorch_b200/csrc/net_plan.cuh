@@ -30,7 +30,9 @@ struct ConvP { long long w, b; int cin, cout, ks; };           // offsets (float
 struct BnP { long long gamma, beta; long long rmean, rvar; int c; long long coef; };   // coef: float offset in acts
 struct DenseLayerP { BnP bn; ConvP conv; int level, in_off, cin, out_off;
                      long long wp_off, wpb_off; };   // byte offsets of this layer's tensor-core weight images inside the wpack / wpack_bwd regions
-struct TransDownP { BnP bn; ConvP conv; int level; long long argmax; };                 // argmax: byte offset in acts
+struct TransDownP { BnP bn; ConvP conv; int level; long long argmax;                    // argmax: byte offset in acts
+                    long long r16, a16; };      // byte offsets in the backward scratch: bf16 [B*h*w][C] routed gradient / relu(bn(x)),
+                                                // by-products of the data-gradient kernel, operands of the weight-gradient GEMM
 struct TransUpP { ConvP conv; int src_level, src_off, cin, dst_level;
                   long long wp_off[8], wpb_off[8]; };   // weight images of the 16-output-channel passes (cout <= 128)
 
@@ -200,6 +202,11 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
     P.acts_bytes = off;
     // ---- backward scratch block
     off = 0;
+    for (int l = 0; l < nd; ++l) {               // in FRONT of the gradient buffers: endo_net_bwd clears from gx_off[1] to the end
+        const long long n16 = 2ll * B * P.h[l] * P.w[l] * (P.C0[l] + P.Dn[l]);
+        P.td[l].r16 = off; off = align_up(off + n16, 256);
+        P.td[l].a16 = off; off = align_up(off + n16, 256);
+    }
     for (int l = 0; l <= nd; ++l) { P.gx_off[l] = off; off = align_up(off + 4ll * B * P.h[l] * P.w[l] * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.ab_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }
     P.bnred_off = off; off = align_up(off + 16ll * P.G * P.maxC, 256);

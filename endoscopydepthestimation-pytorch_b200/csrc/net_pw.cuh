@@ -39,6 +39,7 @@ constexpr int TB_BYTES = MT * TB_PITCH;
 // transposed = 0: B[n][k] = W[n][k] (forward, OIHW with 1x1 taps); 1: B[n][k] = W[k][n] (data gradient).
 __global__ void __launch_bounds__(256)
 pack_w_pw_kernel(const float* __restrict__ w, int C, int Npad, int x3, int transposed, float* __restrict__ out) {
+    pdl_enter();
     const int c = blockIdx.x;
     const int total = 4 * Npad * 4;
     for (int d = threadIdx.x; d < total; d += 256) {
@@ -68,7 +69,13 @@ struct Args {
     double* red; int red_C;                    // dgrad epilogue: [G][red_C][2] BN-backward sums
     int K, N, Npad;
     long long per_group;                       // pixels per statistic group (grid = tiles per group x groups)
-    int mode;                                  // 0 forward, 1 data gradient
+    int mode;                                  // 0 forward, 1 data gradient, 2 forward with the 2x2 max-pool fused into the epilogue:
+                                               // M rows = 32 pool windows x 4 positions, per_group counts COARSE pixels, out = next
+                                               // level buffer, argmax_out = window positions, red = its statistics [G][red_C][2]
+    unsigned char* argmax_out;
+    // mode 1 by-products (nullptr = off): bf16 [pixels][K] routed gradient (operand A as staged) and bf16 [pixels][N] relu(bn(x))
+    // (what the epilogue evaluates for the ReLU mask): the operands of the weight-gradient GEMM (net_pwwgrad.cuh)
+    unsigned short* r16; unsigned short* a16;
     int x3;
 };
 
@@ -98,21 +105,23 @@ pw_gemm_kernel(const Args A) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;                                 // statistic group: tiles never straddle two groups
-    const long long p0 = (long long)g * A.per_group + (long long)blockIdx.x * MT;
+    const long long p0 = (long long)g * A.per_group + (long long)blockIdx.x * (A.mode == 2 ? MT / 4 : MT);   // mode 2: coarse pixels
     const long long p_end = (long long)(g + 1) * A.per_group;
     const int kch = A.x3 ? 8 : 16;
     const int nchunks = (A.K + kch - 1) / kch;
     const uint32_t ncols = A.Npad <= 128 ? 128u : (A.Npad <= 256 ? 256u : 512u);
 
+    pdl_trigger();
     if (warp == 8) tc::tmem_alloc(tmem_slot, ncols);
     if (tid == 0) {
         for (int i = 0; i < NST; ++i) { tc::mbar_init(bars + i, 256); tc::mbar_init(bars + NST + i, 1); }
         tc::mbar_init(bars + 2 * NST, 1);
         tc::fence_mbar_init();
     }
+    pdl_wait();
     if (warp < 8) {
         // tables: operand-A coefficients and the bias / epilogue BatchNorm table
-        if (A.mode == 0) {
+        if (A.mode != 1) {
             for (int i = tid; i < A.K; i += 256)
                 *reinterpret_cast<float4*>(ktab + i * 4) = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)g * A.K + i) * 4));
             for (int i = tid; i < A.Npad; i += 256) ntab[i] = (i < A.N) ? __ldg(A.bias + i) : 0.f;
@@ -146,12 +155,19 @@ pw_gemm_kernel(const Args A) {
             const int i = tid + 256 * j;
             ipx[j] = A.x3 ? (tid >> 1) : (i >> 2);
             igrp[j] = A.x3 ? (tid & 1) : (i & 3);
-            const long long p = p0 + ipx[j];
+            const long long p = p0 + (A.mode == 2 ? (ipx[j] >> 2) : ipx[j]);
             iok[j] = p < p_end && j < nitem;
             ioff[j] = 0; ipos[j] = 0;
             if (iok[j]) {
                 if (A.mode == 0) ioff[j] = (size_t)p * A.in_C + A.in_off + igrp[j] * 4;
-                else {
+                else if (A.mode == 2) {
+                    // row = 4 * window + position: the four pixels of a pool window sit in four consecutive TMEM lanes
+                    const int wc = A.W >> 1, hc = A.H >> 1;
+                    const int x2 = (int)(p % wc), y2 = (int)((p / wc) % hc);
+                    const long long bq = p / ((long long)wc * hc);
+                    const int yq = 2 * y2 + ((ipx[j] >> 1) & 1), xq = 2 * x2 + (ipx[j] & 1);
+                    ioff[j] = (size_t)((bq * A.H + yq) * A.W + xq) * A.in_C + A.in_off + igrp[j] * 4;
+                } else {
                     const int xq = (int)(p % A.W), yq = (int)((p / A.W) % A.H);
                     const long long bq = p / ((long long)A.W * A.H);
                     ioff[j] = (size_t)((bq * (A.H >> 1) + (yq >> 1)) * (A.W >> 1) + (xq >> 1));   // coarse pixel index
@@ -169,7 +185,7 @@ pw_gemm_kernel(const Args A) {
                 if (j < nitem) {
                     const int ch = c * kch + igrp[j] * 4;
                     const bool ok = iok[j] && c < nchunks && ch < A.K;
-                    if (A.mode == 0) {
+                    if (A.mode != 1) {
                         qa[slot][j] = ok ? __ldg(reinterpret_cast<const float4*>(A.in + ioff[j] + c * kch)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     } else {
                         qa[slot & 1][j] = make_float4(0.f, 0.f, 0.f, 0.f); qx[slot & 1][j] = qa[slot & 1][j]; qm[slot & 1][j] = 0xffffffffu;
@@ -182,7 +198,7 @@ pw_gemm_kernel(const Args A) {
                 }
             }
         };
-        const int depth = A.mode == 0 ? NPF : 2;
+        const int depth = A.mode != 1 ? NPF : 2;
 #pragma unroll
         for (int u = 0; u < NPF; ++u)
             if (u < depth) issue(u, u);
@@ -209,7 +225,7 @@ pw_gemm_kernel(const Args A) {
                             const int ch = c * kch + igrp[j] * 4;
                             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (iok[j] && ch < A.K) {
-                                if (A.mode == 0) {
+                                if (A.mode != 1) {
                                     const float4 q = qa[u][j];
                                     const float4 k0 = *reinterpret_cast<const float4*>(ktab + (ch + 0) * 4), k1 = *reinterpret_cast<const float4*>(ktab + (ch + 1) * 4);
                                     const float4 k2 = *reinterpret_cast<const float4*>(ktab + (ch + 2) * 4), k3 = *reinterpret_cast<const float4*>(ktab + (ch + 3) * 4);
@@ -223,6 +239,9 @@ pw_gemm_kernel(const Args A) {
                                     v.y = (((am >> 8) & 0xffu) == pos) ? gq.y + fmaf(c0f.w, xq.y, c0f.z) : 0.f;
                                     v.z = (((am >> 16) & 0xffu) == pos) ? gq.z + fmaf(c1f.y, xq.z, c1f.x) : 0.f;
                                     v.w = ((am >> 24) == pos) ? gq.w + fmaf(c1f.w, xq.w, c1f.z) : 0.f;
+                                    if (A.r16)
+                                        *reinterpret_cast<uint2*>(A.r16 + (size_t)(p0 + ipx[j]) * A.K + ch) =
+                                            make_uint2(tcwgrad::pack_bf16(v.x, v.y), tcwgrad::pack_bf16(v.z, v.w));
                                 }
                             }
                             const float4 hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
@@ -233,7 +252,7 @@ pw_gemm_kernel(const Args A) {
                         }
                     }
                     // refill the ring slot just consumed
-                    if (A.mode == 0) issue(c + NPF, u); else issue(c + 2, u);
+                    if (A.mode != 1) issue(c + NPF, u); else issue(c + 2, u);
                     tc::cp_async_wait<0>();
                     tc::fence_proxy_async();
                     tc::mbar_arrive(bars + s);
@@ -285,6 +304,83 @@ pw_gemm_kernel(const Args A) {
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");           // tile reusable
             }
+        } else if (A.mode == 2) {
+            // forward with the max-pool fused: 64-channel column blocks, TMEM -> transposed shared tile (rows = 4 window + position)
+            // -> thread = (window, channel quad): bias, max / argmax over the four rows in ATen's scan order, pooled value and
+            // argmax word to the next level, statistics of the pooled map.  The full-resolution conv output never reaches HBM
+            // (the separate td_pool pass wrote and re-read it: 2 x 503 MB at the first TransitionDown of a 256x320 batch of 16).
+            unsigned char* tbf = smem;
+            float* red2 = reinterpret_cast<float*>(smem + TB_BYTES);          // [8 warps][64][2], behind the tile (the stages are idle)
+            const int quad = lane & 15, psub = lane >> 4;
+            for (int cb = 0; cb * 64 < A.Npad; ++cb) {
+                {
+                    const uint32_t taddr = tmem + lane_base + cb * 64 + hf * 32;
+                    unsigned char* row = tbf + (size_t)(q * 32 + lane) * TB_PITCH + hf * 128;
+                    float v[16];
+                    if (cb * 64 + hf * 32 < A.Npad) {
+                        tc::tmem_ld16(taddr, v);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(row + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (cb * 64 + hf * 32 + 16 < A.Npad) {
+                        tc::tmem_ld16(taddr + 16, v);
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(row + 64 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int n0 = cb * 64 + quad * 4;
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                if (n0 < A.N) {
+                    const float4 bq = *reinterpret_cast<const float4*>(ntab + n0);
+                    const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const int wl = warp * 4 + it * 2 + psub;               // pool window of this tile
+                        const long long cq = p0 + wl;                          // coarse pixel
+                        if (cq < p_end) {
+                            const unsigned char* r0 = tbf + (size_t)(4 * wl) * TB_PITCH + quad * 16;
+                            const float4 d0 = *reinterpret_cast<const float4*>(r0), d1 = *reinterpret_cast<const float4*>(r0 + TB_PITCH);
+                            const float4 d2 = *reinterpret_cast<const float4*>(r0 + 2 * TB_PITCH), d3 = *reinterpret_cast<const float4*>(r0 + 3 * TB_PITCH);
+                            const float a0[4] = {d0.x, d0.y, d0.z, d0.w}, a1[4] = {d1.x, d1.y, d1.z, d1.w};
+                            const float a2[4] = {d2.x, d2.y, d2.z, d2.w}, a3[4] = {d3.x, d3.y, d3.z, d3.w};
+                            float m[4]; unsigned am4 = 0;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float c0 = a0[e] + bb[e], c1 = a1[e] + bb[e], c2 = a2[e] + bb[e], c3 = a3[e] + bb[e];
+                                float mm = c0; unsigned am = 0;                  // ATen max_pool2d: (val > max) || isnan(val)
+                                if (c1 > mm || c1 != c1) { mm = c1; am = 1; }
+                                if (c2 > mm || c2 != c2) { mm = c2; am = 2; }
+                                if (c3 > mm || c3 != c3) { mm = c3; am = 3; }
+                                m[e] = mm; am4 |= am << (8 * e);
+                                s1[e] += mm; s2[e] += mm * mm;
+                            }
+                            *reinterpret_cast<float4*>(A.out + (size_t)cq * A.out_C + A.out_off + n0) = make_float4(m[0], m[1], m[2], m[3]);
+                            *reinterpret_cast<unsigned*>(A.argmax_out + (size_t)cq * A.N + n0) = am4;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                    s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
+                    if (psub == 0) {
+                        red2[(warp * 64 + quad * 4 + e) * 2] = s1[e];
+                        red2[(warp * 64 + quad * 4 + e) * 2 + 1] = s2[e];
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid < 128) {
+                    const int j = tid >> 1, which = tid & 1;
+                    if (cb * 64 + j < A.N) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int wq = 0; wq < 8; ++wq) sum += (double)red2[(wq * 64 + j) * 2 + which];
+                        atomicAdd(A.red + ((size_t)g * A.red_C + A.out_off + cb * 64 + j) * 2 + which, sum);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");           // tile / red2 reusable
+            }
         } else {
             // 64-channel column blocks: TMEM -> transposed shared tile -> lane = (pixel parity, channel quad): ReLU mask,
             // BN-backward sums (registers of the lane that owns the channel), scaled accumulate into the gradient buffer
@@ -334,10 +430,15 @@ pw_gemm_kernel(const Args A) {
                             const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)pl * TB_PITCH + quad * 16);
                             const float4 xq = xv[it];
                             const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
-                            const float g0 = fmaf(ca[0], e0, cbt[0]) > 0.f ? d.x : 0.f;
-                            const float g1 = fmaf(ca[1], e1, cbt[1]) > 0.f ? d.y : 0.f;
-                            const float g2 = fmaf(ca[2], e2, cbt[2]) > 0.f ? d.z : 0.f;
-                            const float g3 = fmaf(ca[3], e3, cbt[3]) > 0.f ? d.w : 0.f;
+                            const float y0 = fmaf(ca[0], e0, cbt[0]), y1 = fmaf(ca[1], e1, cbt[1]);
+                            const float y2 = fmaf(ca[2], e2, cbt[2]), y3 = fmaf(ca[3], e3, cbt[3]);
+                            const float g0 = y0 > 0.f ? d.x : 0.f;
+                            const float g1 = y1 > 0.f ? d.y : 0.f;
+                            const float g2 = y2 > 0.f ? d.z : 0.f;
+                            const float g3 = y3 > 0.f ? d.w : 0.f;
+                            if (A.a16)
+                                *reinterpret_cast<uint2*>(A.a16 + (size_t)(p0 + pl) * A.N + n0) =
+                                    make_uint2(tcwgrad::pack_bf16(fmaxf(y0, 0.f), fmaxf(y1, 0.f)), tcwgrad::pack_bf16(fmaxf(y2, 0.f), fmaxf(y3, 0.f)));
                             s1[0] += g0; s2[0] += g0 * (e0 * cs[0]);
                             s1[1] += g1; s2[1] += g1 * (e1 * cs[1]);
                             s1[2] += g2; s2[2] += g2 * (e2 * cs[2]);

@@ -93,6 +93,7 @@ __device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
 // against the activation planes [lo ; x] (the cross terms are 2^-12 of the product, so 8-bit operands keep them to 2^-21).
 __global__ void __launch_bounds__(256)
 pack_w_1x1_x3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* __restrict__ out) {
+    pdl_enter();
     const int c = blockIdx.x;
     for (int d = threadIdx.x; d < 768; d += 256) {
         const int part = d / 384, r = d - part * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
@@ -120,6 +121,7 @@ __device__ __forceinline__ uint32_t bf16_split(float lo, float hi, float& rlo, f
 }
 __global__ void __launch_bounds__(256)
 pack_w_1x1_b3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, uint32_t* __restrict__ out) {
+    pdl_enter();
     const int c = blockIdx.x;
     for (int d = threadIdx.x; d < 768; d += 256) {
         const int term = d / 384, r = d - term * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
@@ -136,6 +138,7 @@ pack_w_1x1_b3_kernel(const float* __restrict__ w, int K, int Ntot, int co0, uint
 // 1x1 convolution (TransitionDown): only blocks k8 = 0, 1 of the stage image are used, n = output channel co0 + n
 __global__ void __launch_bounds__(256)
 pack_w_1x1_kernel(const float* __restrict__ w, int K, int Ntot, int co0, float* __restrict__ out) {
+    pdl_enter();
     const int c = blockIdx.x;
     for (int d = threadIdx.x; d < 2304; d += 256) {
         const int blk = d / 384, r = d - blk * 384, kc = r / 192, r2 = r - kc * 192, n = r2 >> 2, e = r2 & 3;
@@ -154,6 +157,7 @@ constexpr int POOL_MAXQ = 6;                               // channel quads per 
 __global__ void __launch_bounds__(256)
 td_pool_kernel(const float* __restrict__ tmp, float* __restrict__ out, unsigned char* __restrict__ argmax, double* __restrict__ stats,
                int B, int h, int w, int Cs, int out_C, int out_off, int G, int stats_C) {
+    pdl_enter();
     extern __shared__ float sm[];                          // [8 warps][Cs][2]
     const int nq = Cs >> 2, oh = h >> 1, ow = w >> 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -219,6 +223,7 @@ struct PackEntry { long long w; int K, N, chunk0; long long out; };      // w: f
 struct PackTable { int n, total_chunks, mode; PackEntry e[112]; };        // mode: forward 0 = tf32, 1 = 3xTF32, 2 = bf16x3; dgrad: unused
 __global__ void __launch_bounds__(256)
 pack_w_fwd_all_kernel(const float* __restrict__ params, unsigned char* __restrict__ wpack, const PackTable T) {
+    pdl_enter();
     int li = 0;
     while (li + 1 < T.n && (int)blockIdx.x >= T.e[li + 1].chunk0) ++li;
     const PackEntry E = T.e[li];
@@ -258,6 +263,7 @@ pack_w_fwd_all_kernel(const float* __restrict__ params, unsigned char* __restric
 }
 __global__ void __launch_bounds__(256)
 pack_w_dgrad_all_kernel(const float* __restrict__ params, unsigned char* __restrict__ wpack, const PackTable T) {
+    pdl_enter();
     int li = 0;
     while (li + 1 < T.n && (int)blockIdx.x >= T.e[li + 1].chunk0) ++li;
     const PackEntry E = T.e[li];
@@ -312,6 +318,15 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
     const int c_begin = A.partial ? (int)blockIdx.y * per_slice : 0;
     const int c_end = min(nchunks, c_begin + per_slice);
 
+    pdl_trigger();
+    if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        tc::mbar_init(bars + 0, NPROD); tc::mbar_init(bars + 1, NPROD);
+        tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
+        tc::mbar_init(bars + 4, 1);
+        tc::fence_mbar_init();
+    }
+    pdl_wait();                        // everything above is on-chip; global memory only from here on
     if (tid == 0) ENDO_TRACE(1);
     // (a, beta, mean, invstd) of every input channel of this statistic group: one L2 read per CTA instead of four dependent
     // global loads per thread and channel chunk (r2 ncu: their latency sat on the producers' critical path)
@@ -320,13 +335,6 @@ dense_fwd_tf32_kernel(const FwdArgs A) {
         const int gq = (int)blockIdx.z / (A.B / A.G);
         for (int i = tid; i < A.K; i += NTHREADS)
             *reinterpret_cast<float4*>(coef_s + i * 4) = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)gq * A.K + i) * 4));
-    }
-    if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
-    if (tid == 0) {
-        tc::mbar_init(bars + 0, NPROD); tc::mbar_init(bars + 1, NPROD);
-        tc::mbar_init(bars + 2, 1);   tc::mbar_init(bars + 3, 1);
-        tc::mbar_init(bars + 4, 1);
-        tc::fence_mbar_init();
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -801,12 +809,14 @@ dense_dgrad_tf32_kernel(const Args A) {
     const int c_begin = gridDim.y > 1 ? (int)blockIdx.y : 0;
     const int c_end = gridDim.y > 1 ? c_begin + 1 : nchunks;
 
+    pdl_trigger();
     if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         tc::mbar_init(bars + 0, 256);
         for (int i = 0; i < NBUF; ++i) { tc::mbar_init(bars + 1 + i, 1); tc::mbar_init(bars + 1 + NBUF + i, 128); }
         tc::fence_mbar_init();
     }
+    pdl_wait();
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -1056,6 +1066,7 @@ dense_dgrad_tf32_kernel(const Args A) {
 // (coarse pixel, channel quad)
 __global__ void __launch_bounds__(256)
 up_sum_kernel(const float* __restrict__ hi, int hiC, float* __restrict__ low, int lowC, int low_off, int B, int h2, int w2, int C) {
+    pdl_enter();
     const int nq = C >> 2;
     const long long total = (long long)B * h2 * w2 * nq;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {

@@ -84,20 +84,25 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
     const int t_end = min(t_begin + A.tiles_per_cta, A.n_tiles);
     const int ntiles = t_end - t_begin;
     const int sh = A.up ? 1 : 0;
-    if (tid == 0) { WG_TRACE(1); if ((A.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0) g_tc_trace[0] = ntiles; }
-
+    pdl_trigger();
     if (warp == 16) tc::tmem_alloc(tmem_slot, 512);
-    if (tid < 2 * MCH) {                                     // coefficient table (zeros for TransitionUp: no BatchNorm in front)
-        const int gi = tid / MCH, cl = tid % MCH, ch = ci0 + cl;
-        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gi < A.G && ch < A.Cin && !A.up) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)gi * A.Cin + ch) * 4));
-        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ktab) + (gi * 8 + (cl >> 3)) * 144 + (cl & 7) * 16) = e;
-    }
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { tc::mbar_init(raw_full + i, 1); tc::mbar_init(raw_empty + i, NPROD); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(op_full + i, NPROD); tc::mbar_init(op_empty + i, 1); }
         tc::mbar_init(accum, 1);
         tc::fence_mbar_init();
+    }
+    // Both operand stages are cleared ONCE: every tile writes the same rows (activation planes: the 8x16 interior; gradient
+    // planes: rows kx .. 179 + kx of plane kx), every other row -- pad columns, margins of the shifted planes -- stays zero.
+    if (warp < 16)
+        for (int i = tid; i < (2 * STAGE + PAD_BYTES) / 16; i += NPROD) reinterpret_cast<uint4*>(smem + OP_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
+    pdl_wait();                                              // on-chip set-up above; global memory from here on
+    if (tid == 0) { WG_TRACE(1); if ((A.dbg & 8) && blockIdx.x == 0 && blockIdx.y == 0) g_tc_trace[0] = ntiles; }
+    if (tid < 2 * MCH) {                                     // coefficient table (zeros for TransitionUp: no BatchNorm in front)
+        const int gi = tid / MCH, cl = tid % MCH, ch = ci0 + cl;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gi < A.G && ch < A.Cin && !A.up) e = __ldg(reinterpret_cast<const float4*>(A.coef + ((size_t)gi * A.Cin + ch) * 4));
+        *reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(ktab) + (gi * 8 + (cl >> 3)) * 144 + (cl & 7) * 16) = e;
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -112,10 +117,6 @@ dense_wgrad_tma_kernel(const Args A, const __grid_constant__ CUtensorMap xmap) {
     };
 
     if (warp < 16) {
-        // Both operand stages are cleared ONCE: every tile writes the same rows (activation planes: the 8x16 interior; gradient
-        // planes: rows kx .. 179 + kx of plane kx), every other row -- pad columns, margins of the shifted planes -- stays zero.
-        for (int i = tid; i < (2 * STAGE + PAD_BYTES) / 16; i += NPROD) reinterpret_cast<uint4*>(smem + OP_OFF)[i] = make_uint4(0u, 0u, 0u, 0u);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
 
         // ---- gradient halo tile, dense / upsampled modes: (8 + 2) x 18 pixels x two 8-channel halves = 360 items, one per thread
         //      (tid < 360).  g and x of the item travel by cp.async into a two-deep ring of thread-private slots, requested one
