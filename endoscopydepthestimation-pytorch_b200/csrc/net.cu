@@ -11,6 +11,7 @@
 #include "net_wgrad2.cuh"
 #include "net_fwd2.cuh"
 #include "net_pwwgrad.cuh"
+#include "net_wgrad3.cuh"
 
 namespace endo {
 
@@ -428,9 +429,12 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     w.g_in = c.GX(l); w.g_x = c.X(l); w.g_ab = c.AB(l); w.g_C = P.Ctot[l]; w.g_off = d.out_off; w.g_K = d.conv.cout;
     w.g_h = P.h[l]; w.g_w = P.w[l]; w.oh = P.h[l]; w.ow = P.w[l]; w.B = P.B; w.G = P.G;
     w.dw = c.gparams + d.conv.w; w.db = c.gparams + d.conv.b; w.w_cin = d.cin;
-    ENDO_TRY(c.fork());
     const bool tc_w = is_tc(c.math) && !(tc_disable_mask() & 4);
     const bool tc_d = is_tc(c.math) && !(tc_disable_mask() & 2);
+    // weight gradient as a pure TMA -> MMA GEMM over the bf16 by-products of the data-gradient kernel (net_wgrad3.cuh); it runs
+    // AFTER that kernel, on the main stream (one by-product buffer serves all layers); ENDO_TC_DISABLE bit 262144: round-2a kernel
+    const bool gemm_w = tc_w && tc_d && d.cin <= 384 && d.conv.cout <= 16 && !(tc_disable_mask() & 262144);
+    if (!gemm_w) ENDO_TRY(c.fork());
     // the conv bias gradient is produced by exactly one kernel: the tcgen05 dgrad if it runs, else the FFMA wgrad if it
     // runs, else a tiny dedicated reduction
     if (tc_d) w.db = nullptr;
@@ -440,7 +444,8 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
                                                   (long long)(P.B / P.G) * P.h[l] * P.w[l], P.G);
         ENDO_CHECK_LAUNCH();
     }
-    if (tc_w) {
+    if (gemm_w) {
+    } else if (tc_w) {
         // bf16 tensor-core weight gradient (pixels are the GEMM K dimension); the bias gradient comes from the dgrad kernel
         tcwgrad::Args t;
         t.x = c.X(l); t.coef = c.COEF(d.bn); t.g = c.GX(l); t.ab = c.AB(l); t.dw = c.gparams + d.conv.w;
@@ -468,13 +473,48 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         t.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + d.wpb_off);   // packed by pack_dense_weights_bwd()
+        const int c8 = (d.cin + 7) / 8 * 8;
+        if (gemm_w) {
+            t.a16 = reinterpret_cast<unsigned short*>(c.scratch + P.a16_off);
+            t.g16 = reinterpret_cast<unsigned short*>(c.scratch + P.g16_off);
+        }
         ENDO_SET_MAX_SMEM(tcdgrad::dense_dgrad_tf32_kernel, tcdgrad::SMEM_BYTES);
         const int tiles = cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH);
         const int ysplit = (tiles * t.B < 4 * kNumSMs && !(tc_disable_mask() & 128)) ? cdiv(t.Cin, tcdgrad::NC) : 1;
         dim3 grid(tiles, ysplit, t.B);
-        ProfScope prof(PC_DGRAD, c.s);
-        launch_pdl(tcdgrad::dense_dgrad_tf32_kernel, grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s, t);
-        ENDO_CHECK_LAUNCH();
+        {
+            ProfScope prof(PC_DGRAD, c.s);
+            launch_pdl(tcdgrad::dense_dgrad_tf32_kernel, grid, tcdgrad::NTHREADS, tcdgrad::SMEM_BYTES, c.s, t);
+            ENDO_CHECK_LAUNCH();
+        }
+        if (gemm_w) {
+            tcwgrad3::Args g{};
+            g.dw = c.gparams + d.conv.w; g.Cin = d.cin; g.Cout = d.conv.cout; g.H = t.H; g.W = t.W;
+            g.tiles_x = cdiv(t.W, tcwgrad3::TW); g.tiles_y = cdiv(t.H, tcwgrad3::TR); g.n_tiles = g.tiles_x * g.tiles_y * t.B;
+            const int mb_all = cdiv(d.cin, 128);
+            int ny = 1;
+            g.groups = c8 / 8; g.mblocks = mb_all;
+            // few tiles, or two stages of all channel groups would not fit: one 128-channel block per CTA
+            if (mb_all > 1 && (g.n_tiles < 2 * kNumSMs || tcwgrad3::smem_bytes(g.groups, g.mblocks, 2) > (size_t)tcwgrad3::SMEM_LIMIT)) {
+                ny = mb_all; g.groups = 16; g.mblocks = 1;
+            }
+            g.sets = 512 / (g.mblocks * tcwgrad3::NB);
+            if (g.sets > 3) g.sets = 3;
+            g.nstages = 1;
+            while (g.nstages < tcwgrad3::MAX_STAGES && tcwgrad3::smem_bytes(g.groups, g.mblocks, g.nstages + 1) <= (size_t)tcwgrad3::SMEM_LIMIT) ++g.nstages;
+            const size_t smem = tcwgrad3::smem_bytes(g.groups, g.mblocks, g.nstages);
+            if (smem > (size_t)tcwgrad3::SMEM_LIMIT || g.sets < 1) return ENDO_ERR_CONFIG;
+            int ctas = kNumSMs < g.n_tiles ? kNumSMs : g.n_tiles;
+            g.tiles_per_cta = cdiv(g.n_tiles, ctas);
+            CUtensorMap amap, gmap;
+            if (!tcwgrad3::make_map(&amap, t.a16, t.B, t.H, t.W, tcwgrad3::TR, c8 / 8, g.groups) ||
+                !tcwgrad3::make_map(&gmap, t.g16, t.B, t.H, t.W, tcwgrad3::TR, 2, 2))
+                return ENDO_ERR_CUDA;
+            ENDO_SET_MAX_SMEM(tcwgrad3::dense_wgrad_gemm_kernel, tcwgrad3::SMEM_LIMIT);
+            ProfScope prof(PC_WGRAD, c.s);
+            launch_pdl(tcwgrad3::dense_wgrad_gemm_kernel, dim3(cdiv(g.n_tiles, g.tiles_per_cta), ny), tcwgrad3::NTHREADS, smem, c.s, g, amap, gmap);
+            ENDO_CHECK_LAUNCH();
+        }
     } else {
         // all 12 (16) output-gradient channels in ONE staging step (no padded K), 32 input channels per CTA so that two
         // CTAs fit an SM (<= 128 registers): their staging / epilogue phases overlap each other's FMA phase

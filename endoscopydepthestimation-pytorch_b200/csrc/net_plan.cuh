@@ -55,6 +55,8 @@ struct NetPlan {
     long long gx_off[kMaxLevels];               // float [B,h,w,Ctot] gradient buffers
     long long ab_off[kMaxLevels];               // float [G][Ctot][2] lazy BN-backward correction (A, Bc)
     long long bnred_off;                        // double [G][maxC][2] per-layer BN backward sums
+    long long a16_off, g16_off;                 // bf16 by-products of the DenseLayer data gradient (operands of its weight-gradient GEMM):
+                                                // relu(bn(x)) [B*h*w][cin rounded to 8] and the corrected output gradient [B*h*w][16]
     long long wpack_bwd_off;                    // sized for the widest layer: tensor-core weight image of the layer being run (backward)
     long long scratch_bytes;
     int maxC;
@@ -206,6 +208,19 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         const long long n16 = 2ll * B * P.h[l] * P.w[l] * (P.C0[l] + P.Dn[l]);
         P.td[l].r16 = off; off = align_up(off + n16, 256);
         P.td[l].a16 = off; off = align_up(off + n16, 256);
+    }
+    {
+        long long a16 = 0, g16 = 0;
+        auto need = [&](const DenseLayerP& d) {
+            const long long px = 1ll * B * P.h[d.level] * P.w[d.level];
+            const long long a = 2 * px * ((d.cin + 7) / 8 * 8), g = 2 * px * 16;
+            if (a > a16) a16 = a;
+            if (g > g16) g16 = g;
+        };
+        for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) need(d);
+        for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) need(d);
+        P.a16_off = off; off = align_up(off + a16, 256);
+        P.g16_off = off; off = align_up(off + g16, 256);
     }
     for (int l = 0; l <= nd; ++l) { P.gx_off[l] = off; off = align_up(off + 4ll * B * P.h[l] * P.w[l] * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.ab_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }

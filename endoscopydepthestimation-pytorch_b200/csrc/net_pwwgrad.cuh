@@ -116,23 +116,29 @@ pw_wgrad_kernel(const Args A, const __grid_constant__ CUtensorMap amap, const __
         const uint32_t plane = (uint32_t)A.KT * 16u;
         const uint64_t d_hi = tc::smem_desc(0, 128, plane);                               // LBO = 8-pixel groups, SBO = channel-group planes
         const int ksteps = A.KT >> 4;
-        int kk = 0;                                                                       // running K-step: picks the accumulator set
+        // incremental bookkeeping: the issuing thread's own instruction stream is the critical path of this kernel
+        const uint32_t set_cols = (uint32_t)(mblocks * A.Nper);
+        uint32_t set = 0, col = tmem, acc = 0;
+        int s = 0, ph = 0;
         for (int it = 0; it < ntiles; ++it) {
-            const int s = it % A.nstages;
-            tc::mbar_wait(full + s, (it / A.nstages) & 1);
+            tc::mbar_wait(full + s, ph);
             tc::tc_fence_after();
             const uint32_t a_base = tc::smem_u32(stages + (size_t)s * stage), b_base = a_base + (uint32_t)A.C * A.KT * 2u;
+            uint64_t ad0 = d_hi | (uint64_t)(a_base >> 4), bd = d_hi | (uint64_t)(b_base >> 4);
 #pragma unroll 1
-            for (int k = 0; k < ksteps; ++k, ++kk) {
-                const int set = kk % A.sets;
-                const uint32_t acc = (uint32_t)(kk >= A.sets);
-                const uint64_t bd = d_hi | (uint64_t)((b_base + (uint32_t)k * 256u) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+                uint64_t ad = ad0;
+                uint32_t cc = col;
                 for (int mb = 0; mb < mblocks; ++mb) {
-                    const uint64_t ad = d_hi | (uint64_t)((a_base + (uint32_t)mb * 16u * plane + (uint32_t)k * 256u) >> 4);
-                    tc::mma_f16_w(tmem + (uint32_t)((set * mblocks + mb) * A.Nper), ad, bd, idesc, acc);
+                    tc::mma_f16_w(cc, ad, bd, idesc, acc);
+                    ad += (uint64_t)(plane); cc += (uint32_t)A.Nper;           // 16 planes = 16 * plane bytes = plane 16-byte units
                 }
+                ad0 += 16; bd += 16;
+                col += set_cols;
+                if (++set == (uint32_t)A.sets) { set = 0; col = tmem; acc = 1; }
             }
             tc::tc_commit_w(empty + s);
+            if (++s == A.nstages) { s = 0; ph ^= 1; }
         }
         tc::tc_commit_w(accum);
     } else {

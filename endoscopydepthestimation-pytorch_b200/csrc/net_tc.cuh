@@ -754,6 +754,12 @@ namespace endo {
 // read-modify-write is done with lane = channel quad (256 contiguous bytes per pixel) and the per-channel
 // BatchNorm-backward sums (sum gy, sum gy*xhat) live in registers of the lane that owns the channel.
 // =====================================================================================================
+__device__ __forceinline__ uint32_t tcwgrad_pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 namespace tcdgrad {
 
 using tcconv::PITCH; using tcconv::TH; using tcconv::TW; using tcconv::MBLK; using tcconv::PLANE_BYTES;
@@ -778,6 +784,11 @@ struct Args {
     float* db;                                            // conv bias gradient [Cout] (sum of the output gradient), accumulated
     double* red; int red_C;                               // [G][red_C][2] BN backward sums
     int C, out_off, Cout, in_off, Cin, H, W, B, G;
+    // by-products for the weight-gradient GEMM (net_wgrad3.cuh; nullptr = off), both bf16 and PLANE-MAJOR, [channel group of
+    // 8][B*H*W pixels][8 channels] (16 consecutive pixels of a group = 256 contiguous bytes: what a TMA box line wants):
+    // relu(bn(x)) of the Cin input channels (the epilogue evaluates it for the ReLU mask) and the corrected output gradient
+    // (16 channels, as staged)
+    unsigned short* a16; unsigned short* g16;
     // plain mode (TransitionUp, models.py:70-80: the convolution input is the upsampled map, no BatchNorm / ReLU in front):
     // the epilogue stores (first = 1) or accumulates the raw data gradient into a scratch tensor [B,H,W,oC] at channel
     // o_off; up_sum_kernel then folds the 2x2 blocks into the half-resolution gradient buffer
@@ -862,7 +873,15 @@ dense_dgrad_tf32_kernel(const Args A) {
                         if (okmask & (1u << j)) {
                             v.x = gq[j].x + fmaf(c0.y, xq[j].x, c0.x); v.y = gq[j].y + fmaf(c0.w, xq[j].y, c0.z);
                             v.z = gq[j].z + fmaf(c1.y, xq[j].z, c1.x); v.w = gq[j].w + fmaf(c1.w, xq[j].w, c1.z);
-                            if (r >= 1 && r <= TH && cc >= 1 && cc <= TW) { bs.x += v.x; bs.y += v.y; bs.z += v.z; bs.w += v.w; }
+                        }
+                        if (r >= 1 && r <= TH && cc >= 1 && cc <= TW) {          // interior: each pixel belongs to exactly one tile
+                            bs.x += v.x; bs.y += v.y; bs.z += v.z; bs.w += v.w;
+                            const int y = y0 + r - 1, x = x0 + cc - 1;
+                            if (A.g16 && blockIdx.y == 0 && y < A.H && x < A.W)   // (padding channels 12 .. 15: zeros)
+                                *reinterpret_cast<uint2*>(A.g16 + (((size_t)(ch >> 3) * A.B * A.H * A.W) + img + (size_t)y * A.W + x) * 8 + (ch & 7)) =
+                                    make_uint2(tcwgrad_pack_bf16(v.x, v.y), tcwgrad_pack_bf16(v.z, v.w));
+                        }
+                        if (okmask & (1u << j)) {
                             v.x = tcconv::tf32_rn(v.x); v.y = tcconv::tf32_rn(v.y); v.z = tcconv::tf32_rn(v.z); v.w = tcconv::tf32_rn(v.w);
                         }
                         *reinterpret_cast<float4*>(g_s + grp * PLANE_BYTES + (size_t)(px + 1) * 16) = v;   // row 0 is a margin row
@@ -919,7 +938,10 @@ dense_dgrad_tf32_kernel(const Args A) {
                 // first, so that they travel while the MMAs finish, the accumulator is drained and the warps meet at the barrier
                 float4 xv[8];
                 unsigned okmask = 0u;
-                size_t off[8];
+                unsigned pix[8];                                          // linear pixel index (b * H + y) * W + x
+                const size_t npix_all = (size_t)A.B * A.H * A.W;
+                const size_t cbase = (A.plain ? A.o_off : A.in_off) + ci0 + quad * 4;
+                const size_t cstr = A.plain ? A.oC : A.C;
                 if (quad_ok) {
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {                     // all 8 loads of this unit in flight at once
@@ -927,14 +949,10 @@ dense_dgrad_tf32_kernel(const Args A) {
                         const int L = PITCH + mb * 128 + p;
                         const int r = L / PITCH, cc = L - r * PITCH;
                         const int y = y0 + r - 1, x = x0 + cc - 1;
-                        off[it] = 0;
+                        pix[it] = 0;
                         if ((r <= TH) && (cc >= 1) && (cc <= TW) && (y < A.H) && (x < A.W)) {
-                            if (A.plain) {
-                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.oC + A.o_off + ci0 + quad * 4;
-                            } else {
-                                off[it] = ((size_t)(b * A.H + y) * A.W + x) * A.C + A.in_off + ci0 + quad * 4;
-                                xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + off[it]));
-                            }
+                            pix[it] = (unsigned)((b * A.H + y) * A.W + x);
+                            if (!A.plain) xv[it] = __ldg(reinterpret_cast<const float4*>(A.x + (size_t)pix[it] * cstr + cbase));
                             okmask |= 1u << it;
                         }
                     }
@@ -966,8 +984,8 @@ dense_dgrad_tf32_kernel(const Args A) {
                             if (okmask & (1u << it)) {
                                 const int p = warp * 16 + it * 2 + psub;
                                 const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
-                                if (A.first) *reinterpret_cast<float4*>(A.po + off[it]) = d;
-                                else tcconv::red_add_v4(A.po + off[it], d.x, d.y, d.z, d.w);
+                                if (A.first) *reinterpret_cast<float4*>(A.po + (size_t)pix[it] * cstr + cbase) = d;
+                                else tcconv::red_add_v4(A.po + (size_t)pix[it] * cstr + cbase, d.x, d.y, d.z, d.w);
                             }
                         }
                     } else
@@ -978,16 +996,24 @@ dense_dgrad_tf32_kernel(const Args A) {
                             const float4 d = *reinterpret_cast<const float4*>(tb + (size_t)p * TB_PITCH + quad * 16);
                             const float4 xq = xv[it];
                             const float e0 = xq.x - cm[0], e1 = xq.y - cm[1], e2 = xq.z - cm[2], e3 = xq.w - cm[3];
-                            const float g0 = fmaf(ca[0], e0, cb[0]) > 0.f ? d.x : 0.f;
-                            const float g1 = fmaf(ca[1], e1, cb[1]) > 0.f ? d.y : 0.f;
-                            const float g2 = fmaf(ca[2], e2, cb[2]) > 0.f ? d.z : 0.f;
-                            const float g3 = fmaf(ca[3], e3, cb[3]) > 0.f ? d.w : 0.f;
+                            const float t0 = fmaf(ca[0], e0, cb[0]), t1 = fmaf(ca[1], e1, cb[1]);
+                            const float t2 = fmaf(ca[2], e2, cb[2]), t3 = fmaf(ca[3], e3, cb[3]);
+                            const float g0 = t0 > 0.f ? d.x : 0.f;
+                            const float g1 = t1 > 0.f ? d.y : 0.f;
+                            const float g2 = t2 > 0.f ? d.z : 0.f;
+                            const float g3 = t3 > 0.f ? d.w : 0.f;
                             s1[0] += g0; s2[0] += g0 * (e0 * cs[0]);
                             s1[1] += g1; s2[1] += g1 * (e1 * cs[1]);
                             s1[2] += g2; s2[2] += g2 * (e2 * cs[2]);
                             s1[3] += g3; s2[3] += g3 * (e3 * cs[3]);
                             // gout[p][ci] += a * g: each (pixel, channel) is touched by exactly one thread of one CTA per launch
-                            tcconv::red_add_v4(A.gout + off[it], ca[0] * g0, ca[1] * g1, ca[2] * g2, ca[3] * g3);
+                            tcconv::red_add_v4(A.gout + (size_t)pix[it] * cstr + cbase, ca[0] * g0, ca[1] * g1, ca[2] * g2, ca[3] * g3);
+                            if (A.a16) {                                 // relu(bn(x)) for the weight-gradient GEMM
+                                unsigned short* ap = A.a16 + ((size_t)((ci0 >> 3) + (quad >> 1)) * npix_all + pix[it]) * 8 + (quad & 1) * 4;
+                                *reinterpret_cast<uint2*>(ap) = make_uint2(tcwgrad_pack_bf16(fmaxf(t0, 0.f), fmaxf(t1, 0.f)),
+                                                                           tcwgrad_pack_bf16(fmaxf(t2, 0.f), fmaxf(t3, 0.f)));
+                                if (ci0 + quad * 4 + 4 == A.Cin && (A.Cin & 4)) *reinterpret_cast<uint2*>(ap + 4) = make_uint2(0u, 0u);
+                            }
                         }
                     }
                 }
