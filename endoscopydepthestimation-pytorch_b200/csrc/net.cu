@@ -126,7 +126,7 @@ static inline int x3_mode(int math) {
 // threads / streams) get different triples, so nobody re-records an event another caller is about to wait on.  Re-use by a
 // LATER call is safe: cudaStreamWaitEvent captures the event's most recent record at the time of the call.  The triples are
 // created on first use (not during stream capture: run one warm-up step before capturing a CUDA graph) and live until exit.
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr, buf[2] = {nullptr, nullptr}; };
 static std::mutex g_side_mu;
 static std::vector<SideStream*> g_side_free[64];
 static SideStream* side_acquire(int dev) {
@@ -138,8 +138,12 @@ static SideStream* side_acquire(int dev) {
     SideStream* t = new SideStream();
     if (cudaStreamCreateWithFlags(&t->s, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&t->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&t->join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&t->join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->buf[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->buf[1], cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
+        if (t->buf[0]) cudaEventDestroy(t->buf[0]);
+        if (t->join) cudaEventDestroy(t->join);
         if (t->fork) cudaEventDestroy(t->fork);
         if (t->s) cudaStreamDestroy(t->s);
         delete t;
@@ -171,6 +175,11 @@ struct Ctx {
     cudaStream_t sw = nullptr;        // stream of the weight-gradient kernels (== s when the side stream is off)
     cudaEvent_t ev_fork = nullptr;
     SideLease* lease = nullptr;
+    // by-product buffer sets of the DenseLayer weight-gradient GEMM: layer i's data gradient (main stream) writes set i & 1, its
+    // GEMM (side stream) reads it; ev_buf[k] = "the GEMM that last read set k has finished", awaited before set k is rewritten
+    cudaEvent_t ev_buf[2] = {nullptr, nullptr};
+    mutable int wg_layers = 0;
+    mutable bool buf_busy[2] = {false, false};
     // everything enqueued on s so far happens-before what is enqueued on sw from now on
     int fork() const {
         if (sw == s) return ENDO_OK;
@@ -474,9 +483,12 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         t.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + d.wpb_off);   // packed by pack_dense_weights_bwd()
         const int c8 = (d.cin + 7) / 8 * 8;
+        const int bk = c.wg_layers & 1;
         if (gemm_w) {
-            t.a16 = reinterpret_cast<unsigned short*>(c.scratch + P.a16_off);
-            t.g16 = reinterpret_cast<unsigned short*>(c.scratch + P.g16_off);
+            ++c.wg_layers;
+            t.a16 = reinterpret_cast<unsigned short*>(c.scratch + P.a16_off[bk]);
+            t.g16 = reinterpret_cast<unsigned short*>(c.scratch + P.g16_off[bk]);
+            if (c.sw != c.s && c.buf_busy[bk]) ENDO_CUDA(cudaStreamWaitEvent(c.s, c.ev_buf[bk], 0));
         }
         ENDO_SET_MAX_SMEM(tcdgrad::dense_dgrad_tf32_kernel, tcdgrad::SMEM_BYTES);
         const int tiles = cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH);
@@ -511,9 +523,13 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
                 !tcwgrad3::make_map(&gmap, t.g16, t.B, t.H, t.W, tcwgrad3::TR, 2, 2))
                 return ENDO_ERR_CUDA;
             ENDO_SET_MAX_SMEM(tcwgrad3::dense_wgrad_gemm_kernel, tcwgrad3::SMEM_LIMIT);
-            ProfScope prof(PC_WGRAD, c.s);
-            launch_pdl(tcwgrad3::dense_wgrad_gemm_kernel, dim3(cdiv(g.n_tiles, g.tiles_per_cta), ny), tcwgrad3::NTHREADS, smem, c.s, g, amap, gmap);
-            ENDO_CHECK_LAUNCH();
+            ENDO_TRY(c.fork());                              // by-products complete -> the GEMM overlaps the next layers' data gradients
+            {
+                ProfScope prof(PC_WGRAD, c.sw);
+                launch_pdl(tcwgrad3::dense_wgrad_gemm_kernel, dim3(cdiv(g.n_tiles, g.tiles_per_cta), ny), tcwgrad3::NTHREADS, smem, c.sw, g, amap, gmap);
+                ENDO_CHECK_LAUNCH();
+            }
+            if (c.sw != c.s) { ENDO_CUDA(cudaEventRecord(c.ev_buf[bk], c.sw)); c.buf_busy[bk] = true; }
         }
     } else {
         // all 12 (16) output-gradient channels in ONE staging step (no padded K), 32 input channels per CTA so that two
@@ -940,6 +956,7 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
     }
     c.sw = lease.t ? lease.t->s : c.s;
     c.ev_fork = lease.t ? lease.t->fork : nullptr;
+    if (lease.t) { c.ev_buf[0] = lease.t->buf[0]; c.ev_buf[1] = lease.t->buf[1]; }
     c.lease = &lease;
     const int nd = cfg->n_down;
     // gradient buffers of levels >= 1, the lazy-correction arrays and the BN sums start at zero; the level-0

@@ -55,7 +55,8 @@ struct NetPlan {
     long long gx_off[kMaxLevels];               // float [B,h,w,Ctot] gradient buffers
     long long ab_off[kMaxLevels];               // float [G][Ctot][2] lazy BN-backward correction (A, Bc)
     long long bnred_off;                        // double [G][maxC][2] per-layer BN backward sums
-    long long a16_off, g16_off;                 // bf16 by-products of the DenseLayer data gradient (operands of its weight-gradient GEMM):
+    long long a16_off[2], g16_off[2];           // (two sets: the GEMM of layer i reads one while the data gradient of layer i-1 writes
+                                                // the other) bf16 by-products of the DenseLayer data gradient (operands of its weight-gradient GEMM):
                                                 // relu(bn(x)) [B*h*w][cin rounded to 8] and the corrected output gradient [B*h*w][16]
     long long wpack_bwd_off;                    // sized for the widest layer: tensor-core weight image of the layer being run (backward)
     long long scratch_bytes;
@@ -219,8 +220,10 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         };
         for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) need(d);
         for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) need(d);
-        P.a16_off = off; off = align_up(off + a16, 256);
-        P.g16_off = off; off = align_up(off + g16, 256);
+        for (int k = 0; k < 2; ++k) {
+            P.a16_off[k] = off; off = align_up(off + a16, 256);
+            P.g16_off[k] = off; off = align_up(off + g16, 256);
+        }
     }
     for (int l = 0; l <= nd; ++l) { P.gx_off[l] = off; off = align_up(off + 4ll * B * P.h[l] * P.w[l] * P.Ctot[l], 256); }
     for (int l = 0; l <= nd; ++l) { P.ab_off[l] = off; off = align_up(off + 8ll * P.G * P.Ctot[l], 256); }
