@@ -180,6 +180,18 @@ struct Ctx {
     cudaEvent_t ev_buf[2] = {nullptr, nullptr};
     mutable int wg_layers = 0;
     mutable bool buf_busy[2] = {false, false};
+    // next by-product set; the MAIN stream waits until the GEMM that last read it has finished
+    int acquire_buf(int* bk) const {
+        *bk = wg_layers++ & 1;
+        if (sw != s && buf_busy[*bk]) ENDO_CUDA(cudaStreamWaitEvent(s, ev_buf[*bk], 0));
+        return ENDO_OK;
+    }
+    int release_buf(int bk) const {                   // after the last GEMM that reads set bk was enqueued on sw
+        if (sw != s) { ENDO_CUDA(cudaEventRecord(ev_buf[bk], sw)); buf_busy[bk] = true; }
+        return ENDO_OK;
+    }
+    unsigned short* A16(int bk) const { return reinterpret_cast<unsigned short*>(scratch + P.a16_off[bk]); }
+    unsigned short* G16(int bk) const { return reinterpret_cast<unsigned short*>(scratch + P.g16_off[bk]); }
     // everything enqueued on s so far happens-before what is enqueued on sw from now on
     int fork() const {
         if (sw == s) return ENDO_OK;
@@ -429,6 +441,42 @@ static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
     return ENDO_OK;
 }
 
+// weight gradient of a 3x3 convolution as a TMA -> tcgen05 GEMM over plane-major bf16 operands (net_wgrad3.cuh), on the
+// weight-gradient stream: act16 = [ceil(Cin/8)][B*H*W][8] activations, g16 = [g_groups][B*H*W][8] output gradient of which the
+// two groups from g_grp0 (16 output channels) are used; dw = OIHW block of those output channels
+static int launch_wgrad_gemm(const Ctx& c, float* dw, int Cin, int Cout, int H, int W, const unsigned short* a16, const unsigned short* g16,
+                             int g_groups, int g_grp0, int cat) {
+    const NetPlan& P = c.P;
+    const int c8 = (Cin + 7) / 8 * 8;
+    tcwgrad3::Args g{};
+    g.dw = dw; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.g_grp0 = g_grp0;
+    g.tiles_x = cdiv(W, tcwgrad3::TW); g.tiles_y = cdiv(H, tcwgrad3::TR); g.n_tiles = g.tiles_x * g.tiles_y * P.B;
+    const int mb_all = cdiv(Cin, 128);
+    int ny = 1;
+    g.groups = c8 / 8; g.mblocks = mb_all;
+    // few tiles, or two stages of all channel groups would not fit: one 128-channel block per CTA
+    if (mb_all > 1 && (g.n_tiles < 2 * kNumSMs || tcwgrad3::smem_bytes(g.groups, g.mblocks, 2) > (size_t)tcwgrad3::SMEM_LIMIT)) {
+        ny = mb_all; g.groups = 16; g.mblocks = 1;
+    }
+    g.sets = 512 / (g.mblocks * tcwgrad3::NB);
+    if (g.sets > 3) g.sets = 3;
+    g.nstages = 1;
+    while (g.nstages < tcwgrad3::MAX_STAGES && tcwgrad3::smem_bytes(g.groups, g.mblocks, g.nstages + 1) <= (size_t)tcwgrad3::SMEM_LIMIT) ++g.nstages;
+    const size_t smem = tcwgrad3::smem_bytes(g.groups, g.mblocks, g.nstages);
+    if (smem > (size_t)tcwgrad3::SMEM_LIMIT || g.sets < 1) return ENDO_ERR_CONFIG;
+    const int ctas = kNumSMs < g.n_tiles ? kNumSMs : g.n_tiles;
+    g.tiles_per_cta = cdiv(g.n_tiles, ctas);
+    CUtensorMap amap, gmap;
+    if (!tcwgrad3::make_map(&amap, a16, P.B, H, W, tcwgrad3::TR, c8 / 8, g.groups) ||
+        !tcwgrad3::make_map(&gmap, g16, P.B, H, W, tcwgrad3::TR, g_groups, 2))
+        return ENDO_ERR_CUDA;
+    ENDO_SET_MAX_SMEM(tcwgrad3::dense_wgrad_gemm_kernel, tcwgrad3::SMEM_LIMIT);
+    ProfScope prof(cat, c.sw);
+    launch_pdl(tcwgrad3::dense_wgrad_gemm_kernel, dim3(cdiv(g.n_tiles, g.tiles_per_cta), ny), tcwgrad3::NTHREADS, smem, c.sw, g, amap, gmap);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}
+
 static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
     const NetPlan& P = c.P;
     const int l = d.level;
@@ -482,13 +530,10 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
         t.C = P.Ctot[l]; t.out_off = d.out_off; t.Cout = d.conv.cout; t.in_off = d.in_off; t.Cin = d.cin;
         t.H = P.h[l]; t.W = P.w[l]; t.B = P.B; t.G = P.G;
         t.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + d.wpb_off);   // packed by pack_dense_weights_bwd()
-        const int c8 = (d.cin + 7) / 8 * 8;
-        const int bk = c.wg_layers & 1;
+        int bk = 0;
         if (gemm_w) {
-            ++c.wg_layers;
-            t.a16 = reinterpret_cast<unsigned short*>(c.scratch + P.a16_off[bk]);
-            t.g16 = reinterpret_cast<unsigned short*>(c.scratch + P.g16_off[bk]);
-            if (c.sw != c.s && c.buf_busy[bk]) ENDO_CUDA(cudaStreamWaitEvent(c.s, c.ev_buf[bk], 0));
+            ENDO_TRY(c.acquire_buf(&bk));
+            t.a16 = c.A16(bk); t.g16 = c.G16(bk);
         }
         ENDO_SET_MAX_SMEM(tcdgrad::dense_dgrad_tf32_kernel, tcdgrad::SMEM_BYTES);
         const int tiles = cdiv(t.W, tcconv::TW) * cdiv(t.H, tcconv::TH);
@@ -500,36 +545,9 @@ static int dense_layer_bwd(const Ctx& c, const DenseLayerP& d) {
             ENDO_CHECK_LAUNCH();
         }
         if (gemm_w) {
-            tcwgrad3::Args g{};
-            g.dw = c.gparams + d.conv.w; g.Cin = d.cin; g.Cout = d.conv.cout; g.H = t.H; g.W = t.W;
-            g.tiles_x = cdiv(t.W, tcwgrad3::TW); g.tiles_y = cdiv(t.H, tcwgrad3::TR); g.n_tiles = g.tiles_x * g.tiles_y * t.B;
-            const int mb_all = cdiv(d.cin, 128);
-            int ny = 1;
-            g.groups = c8 / 8; g.mblocks = mb_all;
-            // few tiles, or two stages of all channel groups would not fit: one 128-channel block per CTA
-            if (mb_all > 1 && (g.n_tiles < 2 * kNumSMs || tcwgrad3::smem_bytes(g.groups, g.mblocks, 2) > (size_t)tcwgrad3::SMEM_LIMIT)) {
-                ny = mb_all; g.groups = 16; g.mblocks = 1;
-            }
-            g.sets = 512 / (g.mblocks * tcwgrad3::NB);
-            if (g.sets > 3) g.sets = 3;
-            g.nstages = 1;
-            while (g.nstages < tcwgrad3::MAX_STAGES && tcwgrad3::smem_bytes(g.groups, g.mblocks, g.nstages + 1) <= (size_t)tcwgrad3::SMEM_LIMIT) ++g.nstages;
-            const size_t smem = tcwgrad3::smem_bytes(g.groups, g.mblocks, g.nstages);
-            if (smem > (size_t)tcwgrad3::SMEM_LIMIT || g.sets < 1) return ENDO_ERR_CONFIG;
-            int ctas = kNumSMs < g.n_tiles ? kNumSMs : g.n_tiles;
-            g.tiles_per_cta = cdiv(g.n_tiles, ctas);
-            CUtensorMap amap, gmap;
-            if (!tcwgrad3::make_map(&amap, t.a16, t.B, t.H, t.W, tcwgrad3::TR, c8 / 8, g.groups) ||
-                !tcwgrad3::make_map(&gmap, t.g16, t.B, t.H, t.W, tcwgrad3::TR, 2, 2))
-                return ENDO_ERR_CUDA;
-            ENDO_SET_MAX_SMEM(tcwgrad3::dense_wgrad_gemm_kernel, tcwgrad3::SMEM_LIMIT);
             ENDO_TRY(c.fork());                              // by-products complete -> the GEMM overlaps the next layers' data gradients
-            {
-                ProfScope prof(PC_WGRAD, c.sw);
-                launch_pdl(tcwgrad3::dense_wgrad_gemm_kernel, dim3(cdiv(g.n_tiles, g.tiles_per_cta), ny), tcwgrad3::NTHREADS, smem, c.sw, g, amap, gmap);
-                ENDO_CHECK_LAUNCH();
-            }
-            if (c.sw != c.s) { ENDO_CUDA(cudaEventRecord(c.ev_buf[bk], c.sw)); c.buf_busy[bk] = true; }
+            ENDO_TRY(launch_wgrad_gemm(c, c.gparams + d.conv.w, d.cin, d.conv.cout, t.H, t.W, t.a16, t.g16, 2, 0, PC_WGRAD));
+            ENDO_TRY(c.release_buf(bk));
         }
     } else {
         // all 12 (16) output-gradient channels in ONE staging step (no padded K), 32 input channels per CTA so that two
@@ -793,8 +811,24 @@ static int trans_up_bwd(const Ctx& c, int i) {
     const long long tmp_need = 4ll * P.B * P.h[l] * P.w[l] * t.cin;
     const bool dgrad_tc = is_tc(c.math) && !(tc_disable_mask() & 2048) && t.cin <= tcdgrad::NC && (t.cin & 3) == 0 &&
                           tmp_need <= P.tdtmp_bytes;
-    ENDO_TRY(c.fork());
-    if (is_tc(c.math) && !(tc_disable_mask() & 16)) {
+    // weight gradient as TMA -> tcgen05 GEMMs (net_wgrad3.cuh): the upsampled input is packed to bf16 planes by a small kernel, the
+    // output gradient planes are by-products of the data-gradient passes below; ENDO_TC_DISABLE bit 262144: round-2a kernel
+    const bool gemm_w = dgrad_tc && !(tc_disable_mask() & 16) && !(tc_disable_mask() & 262144) && !(t.cin & 7) && t.cin <= 384 &&
+                        !(P.h[l] & 1) && !(P.w[l] & 1);
+    int bk = 0;
+    if (gemm_w) {
+        ENDO_TRY(c.acquire_buf(&bk));
+        const long long items = (long long)P.B * P.h[l] * P.w[l] * (t.cin / 8);
+        int blocks = (int)((items + 255) / 256);
+        if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
+        ProfScope prof(PC_WGRAD_TRANS, c.s);
+        launch_pdl(tcwgrad3::upsample_pack16_kernel, blocks, 256, 0, c.s, c.X(ls), P.Ctot[ls], t.src_off, t.cin, c.A16(bk), P.B, P.h[l], P.w[l]);
+        ENDO_CHECK_LAUNCH();
+    } else {
+        ENDO_TRY(c.fork());
+    }
+    if (gemm_w) {
+    } else if (is_tc(c.math) && !(tc_disable_mask() & 16)) {
         // tcgen05 (bf16): the DenseLayer weight-gradient kernel with the upsampling loader, 16 output channels per pass;
         // the bias gradient comes from the small dedicated reduction
         if (!dgrad_tc) {                                  // otherwise the data-gradient passes below produce the bias gradient
@@ -830,6 +864,7 @@ static int trans_up_bwd(const Ctx& c, int i) {
             q.C = P.Ctot[l]; q.out_off = co0; q.Cout = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16; q.in_off = 0; q.Cin = t.cin;
             q.H = P.h[l]; q.W = P.w[l]; q.B = P.B; q.G = P.G;
             q.plain = 1; q.first = co0 == 0; q.oC = t.cin; q.o_off = 0; q.po = tmp;
+            if (gemm_w) q.g16 = c.G16(bk) + (size_t)(co0 / 8) * P.B * P.h[l] * P.w[l] * 8;     // groups co0/8, co0/8 + 1 of the gradient planes
             q.wpack = reinterpret_cast<const float*>(c.scratch + P.wpack_bwd_off + t.wpb_off[co0 / 16]);   // packed by pack_dense_weights_bwd()
             dim3 grid(cdiv(q.W, tcconv::TW) * cdiv(q.H, tcconv::TH), 1, q.B);
             ProfScope prof(PC_DGRAD_TRANS, c.s);
@@ -839,9 +874,21 @@ static int trans_up_bwd(const Ctx& c, int i) {
         const long long items = (long long)P.B * P.h[ls] * P.w[ls] * (t.cin / 4);
         int blocks = (int)((items + 255) / 256);
         if (blocks > 16 * kNumSMs) blocks = 16 * kNumSMs;
-        ProfScope prof(PC_DGRAD_TRANS, c.s);
-        launch_pdl(tcdgrad::up_sum_kernel, blocks, 256, 0, c.s, tmp, t.cin, c.GX(ls), P.Ctot[ls], t.src_off, P.B, P.h[ls], P.w[ls], t.cin);
-        ENDO_CHECK_LAUNCH();
+        {
+            ProfScope prof(PC_DGRAD_TRANS, c.s);
+            launch_pdl(tcdgrad::up_sum_kernel, blocks, 256, 0, c.s, tmp, t.cin, c.GX(ls), P.Ctot[ls], t.src_off, P.B, P.h[ls], P.w[ls], t.cin);
+            ENDO_CHECK_LAUNCH();
+        }
+        if (gemm_w) {
+            ENDO_TRY(c.fork());
+            const int g_groups = (t.conv.cout + 15) / 16 * 2;
+            for (int co0 = 0; co0 < t.conv.cout; co0 += 16) {
+                const int nco = (t.conv.cout - co0) < 16 ? (t.conv.cout - co0) : 16;
+                ENDO_TRY(launch_wgrad_gemm(c, c.gparams + t.conv.w + (size_t)co0 * t.cin * 9, t.cin, nco, P.h[l], P.w[l], c.A16(bk), c.G16(bk),
+                                           g_groups, co0 / 8, PC_WGRAD_TRANS));
+            }
+            ENDO_TRY(c.release_buf(bk));
+        }
         return ENDO_OK;
     }
     ConvArgs a = base_args(c);
@@ -988,7 +1035,28 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
         w.g_h = H; w.g_w = W; w.oh = H; w.ow = W; w.B = B; w.G = P.G;
         w.dw = g_params + P.first.w; w.db = g_params + P.first.b; w.w_cin = cfg->in_channels;
         ENDO_TRY(c.fork());
-        if (cfg->in_channels == 3 && P.first.cout == 48 && !(tc_disable_mask() & 4096)) {
+        if (is_tc(c.math) && cfg->in_channels <= 8 && !(tc_disable_mask() & 4) && !(tc_disable_mask() & 262144)) {
+            // TMA -> tcgen05 GEMMs (net_wgrad3.cuh), 16 output channels per pass, over bf16 planes packed by two small kernels (all on the
+            // weight-gradient stream; the second one also yields the bias gradient).  ENDO_TC_DISABLE bit 262144: the FFMA kernel below
+            int bk = 0;
+            ENDO_TRY(c.acquire_buf(&bk));
+            const long long npix = (long long)B * H * W;
+            {
+                ProfScope prof(PC_WGRAD_TRANS, c.sw);
+                launch_pdl(tcwgrad3::image_pack16_kernel, 8 * kNumSMs, 256, 0, c.sw, x, c.A16(bk), B, cfg->in_channels, (long long)H * W);
+                ENDO_CHECK_LAUNCH();
+                launch_pdl(tcwgrad3::grad_pack16_kernel, dim3(2 * kNumSMs, cdiv(P.first.cout, 16)), 256, 0, c.sw, c.GX(0), c.X(0), c.AB(0), c.G16(bk),
+                           g_params + P.first.b, P.Ctot[0], P.offIn[0], P.first.cout, npix / P.G, P.G);
+                ENDO_CHECK_LAUNCH();
+            }
+            const int g_groups = (P.first.cout + 15) / 16 * 2;
+            for (int co0 = 0; co0 < P.first.cout; co0 += 16) {
+                const int nco = (P.first.cout - co0) < 16 ? (P.first.cout - co0) : 16;
+                ENDO_TRY(launch_wgrad_gemm(c, g_params + P.first.w + (size_t)co0 * cfg->in_channels * 9, cfg->in_channels, nco, H, W, c.A16(bk),
+                                           c.G16(bk), g_groups, co0 / 8, PC_WGRAD_TRANS));
+            }
+            ENDO_TRY(c.release_buf(bk));
+        } else if (cfg->in_channels == 3 && P.first.cout == 48 && !(tc_disable_mask() & 4096)) {
             ProfScope prof(PC_WGRAD_TRANS, c.sw);
             launch_pdl(first_wgrad_kernel, 4 * kNumSMs, FW_THREADS, 0, c.sw, w);
             ENDO_CHECK_LAUNCH();

@@ -220,6 +220,17 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         };
         for (int l = 0; l <= nd; ++l) for (auto& d : P.down[l]) need(d);
         for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) need(d);
+        for (int i = 0; i < nd; ++i) {           // TransitionUp convolutions: upsampled input / all output-gradient channels at the fine level
+            const long long px = 1ll * B * P.h[P.tu[i].dst_level] * P.w[P.tu[i].dst_level];
+            const long long a = 2 * px * ((P.tu[i].cin + 7) / 8 * 8), g = 2 * px * ((P.tu[i].conv.cout + 15) / 16 * 16);
+            if (a > a16) a16 = a;
+            if (g > g16) g16 = g;
+        }
+        {                                        // first convolution: 8-channel image planes, all output-gradient channels
+            const long long px = 1ll * B * H * W, g = 2 * px * ((P.first.cout + 15) / 16 * 16);
+            if (2 * px * 8 > a16) a16 = 2 * px * 8;
+            if (g > g16) g16 = g;
+        }
         for (int k = 0; k < 2; ++k) {
             P.a16_off[k] = off; off = align_up(off + a16, 256);
             P.g16_off[k] = off; off = align_up(off + g16, 256);

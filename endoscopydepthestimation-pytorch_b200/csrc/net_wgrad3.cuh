@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tma.cuh"
+#include "net_tc.cuh"
 
 namespace endo {
 namespace tcwgrad3 {
@@ -40,6 +41,8 @@ struct Args {
     int mblocks;                                      // M blocks (128 channels) per CTA
     int nstages, sets;
     int H, W, tiles_x, tiles_y, n_tiles, tiles_per_cta;
+    int g_grp0;                                       // first channel group of the gradient buffer (16-output-channel passes of the
+                                                      // TransitionUp / first convolutions: pass p reads groups 2p, 2p + 1)
 };
 
 __host__ __device__ inline int stage_bytes(int groups) { return groups * A_PLANE + G_BYTES; }
@@ -64,6 +67,91 @@ static inline bool make_map(CUtensorMap* map, const void* base, int B, int H, in
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ---- operand packers for the layers whose data-gradient kernel does not leave the by-products behind ----------------------
+// corrected output gradient G = g + A_c + B_c x (lazy BatchNorm term) of `Cout` channels of a level buffer -> plane-major bf16
+// [Cout/8][npix][8] (padding channels zero), and its per-channel sum = the conv bias gradient.  4 lanes per pixel and 16-channel
+// slice (blockIdx.y), HBM-bound.
+__global__ void __launch_bounds__(256)
+grad_pack16_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ ab, unsigned short* __restrict__ out,
+                   float* __restrict__ db, int C, int off, int Cout, long long npix_per_group, int G) {
+    pdl_enter();
+    const int c0 = 16 * blockIdx.y;
+    __shared__ float red[8][16];
+    const int grp = threadIdx.x & 3, ch = c0 + grp * 4;
+    const bool ch_ok = ch < Cout;
+    const size_t npix = (size_t)npix_per_group * G;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int gi = 0; gi < G; ++gi) {
+        float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
+        if (ch_ok) {
+            const float* abp = ab + ((size_t)gi * C + off + ch) * 2;
+            k0 = __ldg(reinterpret_cast<const float4*>(abp)); k1 = __ldg(reinterpret_cast<const float4*>(abp + 4));
+        }
+        for (long long p = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); p < npix_per_group; p += (long long)gridDim.x * 64) {
+            const size_t pp = (size_t)gi * npix_per_group + p;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ch_ok) {
+                const size_t o = pp * C + off + ch;
+                const float4 gq = __ldg(reinterpret_cast<const float4*>(g + o)), xq = __ldg(reinterpret_cast<const float4*>(x + o));
+                v.x = gq.x + fmaf(k0.y, xq.x, k0.x); v.y = gq.y + fmaf(k0.w, xq.y, k0.z);
+                v.z = gq.z + fmaf(k1.y, xq.z, k1.x); v.w = gq.w + fmaf(k1.w, xq.w, k1.z);
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            *reinterpret_cast<uint2*>(out + ((size_t)(ch >> 3) * npix + pp) * 8 + (ch & 7)) =
+                make_uint2(tcwgrad_pack_bf16(v.x, v.y), tcwgrad_pack_bf16(v.z, v.w));
+        }
+    }
+    if (!db) return;
+#pragma unroll
+    for (int o2 = 4; o2 < 32; o2 <<= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, o2); s.y += __shfl_xor_sync(0xffffffffu, s.y, o2);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, o2); s.w += __shfl_xor_sync(0xffffffffu, s.w, o2);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 4) { red[warp][lane * 4] = s.x; red[warp][lane * 4 + 1] = s.y; red[warp][lane * 4 + 2] = s.z; red[warp][lane * 4 + 3] = s.w; }
+    __syncthreads();
+    if (threadIdx.x < 16 && c0 + threadIdx.x < Cout) {
+        float t = 0.f;
+        for (int wq = 0; wq < 8; ++wq) t += red[wq][threadIdx.x];
+        atomicAdd(db + c0 + threadIdx.x, t);
+    }
+}
+
+// NCHW input images (<= 8 channels) -> plane-major bf16 [1][npix][8], channels past Cimg zero (operand of the first convolution's
+// weight gradient, models.py:111-113)
+__global__ void __launch_bounds__(256)
+image_pack16_kernel(const float* __restrict__ img, unsigned short* __restrict__ out, int B, int Cimg, long long hw) {
+    pdl_enter();
+    const long long total = (long long)B * hw;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long b = i / hw, p = i - b * hw;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = c < Cimg ? __ldg(img + ((size_t)b * Cimg + c) * hw + p) : 0.f;
+        *reinterpret_cast<uint4*>(out + (size_t)i * 8) = make_uint4(tcwgrad_pack_bf16(v[0], v[1]), tcwgrad_pack_bf16(v[2], v[3]),
+                                                                    tcwgrad_pack_bf16(v[4], v[5]), tcwgrad_pack_bf16(v[6], v[7]));
+    }
+}
+
+// nearest-neighbour x2 upsampling (models.py:73) of `cin` channels of a half-resolution level buffer -> plane-major bf16
+// [cin/8][B*H*W][8] at the FULL resolution (operand of the TransitionUp convolution's weight gradient); thread = (pixel, group)
+__global__ void __launch_bounds__(256)
+upsample_pack16_kernel(const float* __restrict__ src, int srcC, int src_off, int cin, unsigned short* __restrict__ out, int B, int H, int W) {
+    pdl_enter();
+    const int ng = cin >> 3;
+    const size_t npix = (size_t)B * H * W;
+    const long long total = (long long)npix * ng;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int gq = (int)(i % ng);
+        const size_t p = (size_t)(i / ng);
+        const int x = (int)(p % W), y = (int)((p / W) % H), b = (int)(p / ((size_t)W * H));
+        const float* sp = src + (((size_t)b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) * srcC + src_off + gq * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sp)), c = __ldg(reinterpret_cast<const float4*>(sp + 4));
+        *reinterpret_cast<uint4*>(out + ((size_t)gq * npix + p) * 8) = make_uint4(tcwgrad_pack_bf16(a.x, a.y), tcwgrad_pack_bf16(a.z, a.w),
+                                                                                  tcwgrad_pack_bf16(c.x, c.y), tcwgrad_pack_bf16(c.z, c.w));
+    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -114,7 +202,7 @@ dense_wgrad_gemm_kernel(const Args A, const __grid_constant__ CUtensorMap amap, 
                 unsigned char* gs = st + (size_t)A.groups * A_PLANE;
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap)
-                    tma::load_4d(gs + tap * 2 * G_PLANE, &gmap, (x0 - (tap % 3 - 1)) * 8, y0 - (tap / 3 - 1), b, 0, full + s);
+                    tma::load_4d(gs + tap * 2 * G_PLANE, &gmap, (x0 - (tap % 3 - 1)) * 8, y0 - (tap / 3 - 1), b, A.g_grp0, full + s);
                 tc::mbar_arrive(full + s);
             }
         }
