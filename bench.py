@@ -148,12 +148,18 @@ def conv_bytes_per_image(h, w):
     activations (Cin) + output gradient (Cout).  Pooled / upsampled sides are counted at their own resolution."""
     g, first = 12, 48
     by = {k: 0.0 for k in ("conv_dense_fwd", "conv_dense_dgrad", "conv_dense_wgrad", "conv_trans_fwd", "conv_trans_dgrad",
-                           "conv_trans_wgrad")}
+                           "conv_trans_wgrad", "design_dense_dgrad", "design_dense_wgrad")}
 
     def dense(cin, px):
         by["conv_dense_fwd"] += 4.0 * (cin + g) * px
         by["conv_dense_dgrad"] += 4.0 * (3 * cin + g) * px
         by["conv_dense_wgrad"] += 4.0 * (cin + g) * px
+        # what the round-2b kernels are DESIGNED to move (DESIGN.md section 4): the data-gradient kernel also writes the bf16
+        # operands of the weight-gradient GEMM (relu(bn(x)), cin rounded to 8 channels, and the 16-channel corrected gradient),
+        # which then reads those 2-byte planes instead of the fp32 buffers
+        c8 = (cin + 7) // 8 * 8
+        by["design_dense_dgrad"] += (4.0 * (3 * cin + g) + 2.0 * c8 + 2.0 * 16) * px
+        by["design_dense_wgrad"] += (2.0 * c8 + 2.0 * 16) * px
 
     by["conv_trans_fwd"] += 4.0 * (3 + first) * h * w                       # firstconv (no data gradient: images need none)
     by["conv_trans_wgrad"] += 4.0 * (3 + first) * h * w
@@ -467,7 +473,13 @@ def kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg=N
     dominant = max(work_flops, key=lambda k: cat_ms.get(k, 0.0))
     dom_ms = cat_ms[dominant]
     dom_launches = max(cat_n[dominant], 1)
-    achieved_gbs = work_bytes[dominant] / (dom_ms * 1e-3) / 1e9
+    # the dense backward kernels are judged on the bytes THIS design moves (by-product planes included), the layer-by-layer fp32
+    # model of round 1 is kept beside it (frac_layer_model) so that rounds stay comparable
+    design = {"conv_dense_dgrad": "design_dense_dgrad", "conv_dense_wgrad": "design_dense_wgrad"}
+    use_design = math_mode != "fp32" and not (int(os.environ.get("ENDO_TC_DISABLE", "0")) & 262144)
+    dom_bytes = work_bytes[design[dominant]] if (use_design and dominant in design) else work_bytes[dominant]
+    layer_model_gbs = work_bytes[dominant] / (dom_ms * 1e-3) / 1e9
+    achieved_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9
     achieved_tf = work_flops[dominant] / (dom_ms * 1e-3) / 1e12
     kind = {"fp32": "fp32 FFMA implicit-GEMM kernels (strict-parity path, no tensor pipe)",
             "tf32": "tcgen05 kernels, tf32 / bf16 operands, fp32 accumulate in TMEM",
@@ -477,12 +489,15 @@ def kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg=N
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " (copy bandwidth)",
                 "launches_per_step": dom_launches, "avg_launch_ms": dom_ms / dom_launches,
-                "algorithmic_bytes_per_launch_avg": work_bytes[dominant] / dom_launches,
+                "algorithmic_bytes_per_launch_avg": dom_bytes / dom_launches,
+                "frac_layer_model": layer_model_gbs / peaks["hbm_gbs"],
                 "tensor": {"achieved": achieved_tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                            "frac": achieved_tf / peaks["bf16_tflops_sustained"],
                            "note": "algorithmic conv FLOPs of the class over the same time, against the measured dense bf16 peak"},
-                "note": kind + "; algorithmic bytes = layer-by-layer operand stream (conv_bytes_per_image), time = sum of the "
-                        "class's launches in one step (CUDA events on the launching stream)",
+                "note": kind + "; algorithmic bytes = the operand stream the kernel is designed to move (conv_bytes_per_image: the "
+                        "layer-by-layer fp32 stream, plus -- dense data gradient -- the bf16 operand planes it writes for the "
+                        "weight-gradient GEMM; frac_layer_model = the round-1 model without them), time = sum of the class's "
+                        "launches in one step (CUDA events on the launching stream)",
                 "share_of_step": dom_ms / max(sum(cat_ms.values()), 1e-9)}
     # dram__bytes_read + dram__bytes_write per launch of the dominant class from the committed `ncu --set full` capture of
     # THIS round's tree (profiles/ncu_traffic.json, written by tools/summarize_ncu.py): same launch as `traffic_of.launch`,
@@ -502,6 +517,18 @@ def kernel_breakdown(model, resident, h, w, bsz, peaks, barrier, math_mode, pg=N
         if cat_ms.get(k, 0.0) > 0:
             gbs = byts / (cat_ms[k] * 1e-3) / 1e9
             kernels[k].update({"algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4)})
+            if use_design and k in design:
+                dg = work_bytes[design[k]] / (cat_ms[k] * 1e-3) / 1e9
+                kernels[k].update({"frac_layer_model": kernels[k]["frac_of_hbm_peak"], "design_GBps": round(dg, 1),
+                                   "frac_of_hbm_peak": round(dg / peaks["hbm_gbs"], 4)})
+    if use_design and all(cat_ms.get(k, 0.0) > 0 for k in design):
+        # data gradient + weight gradient of the DenseLayers as ONE unit of work: the by-product planes move bytes from the second
+        # kernel to the first, so only the sum compares across designs (layer-by-layer fp32 model over the summed time)
+        t = sum(cat_ms[k] for k in design)
+        gbs = sum(work_bytes[k] for k in design) / (t * 1e-3) / 1e9
+        kernels["conv_dense_bwd_combined"] = {"ms_per_step": round(t, 4), "algorithmic_GBps": round(gbs, 1),
+                                              "frac_of_hbm_peak": round(gbs / peaks["hbm_gbs"], 4),
+                                              "note": "conv_dense_dgrad + conv_dense_wgrad, layer-by-layer fp32 byte model"}
     for k, fl in work_flops.items():
         if cat_ms.get(k, 0.0) > 0:
             kernels[k].update({"TFLOPps": round(fl / (cat_ms[k] * 1e-3) / 1e12, 2)})

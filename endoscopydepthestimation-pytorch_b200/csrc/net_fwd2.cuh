@@ -30,9 +30,9 @@ using tcconv::tf32_hi; using tcconv::bf16x2_rn;
 constexpr int TH = 16, TW = 32, PITCH = 34;
 constexpr int HALO_ROWS = PITCH * (TH + 2);              // 612 halo-tile pixels
 constexpr int MBLK = 5;                                  // ceil(TH * PITCH / 128)
-constexpr int PLANE_ROWS = 714;                          // >= 34 + 5*128 + 34 ; 714*16 % 128 == 32 (bank spread)
-constexpr int PLANE_BYTES = PLANE_ROWS * 16;             // 11,424
-constexpr int A_STAGE = 4 * PLANE_BYTES;                 // 45,696: hi0 | hi1 | lo | x
+constexpr int PLANE_ROWS = 716;                          // >= 34 + 5*128 + 34 ; 716*16 % 128 == 64: the two hi planes a warp stores to (lane parity) fall in disjoint bank halves
+constexpr int PLANE_BYTES = PLANE_ROWS * 16;             // 11,456
+constexpr int A_STAGE = 4 * PLANE_BYTES;                 // 45,824: hi0 | hi1 | lo | x
 constexpr int NB = 48;
 constexpr int B_BLOCK = 2 * NB * 16;                     // 1,536
 constexpr int B_STAGE = 6 * B_BLOCK;                     // 9,216 = one packed weight chunk (pack_w_fwd_all_kernel, mode 1)
@@ -46,16 +46,16 @@ constexpr int NUNITS = MBLK * 4;
 // shared-memory map
 constexpr int RAW_OFF = 0;
 constexpr int A_OFF = RAW_OFF + NRAW * RAW_BYTES;        // 78,336
-constexpr int B_OFF = A_OFF + 2 * A_STAGE;               // 169,728
-constexpr int OUT_OFF = B_OFF + 2 * B_STAGE;             // 188,160 (128-byte aligned: TMA store source)
+constexpr int B_OFF = A_OFF + 2 * A_STAGE;               // 169,984
+constexpr int OUT_OFF = B_OFF + 2 * B_STAGE;             // 188,416 (128-byte aligned: TMA store source)
 constexpr int OUT_BYTES = TH * TW * OUT_MAXN * 4;        // 32,768 (N = 12: 24,576 used)
-constexpr int COEF_OFF = OUT_OFF + OUT_BYTES;            // 220,928
-constexpr int EDGE_OFF = COEF_OFF + COEF_MAX * 16;       // 227,072
+constexpr int COEF_OFF = OUT_OFF + OUT_BYTES;            // 221,184
+constexpr int EDGE_OFF = COEF_OFF + COEF_MAX * 16;       // 227,328
 constexpr int EDGE_BYTES = NUNITS * 2 * 16 * 4;          // 2,560
-constexpr int RED_OFF = EDGE_OFF + EDGE_BYTES;           // 229,632
+constexpr int RED_OFF = EDGE_OFF + EDGE_BYTES;           // 229,888
 constexpr int RED_BYTES = 4 * 16 * 2 * 4;                // 512
-constexpr int BAR_OFF = RED_OFF + RED_BYTES;             // 230,144
-constexpr int SMEM_BYTES = BAR_OFF + 256;                // 230,400 <= 232,448
+constexpr int BAR_OFF = RED_OFF + RED_BYTES;             // 230,400
+constexpr int SMEM_BYTES = BAR_OFF + 256;                // 230,656 <= 232,448
 constexpr int NPROD = 512;
 constexpr int NTHREADS = NPROD + 64 + 128;               // 16 transform warps + MMA warp + TMA warp + 4 epilogue warps
 

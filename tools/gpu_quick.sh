@@ -10,5 +10,5 @@ d=json.load(open('gpurun_out/${TAG}_bench.json'))
 print('value',d['value'],'ms',d['ms_per_step'],'launches/step',d.get('gpu_launches_per_step'),'loss',d['config']['loss'])
 print('e2e',d['e2e']['value'],d['e2e']['ms_per_step'],'modules',d['e2e']['modules_as_train_py']['value'])
 for k,v in d['kernels'].items(): print('  %-18s %8.3f ms  %s'%(k,v['ms_per_step'],v.get('frac_of_hbm_peak')))
-print('sum', sum(v['ms_per_step'] for v in d['kernels'].values()))
+print('sum', sum(v['ms_per_step'] for k,v in d['kernels'].items() if 'combined' not in k))
 PY

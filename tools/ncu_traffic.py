@@ -11,7 +11,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = 16 * 256 * 320                     # pixels of the captured launch: both images of 8 pairs at 256x320
 CIN, COUT = 180, 12
-ALG = {"conv_dense_dgrad": 4.0 * (3 * CIN + COUT) * P, "conv_dense_wgrad": 4.0 * (CIN + COUT) * P,
+C8 = (CIN + 7) // 8 * 8
+# the same per-launch figures as bench.py's conv_bytes_per_image (design_* entries for the two backward kernels: the data
+# gradient also writes the bf16 operand planes, the weight-gradient GEMM reads them)
+ALG = {"conv_dense_dgrad": (4.0 * (3 * CIN + COUT) + 2.0 * C8 + 2.0 * 16) * P, "conv_dense_wgrad": (2.0 * C8 + 2.0 * 16) * P,
        "conv_dense_fwd": 4.0 * (CIN + COUT) * P}
 out = {}
 for arg in sys.argv[1:]:
