@@ -96,7 +96,10 @@ static int launch_wgrad2(WgradArgs a, cudaStream_t s) {
 
 // ENDO_TC_DISABLE (bit mask, debugging / A-B tests only): 1 = forward, 2 = data gradient, 4 = weight gradient fall back
 // to the FFMA kernels even when the math mode asks for tensor cores (8/16/32/64: transition layers); 128 = no split-K
-// in the FFMA DenseLayer forward.
+// in the FFMA DenseLayer forward; 8192 = no side stream; 16384 / 32768 = round-1 weight-gradient / forward kernels;
+// 65536 = TransitionDown max-pool as a separate pass; 131072 = TransitionDown weight gradient through the 1x1 mode of the
+// DenseLayer kernel; 262144 = DenseLayer / TransitionUp / first-convolution weight gradients through the round-2a kernels
+// (no bf16 by-product planes).  ENDO_PDL=0: no programmatic dependent launch.
 static int tc_debug_mask() {
     const char* e = getenv("ENDO_TC_DEBUG");
     return e ? atoi(e) : 0;
@@ -115,10 +118,11 @@ static inline int x3_mode(int math) {
     return math == ENDO_MATH_TF32X3 ? 1 : (math == ENDO_MATH_BF16X3 ? 2 : (math == ENDO_MATH_BF16 ? 3 : 0));
 }
 
-// Weight-gradient kernels only feed the optimiser, and a layer's weight gradient is independent of the same layer's data
-// gradient: they are enqueued on a side stream (forked from / joined to the caller's stream with events) so that
-// the CTAs of one kernel fill the SMs the other leaves idle in its last wave and prologue (every tensor-core kernel here
-// occupies a whole SM per CTA; 5-30 % of a launch is tail).  ENDO_NET_SINGLE_STREAM (math flag) or ENDO_TC_DISABLE bit 8192
+// Weight-gradient kernels only feed the optimiser: they are enqueued on a side stream (forked from / joined to the caller's
+// stream with events) so that the CTAs of one kernel fill the SMs the other leaves idle in its last wave and prologue (every
+// tensor-core kernel here occupies a whole SM per CTA; 5-30 % of a launch is tail).  The GEMM weight-gradient kernels consume
+// bf16 operand planes that the data-gradient kernel of the same layer writes: two plane sets alternate, Ctx::acquire_buf /
+// release_buf order "GEMM of layer i has read set k" before "data gradient of layer i-2 rewrites set k" with events.  ENDO_NET_SINGLE_STREAM (math flag) or ENDO_TC_DISABLE bit 8192
 // keeps everything on the caller's stream.
 //
 // Re-entrancy: a call BORROWS a (stream, fork event, join event) triple from a per-device pool for the duration of its
