@@ -99,7 +99,7 @@ static int launch_wgrad2(WgradArgs a, cudaStream_t s) {
 // in the FFMA DenseLayer forward; 8192 = no side stream; 16384 / 32768 = round-1 weight-gradient / forward kernels;
 // 65536 = TransitionDown max-pool as a separate pass; 131072 = TransitionDown weight gradient through the 1x1 mode of the
 // DenseLayer kernel; 262144 = DenseLayer / TransitionUp / first-convolution weight gradients through the round-2a kernels
-// (no bf16 by-product planes).  ENDO_PDL=0: no programmatic dependent launch.
+// (no bf16 by-product planes); 524288 = first convolution forward on the FFMA kernel.  ENDO_PDL=0: no programmatic dependent launch.
 static int tc_debug_mask() {
     const char* e = getenv("ENDO_TC_DEBUG");
     return e ? atoi(e) : 0;
@@ -289,6 +289,11 @@ static int pack_all(const Ctx& c, bool bwd, int per, int mode, K kern, unsigned 
             add(t.conv.w + (long long)q * 16 * t.cin * 9, t.cin, n, bwd ? t.wpb_off[q] : t.wp_off[q]);
         }
     }
+    if (!bwd && P.first.cout <= 128)                     // first convolution (forward on the persistent kernel, 16 output channels per pass)
+        for (int q = 0; q * 16 < P.first.cout; ++q) {
+            const int n = (P.first.cout - q * 16) < 16 ? (P.first.cout - q * 16) : 16;
+            add(P.first.w + (long long)q * 16 * P.cfg.in_channels * 9, P.cfg.in_channels, n, P.first_wp_off[q]);
+        }
     if (rc != ENDO_OK) return rc;
     return flush();
 }
@@ -951,7 +956,36 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
     const int nd = cfg->n_down;
     // statistics accumulate with atomics: clear them
     ENDO_CUDA(cudaMemsetAsync(c.acts + P.stat_off[0], 0, (size_t)(P.mi_off[0] - P.stat_off[0]), c.s));
-    {   // firstconv 3x3 in_channels -> first_conv_channels on the NCHW input (models.py:111-113, :172)
+    if (is_tc(math)) ENDO_TRY(pack_dense_weights_fwd(c));
+    const int tx2 = cdiv(W, tcfwd2::TW), ty2 = cdiv(H, tcfwd2::TH), n2 = tx2 * ty2 * B;
+    if (x3_mode(math) == 1 && cfg->in_channels <= 8 && P.first.cout <= 128 && !(P.first.cout & 3) && n2 >= 4 * kNumSMs &&
+        32ll * B * H * W <= P.tdtmp_bytes && !(tc_disable_mask() & 524288)) {
+        // firstconv on the persistent 3xTF32 kernel (net_fwd2.cuh), 16 output channels per pass: the NCHW images are repacked once
+        // to NHWC with 8 channels (into the TransitionDown scratch, idle until the backward) so that TMA boxes can fetch them;
+        // ENDO_TC_DISABLE bit 524288: the FFMA kernel below (0.45 ms instead of 0.16 ms at 16 x 256x320)
+        float* x8 = reinterpret_cast<float*>(c.acts + P.tdtmp_off);
+        {
+            ProfScope prof(PC_CONV_TRANS_FWD, c.s);
+            launch_pdl(tcfwd2::nchw_to_nhwc8_kernel, 8 * kNumSMs, 256, 0, c.s, x, x8, B, cfg->in_channels, (long long)H * W);
+            ENDO_CHECK_LAUNCH();
+        }
+        for (int co0 = 0; co0 < P.first.cout; co0 += 16) {
+            tcfwd2::Args f;
+            f.coef = nullptr; f.bias = params + P.first.b + co0; f.stats = c.ST(0);
+            f.wpack = reinterpret_cast<const float*>(c.acts + P.wpack_off + P.first_wp_off[co0 / 16]);
+            f.in_off = 0; f.K = 8; f.out_off = P.offIn[0] + co0; f.N = (P.first.cout - co0) < 16 ? (P.first.cout - co0) : 16;
+            f.H = H; f.W = W; f.B = B; f.G = P.G; f.stats_C = P.Ctot[0]; f.tiles_x = tx2; f.tiles_y = ty2; f.n_tiles = n2;
+            f.up = 0; f.dbg = 0;
+            CUtensorMap in_map, out_map;
+            if (!tma::make_nhwc_map(&in_map, x8, B, H, W, 8, 8, tcfwd2::PITCH, tcfwd2::TH + 2) ||
+                !tma::make_nhwc_map(&out_map, c.X(0), B, H, W, P.Ctot[0], f.N, tcfwd2::TW, tcfwd2::TH))
+                return ENDO_ERR_CUDA;
+            ENDO_SET_MAX_SMEM(tcfwd2::dense_fwd_x3_persistent_kernel, tcfwd2::SMEM_BYTES);
+            ProfScope prof(PC_CONV_TRANS_FWD, c.s);
+            launch_pdl(tcfwd2::dense_fwd_x3_persistent_kernel, n2 < kNumSMs ? n2 : kNumSMs, tcfwd2::NTHREADS, tcfwd2::SMEM_BYTES, c.s, f, in_map, out_map);
+            ENDO_CHECK_LAUNCH();
+        }
+    } else {   // firstconv 3x3 in_channels -> first_conv_channels on the NCHW input (models.py:111-113, :172)
         ConvArgs a = base_args(c);
         a.in = x; a.K = cfg->in_channels; a.ih = H; a.iw = W;
         a.w = params + P.first.w; a.bias = params + P.first.b; a.w_cin = cfg->in_channels;
@@ -959,7 +993,6 @@ extern "C" int endo_net_fwd(const endo_net_config* cfg, const float* x, const fl
         a.stats = c.ST(0); a.stats_C = P.Ctot[0];
         ENDO_TRY((launch_conv<3, 2, 48, 8, LM_NCHW, EM_STORE, WM_FWD, false>(a, c.s)));
     }
-    if (is_tc(math)) ENDO_TRY(pack_dense_weights_fwd(c));
     for (int l = 0; l < nd; ++l) {                           // models.py:175-178
         for (const auto& d : P.down[l]) ENDO_TRY(dense_layer_fwd(c, d));
         ENDO_TRY(trans_down_fwd(c, l));

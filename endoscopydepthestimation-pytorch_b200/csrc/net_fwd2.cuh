@@ -78,6 +78,23 @@ struct Args {
 #define F2_TRACE(slot) do { } while (0)
 #endif
 
+// NCHW images (<= 8 channels) -> NHWC fp32 with 8 channels (zeros past Cimg): the operand of the first convolution
+// (models.py:111-113) in the layout the TMA boxes of the kernel below want
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc8_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int Cimg, long long hw) {
+    pdl_enter();
+    const long long total = (long long)B * hw;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long b = i / hw, p = i - b * hw;
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = c < Cimg ? __ldg(img + ((size_t)b * Cimg + c) * hw + p) : 0.f;
+        float4* o = reinterpret_cast<float4*>(out + (size_t)i * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -96,6 +113,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
     __shared__ float s_bias[16];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool bn = !A.up && A.coef != nullptr;              // coef == nullptr: the operand is used as it is (first convolution)
     const int nchunks = (A.K + 7) >> 3;
     const int my_tiles = ((int)blockIdx.x < A.n_tiles) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int per_img = A.tiles_x * A.tiles_y;
@@ -137,7 +155,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
             int b, y0, x0;
             tile_origin(k, b, y0, x0);
             const int g = b / per_group;
-            if (g != cur_g && !A.up) {
+            if (g != cur_g && bn) {
                 // (a, beta, mean, invstd) of every input channel of this statistic group.  The table is only read by these 512
                 // threads, between their own barriers: safe to rewrite when the group changes (tiles are visited in image order).
                 asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -159,7 +177,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                 const int ch = c * 8 + quad * 4;
                 const bool ch_ok = ch < A.K;
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0, k2 = k0, k3 = k0;   // (a, beta, mean, invstd) x 4 channels
-                if (ch_ok && !A.up) {
+                if (ch_ok && bn) {
                     const float* cf = coef_s + ch * 4;
                     k0 = *reinterpret_cast<const float4*>(cf); k1 = *reinterpret_cast<const float4*>(cf + 4);
                     k2 = *reinterpret_cast<const float4*>(cf + 8); k3 = *reinterpret_cast<const float4*>(cf + 12);
@@ -197,7 +215,7 @@ dense_fwd_x3_persistent_kernel(const Args A, const __grid_constant__ CUtensorMap
                     const int i = tid + NPROD * r3;
                     const int px = i >> 1;
                     float4 v = v3[r3];
-                    if (!A.up) {
+                    if (bn) {
                         v.x = fmaxf(fmaf(k0.x, v.x - k0.z, k0.y), 0.f); v.y = fmaxf(fmaf(k1.x, v.y - k1.z, k1.y), 0.f);
                         v.z = fmaxf(fmaf(k2.x, v.z - k2.z, k2.y), 0.f); v.w = fmaxf(fmaf(k3.x, v.w - k3.z, k3.y), 0.f);
                     }

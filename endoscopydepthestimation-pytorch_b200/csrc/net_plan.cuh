@@ -47,6 +47,7 @@ struct NetPlan {
     long long stat_off[kMaxLevels];             // double [G][Ctot][2]  (sum, sumsq)
     long long mi_off[kMaxLevels];               // float  [G][Ctot][2]  (mean, invstd)
     long long pre_off;                          // float  [B*H*W] finalConv output before abs
+    long long first_wp_off[8];                  // weight images of the first convolution's 16-output-channel passes (tensor-core forward)
     long long wpack_off;                        // sized for the widest layer: tensor-core weight image of the layer being run (forward)
     long long tdtmp_off, tdtmp_bytes;           // forward scratch: float [B,h,w,Cs] TransitionDown conv output before pooling (tensor-core
                                                 // path, largest level); split-K partial sums of low-resolution DenseLayers
@@ -192,6 +193,7 @@ static inline int build_plan(const endo_net_config* c, int B, int H, int W, int 
         for (int i = 0; i < nd; ++i) for (auto& d : P.up[i]) slot(d);
         for (int i = 0; i < nd; ++i)
             for (int q = 0; q < 8; ++q) { P.tu[i].wp_off[q] = sz; if (q * 16 < P.tu[i].conv.cout) sz += 9216ll * ((P.tu[i].cin + 7) / 8); }
+        for (int q = 0; q < 8; ++q) { P.first_wp_off[q] = sz; if (q * 16 < P.first.cout) sz += 9216ll * ((c->in_channels + 7) / 8); }
         P.wpack_off = off; off = align_up(off + sz, 256);
     }
     {
