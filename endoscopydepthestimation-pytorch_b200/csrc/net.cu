@@ -454,13 +454,14 @@ static int launch_wgrad_tc(tcwgrad::Args t, int cin, cudaStream_t s, int cat) {
 // weight-gradient stream: act16 = [ceil(Cin/8)][B*H*W][8] activations, g16 = [g_groups][B*H*W][8] output gradient of which the
 // two groups from g_grp0 (16 output channels) are used; dw = OIHW block of those output channels
 static int launch_wgrad_gemm(const Ctx& c, float* dw, int Cin, int Cout, int H, int W, const unsigned short* a16, const unsigned short* g16,
-                             int g_groups, int g_grp0, int cat) {
+                             int g_groups, int g_grp0, int cat, bool swap = false) {
     const NetPlan& P = c.P;
-    const int c8 = (Cin + 7) / 8 * 8;
+    // swap (Cin <= 8, Cout <= 128): the gradient planes are the M operand, ALL output channels in one pass (net_wgrad3.cuh)
+    const int c8 = swap ? g_groups * 8 : (Cin + 7) / 8 * 8;      // channels of the M operand
     tcwgrad3::Args g{};
-    g.dw = dw; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.g_grp0 = g_grp0;
+    g.dw = dw; g.Cin = Cin; g.Cout = Cout; g.H = H; g.W = W; g.g_grp0 = g_grp0; g.swap = swap ? 1 : 0;
     g.tiles_x = cdiv(W, tcwgrad3::TW); g.tiles_y = cdiv(H, tcwgrad3::TR); g.n_tiles = g.tiles_x * g.tiles_y * P.B;
-    const int mb_all = cdiv(Cin, 128);
+    const int mb_all = cdiv(swap ? Cout : Cin, 128);
     int ny = 1;
     g.groups = c8 / 8; g.mblocks = mb_all;
     // few tiles, or two stages of all channel groups would not fit: one 128-channel block per CTA
@@ -476,8 +477,12 @@ static int launch_wgrad_gemm(const Ctx& c, float* dw, int Cin, int Cout, int H, 
     const int ctas = kNumSMs < g.n_tiles ? kNumSMs : g.n_tiles;
     g.tiles_per_cta = cdiv(g.n_tiles, ctas);
     CUtensorMap amap, gmap;
-    if (!tcwgrad3::make_map(&amap, a16, P.B, H, W, tcwgrad3::TR, c8 / 8, g.groups) ||
-        !tcwgrad3::make_map(&gmap, g16, P.B, H, W, tcwgrad3::TR, g_groups, 2))
+    if (swap) {
+        if (!tcwgrad3::make_map(&amap, g16, P.B, H, W, tcwgrad3::TR, g_groups, g.groups) ||
+            !tcwgrad3::make_map(&gmap, a16, P.B, H, W, tcwgrad3::TR, 1, 2))
+            return ENDO_ERR_CUDA;
+    } else if (!tcwgrad3::make_map(&amap, a16, P.B, H, W, tcwgrad3::TR, c8 / 8, g.groups) ||
+               !tcwgrad3::make_map(&gmap, g16, P.B, H, W, tcwgrad3::TR, g_groups, 2))
         return ENDO_ERR_CUDA;
     ENDO_SET_MAX_SMEM(tcwgrad3::dense_wgrad_gemm_kernel, tcwgrad3::SMEM_LIMIT);
     ProfScope prof(cat, c.sw);
@@ -1087,6 +1092,10 @@ extern "C" int endo_net_bwd(const endo_net_config* cfg, const float* g_y, const 
                 ENDO_CHECK_LAUNCH();
             }
             const int g_groups = (P.first.cout + 15) / 16 * 2;
+            if (P.first.cout <= 128) {                       // operands swapped: all output channels in one pass (this tail is not overlapped)
+                ENDO_TRY(launch_wgrad_gemm(c, g_params + P.first.w, cfg->in_channels, P.first.cout, H, W, c.A16(bk), c.G16(bk), g_groups, 0,
+                                           PC_WGRAD_TRANS, true));
+            } else
             for (int co0 = 0; co0 < P.first.cout; co0 += 16) {
                 const int nco = (P.first.cout - co0) < 16 ? (P.first.cout - co0) : 16;
                 ENDO_TRY(launch_wgrad_gemm(c, g_params + P.first.w + (size_t)co0 * cfg->in_channels * 9, cfg->in_channels, nco, H, W, c.A16(bk),

@@ -43,6 +43,11 @@ struct Args {
     int H, W, tiles_x, tiles_y, n_tiles, tiles_per_cta;
     int g_grp0;                                       // first channel group of the gradient buffer (16-output-channel passes of the
                                                       // TransitionUp / first convolutions: pass p reads groups 2p, 2p + 1)
+    int swap;                                         // 1: operands swapped (first convolution, Cin <= 8 and Cout <= 128): the M operand
+                                                      // (`amap`) holds the GRADIENT planes (rows = co, no halo), the nine shifted boxes
+                                                      // are taken from the ACTIVATION planes (`gmap`, one real group; the second group of
+                                                      // a box is out of bounds = zeros): all output channels in ONE pass instead of
+                                                      // Cout/16, D[co][tap * 16 + ci] with tap (ty, tx) = weight tap (2 - ty, 2 - tx)
 };
 
 __host__ __device__ inline int stage_bytes(int groups) { return groups * A_PLANE + G_BYTES; }
@@ -257,7 +262,13 @@ dense_wgrad_gemm_kernel(const Args A, const __grid_constant__ CUtensorMap amap, 
 #pragma unroll
                             for (int j = 0; j < 16; ++j) v[j] += w[j];
                         }
-                        if (ci < A.Cin) {
+                        if (A.swap) {
+                            if (ci < A.Cout) {                                   // the lane owns an OUTPUT channel, the 16 columns are ci
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (j < A.Cin) atomicAdd(A.dw + (((size_t)ci * A.Cin + j) * 3 + (2 - ky)) * 3 + (2 - kx), v[j]);
+                            }
+                        } else if (ci < A.Cin) {
 #pragma unroll
                             for (int co = 0; co < 16; ++co)
                                 if (co < A.Cout) atomicAdd(A.dw + (((size_t)co * A.Cin + ci) * 3 + ky) * 3 + kx, v[co]);
