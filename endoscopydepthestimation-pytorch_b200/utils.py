@@ -79,3 +79,23 @@ def get_torch_training_data(pair_extrinsics, pair_projections, pair_indexes, poi
                                         flow.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(device)), "rasterize_pair")
     out = (depth_mask, depth, flow_mask, flow)
     return out if return_tensor else tuple(o.cpu().numpy() for o in out)
+
+
+def generating_pos_and_increment(idx, visible_view_indexes, adjacent_range):
+    """`utils.generating_pos_and_increment` (utils.py:410-438), the pair sampler in front of the rasteriser: host logic, kept
+    call-for-call compatible with the reference's use of the `random` module (same draws in the same order, so a seeded
+    DataLoader worker yields the same pairs).  Returns [position in the visible-view list, signed offset of the partner]."""
+    import random
+    n = len(visible_view_indexes)
+    pos = idx % n
+    lo, hi = adjacent_range[0], adjacent_range[1]
+    if n <= 2 * lo:                      # short sequence: shrink the minimum distance (utils.py:418-419)
+        lo = n // 2
+    forward_room, backward_room = min(hi, n - 1 - pos), min(hi, pos)
+    if pos < lo:                         # too close to the start: the partner lies ahead
+        return [pos, random.randint(lo, forward_room)]
+    if pos >= n - lo:                    # too close to the end: the partner lies behind
+        return [pos, -random.randint(lo, backward_room)]
+    if random.randint(0, 1) == 1:        # interior: a coin decides the direction
+        return [pos, random.randint(lo, forward_room)]
+    return [pos, -random.randint(lo, backward_room)]

@@ -41,7 +41,8 @@ def reference_function(name, path=REF + "/utils.py"):
     import ast
     src = open(path).read()
     node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
-    ns = {"np": np}
+    import random
+    ns = {"np": np, "random": random}
     exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return ns[name]
 
@@ -79,8 +80,26 @@ def record_raster():
     np.savez_compressed(os.path.join(OUT, "raster_a.npz"), **out)
 
 
+def record_sampler():
+    """utils.generating_pos_and_increment (utils.py:410-438), the pair sampler in front of the rasteriser: seeded `random`, a sweep
+    of sequence lengths / adjacent ranges / indexes incl. the short-sequence clamp (utils.py:418-419) and both edge branches."""
+    import random
+    fn = reference_function("generating_pos_and_increment")
+    cases, out = [], []
+    for n, rng in ((60, (5, 20)), (12, (5, 20)), (9, (5, 20)), (3, (1, 2)), (200, (1, 50)), (31, (10, 10))):
+        views = list(range(100, 100 + 3 * n, 3))
+        for idx in list(range(0, n, max(1, n // 12))) + [n - 1, n, 5 * n + 7]:
+            for seed in (0, 1, 2):
+                random.seed(1000 * seed + idx)
+                pos, inc = fn(idx, views, list(rng))
+                cases.append((n, rng[0], rng[1], idx, seed))
+                out.append((pos, inc))
+    np.savez_compressed(os.path.join(OUT, "sampler_a.npz"), cases=np.array(cases, dtype=np.int64), out=np.array(out, dtype=np.int64))
+    print("sampler_a", len(cases), "cases")
+
+
 def main(only=None):
-    for tag, rec in (("export_a", record_export), ("raster_a", record_raster)):
+    for tag, rec in (("export_a", record_export), ("raster_a", record_raster), ("sampler_a", record_sampler)):
         if only and tag in only:
             rec()
             only = [t for t in only if t != tag]

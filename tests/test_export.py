@@ -103,3 +103,19 @@ def test_cuda_rasteriser_empty_point_cloud_and_larger_image():
     got = endo_b200.utils.get_torch_training_data(*args)
     for key, o, wnt in zip(RASTER_KEYS, got, want):
         assert np.array_equal(o, wnt), key
+
+
+# ------------------------------------------------------------------ pair sampler (utils.generating_pos_and_increment, utils.py:410-438)
+def test_pair_sampler_draws_the_reference_pairs():
+    """Host logic: with the same `random` seed the mirror returns what the unmodified reference function returned (fixture)."""
+    import random
+    g = load_golden("sampler_a")
+    branches = set()
+    for (n, lo, hi, idx, seed), (pos, inc) in zip(g["cases"].tolist(), g["out"].tolist()):
+        views = list(range(100, 100 + 3 * n, 3))
+        random.seed(1000 * seed + idx)
+        got = endo_b200.utils.generating_pos_and_increment(idx, views, [lo, hi])
+        assert got == [pos, inc], (n, lo, hi, idx, seed, got, pos, inc)
+        assert 0 <= pos + inc < n
+        branches.add("start" if pos < min(lo, n // 2 if n <= 2 * lo else lo) else ("end" if inc < 0 else "fwd"))
+    assert len(g["cases"]) > 200 and len(branches) == 3
