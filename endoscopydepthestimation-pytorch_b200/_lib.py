@@ -7,7 +7,7 @@ raises on a non-CUDA tensor or a non-zero status code.
 import ctypes
 import os
 import threading
-from ctypes import c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 import torch
 
@@ -64,6 +64,7 @@ _SIGNATURES = {
                                             c_float, _P, _P, _P, c_size_t, _P]),
     "endo_rasterize_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "endo_rasterize_pair": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "endo_resize_crop_u8": (c_int, [_P, c_int, c_int, c_double, c_int, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "endo_tma_probe": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "endo_sgd_workspace_bytes": (c_size_t, [c_longlong]),
     "endo_sgd_clip_step": (c_int, [_P, _P, _P, c_longlong, c_float, c_float, c_float, c_int, _P, _P, _P, c_size_t,

@@ -208,3 +208,75 @@ extern "C" int endo_rasterize_pair(const double* points, const double* projectio
     ENDO_CHECK_LAUNCH();
     return ENDO_OK;
 }
+
+// =====================================================================================================
+// Image side of the input pipeline ("next" row N3): utils.get_pair_color_imgs (utils.py:441-457) after the JPEG decode --
+// cv2.resize(fx = fy = 1/downsampling, INTER_LINEAR, 8-bit) -> crop -> BGR2RGB -- and the normalisation dataset.py:148,446-453
+// applies (albumentations Normalize(0.5, 0.5, 255) + img_to_tensor).  The reference does this per sample on DataLoader workers
+// from 1080x1920 frames; here one thread produces one output pixel straight from the decoded frame in HBM, bit for bit like
+// cv::resize's fixed-point bilinear filter (11-bit coefficients, int horizontal pass, truncating vertical pass; see
+// oracle/pipeline.py for the restatement and its pinning against cv2 itself).  This file is compiled with -fmad=false: the
+// source coordinate (d + 0.5) * scale - 0.5 must round like the two separate double operations cv::resize performs.
+// =====================================================================================================
+namespace endo {
+
+struct ResizeArgs {
+    const unsigned char* src; int sh, sw;            // decoded frame, HWC, 3 channels (BGR as cv2.imread returns it)
+    double scale_x, scale_y;                         // source pixels per destination pixel (= downsampling factor)
+    int start_h, start_w, H, W;                      // crop origin inside the resized image, output size
+    int swap_rb;                                     // 1: BGR -> RGB
+    unsigned char* out_u8;                           // [H][W][3] or nullptr
+    float* out_norm;                                 // [3][H][W] float32, (v - 127.5) * (1 / 127.5), or nullptr
+};
+
+__global__ void __launch_bounds__(256) resize_crop_kernel(const ResizeArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.H * A.W) return;
+    const int y = i / A.W, x = i - y * A.W;
+    const int dx = x + A.start_w, dy = y + A.start_h;
+    // horizontal: fractional weight AND position clamp at the borders
+    float fx = (float)(((double)dx + 0.5) * A.scale_x - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= (float)sx;
+    if (sx < 0) { fx = 0.f; sx = 0; }
+    if (sx >= A.sw - 1) { fx = 0.f; sx = A.sw - 1; }
+    const int sx1 = min(sx + 1, A.sw - 1);
+    const int a1 = __float2int_rn(fx * 2048.f), a0 = __float2int_rn((1.f - fx) * 2048.f);
+    // vertical: only the row indices clamp, the weights stay
+    float fy = (float)(((double)dy + 0.5) * A.scale_y - 0.5);
+    const int sy = (int)floorf(fy);
+    fy -= (float)sy;
+    const int b1 = __float2int_rn(fy * 2048.f), b0 = __float2int_rn((1.f - fy) * 2048.f);
+    const int y0 = min(max(sy, 0), A.sh - 1), y1 = min(max(sy + 1, 0), A.sh - 1);
+    const unsigned char* r0 = A.src + (size_t)y0 * A.sw * 3;
+    const unsigned char* r1 = A.src + (size_t)y1 * A.sw * 3;
+    const float mean = 0.5f * 255.0f, den = 1.0f / (0.5f * 255.0f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int s0 = (int)r0[sx * 3 + c] * a0 + (int)r0[sx1 * 3 + c] * a1;
+        const int s1 = (int)r1[sx * 3 + c] * a0 + (int)r1[sx1 * 3 + c] * a1;
+        const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+        const int oc = A.swap_rb ? 2 - c : c;
+        if (A.out_u8) A.out_u8[(size_t)i * 3 + oc] = (unsigned char)v;
+        if (A.out_norm) A.out_norm[(size_t)oc * A.H * A.W + i] = ((float)v - mean) * den;
+    }
+}
+
+}  // namespace endo
+
+extern "C" int endo_resize_crop_u8(const unsigned char* src_bgr, int src_h, int src_w, double downsampling, int start_h, int end_h,
+                                   int start_w, int end_w, int swap_rb, unsigned char* out_u8, float* out_norm, endo_stream_t stream) {
+    if (src_h <= 0 || src_w <= 0 || !(downsampling > 0.0)) return ENDO_ERR_BAD_SHAPE;
+    if (!src_bgr || (!out_u8 && !out_norm)) return ENDO_ERR_BAD_POINTER;
+    const double f = 1.0 / downsampling;                     // fx = fy of cv2.resize(img, (0, 0), fx, fy)
+    const int dh = (int)nearbyint(src_h * f), dw = (int)nearbyint(src_w * f);       // saturate_cast<int>: round half to even
+    if (start_h < 0 || start_w < 0 || end_h <= start_h || end_w <= start_w || end_h > dh || end_w > dw) return ENDO_ERR_BAD_SHAPE;
+    // cv::resize switches to its INTER_AREA fast path at a factor of exactly 2; it equals the bilinear formula except on the
+    // last row / column of odd-sized sources
+    if (fabs(1.0 / f - 2.0) < 2.220446049250313e-16 && ((src_h | src_w) & 1)) return ENDO_ERR_CONFIG;
+    endo::ResizeArgs A{src_bgr, src_h, src_w, 1.0 / f, 1.0 / f, start_h, start_w, end_h - start_h, end_w - start_w, swap_rb, out_u8, out_norm};
+    const long long n = (long long)A.H * A.W;
+    endo::resize_crop_kernel<<<endo::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(A);
+    ENDO_CHECK_LAUNCH();
+    return ENDO_OK;
+}

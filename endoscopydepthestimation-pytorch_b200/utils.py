@@ -99,3 +99,45 @@ def generating_pos_and_increment(idx, visible_view_indexes, adjacent_range):
     if random.randint(0, 1) == 1:        # interior: a coin decides the direction
         return [pos, random.randint(lo, forward_room)]
     return [pos, -random.randint(lo, backward_room)]
+
+
+def resize_crop_color(img_bgr, start_h, end_h, start_w, end_w, downsampling_factor, rgb_mode="rgb", normalize=False, device=None):
+    """One decoded frame (HxWx3 uint8, BGR as cv2.imread returns it; numpy or a CUDA tensor) -> cv2.resize(fx = fy =
+    1/downsampling_factor) -> crop -> BGR2RGB (rgb_mode == "rgb"), bit for bit like utils.py:446-452, on the GPU.  Returns a
+    CUDA uint8 tensor [H, W, 3]; with normalize=True also the float32 [3, H, W] tensor of dataset.py:148,446-453."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("endo_b200.utils.resize_crop_color runs on a CUDA device only (there is no CPU fallback)")
+    if device is None:
+        device = img_bgr.device if isinstance(img_bgr, torch.Tensor) and img_bgr.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    src = img_bgr if isinstance(img_bgr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img_bgr))
+    if src.dtype != torch.uint8 or src.dim() != 3 or src.shape[2] != 3:
+        raise RuntimeError("expected an HxWx3 uint8 image, got " + str(tuple(src.shape)) + " " + str(src.dtype))
+    src = src.to(device).contiguous()
+    h, w = int(end_h) - int(start_h), int(end_w) - int(start_w)
+    if h <= 0 or w <= 0:
+        raise RuntimeError("empty crop")
+    out = torch.empty((h, w, 3), dtype=torch.uint8, device=device)
+    norm = torch.empty((3, h, w), dtype=torch.float32, device=device) if normalize else None
+    with torch.cuda.device(device):
+        L.check(L.lib().endo_resize_crop_u8(src.data_ptr(), src.shape[0], src.shape[1], float(downsampling_factor), int(start_h), int(end_h),
+                                            int(start_w), int(end_w), 1 if rgb_mode == "rgb" else 0, out.data_ptr(), L.ptr(norm),
+                                            L.stream_ptr(device)), "resize_crop_u8")
+    return (out, norm) if normalize else out
+
+
+def get_pair_color_imgs(prefix_seq, pair_indexes, start_h, end_h, start_w, end_w, downsampling_factor, is_hsv, rgb_mode,
+                        device=None, return_tensor=False):
+    """`utils.get_pair_color_imgs` (utils.py:441-457), same arguments, same uint8 [2, H, W, 3] result: the JPEG decode stays
+    cv2.imread on the host (no device decoder in this image), resize + crop + colour order run on the GPU."""
+    if is_hsv:
+        raise NotImplementedError("is_hsv=True (cv2.COLOR_BGR2HSV_FULL) is not implemented")
+    import cv2
+    from pathlib import Path
+    imgs = []
+    for i in pair_indexes:
+        img = cv2.imread(str(Path(prefix_seq) / "{:08d}.jpg".format(i)))
+        if img is None:
+            raise RuntimeError("cannot read " + str(Path(prefix_seq) / "{:08d}.jpg".format(i)))
+        imgs.append(resize_crop_color(img, start_h, end_h, start_w, end_w, downsampling_factor, rgb_mode, device=device))
+    out = torch.stack(imgs)
+    return out if return_tensor else out.cpu().numpy()

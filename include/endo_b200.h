@@ -255,6 +255,17 @@ int endo_rasterize_pair(const double* points, const double* projections, const d
                         const float* clean, const unsigned char* mask_boundary, int M, int H, int W, float* depth_mask,
                         float* depth, float* flow_mask, float* flow, void* ws, size_t ws_bytes, endo_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * utils.get_pair_color_imgs after the JPEG decode (utils.py:446-452) + dataset.py:148,446-453's normalisation, one image:
+ * src_bgr[src_h][src_w][3] uint8 (what cv2.imread returns) -> cv2.resize(fx = fy = 1/downsampling, INTER_LINEAR) bit for bit
+ * -> crop [start_h:end_h, start_w:end_w] -> optional BGR->RGB -> out_u8[H][W][3] and / or out_norm[3][H][W] float32
+ * ((v - 127.5) * (1/127.5): albumentations Normalize(0.5, 0.5, 255) + img_to_tensor).  Either output may be NULL.
+ * ENDO_ERR_BAD_SHAPE: crop outside the resized image; ENDO_ERR_CONFIG: factor 2 on an odd-sized image (cv::resize takes a
+ * different border path there).
+ * ---------------------------------------------------------------------------------------------- */
+int endo_resize_crop_u8(const unsigned char* src_bgr, int src_h, int src_w, double downsampling, int start_h, int end_h,
+                        int start_w, int end_w, int swap_rb, unsigned char* out_u8, float* out_norm, endo_stream_t stream);
+
 /* TMA bring-up probe (tests only): out[box_h][box_w][box_c] = the box of the NHWC fp32 buffer src[B][H][W][C] at channel c0,
  * column x0, row y0 (either may be negative or overhang: zero fill) of image b, loaded by one cp.async.bulk.tensor. */
 int endo_tma_probe(const float* src, int B, int H, int W, int C, int box_c, int box_w, int box_h, int c0, int x0,

@@ -20,4 +20,4 @@ pinned against outputs of the reference itself: `oracle/gen_golden.py` imports t
 shims of SURVEY.md §8c) on seeded inputs and commits the results under `tests/golden/`;
 `tests/test_oracle_golden.py` checks this restatement against those fixtures.
 """
-from . import net, geometry, losses, step, export  # noqa: F401
+from . import net, geometry, losses, step, export, pipeline  # noqa: F401

@@ -42,7 +42,13 @@ def reference_function(name, path=REF + "/utils.py"):
     src = open(path).read()
     node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
     import random
-    ns = {"np": np, "random": random}
+    from pathlib import Path
+    ns = {"np": np, "random": random, "Path": Path}
+    try:
+        import cv2
+        ns["cv2"] = cv2
+    except ImportError:
+        pass
     exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     return ns[name]
 
@@ -98,8 +104,38 @@ def record_sampler():
     print("sampler_a", len(cases), "cases")
 
 
+def record_pipeline():
+    """utils.get_pair_color_imgs (utils.py:441-457) on two synthetic JPEG frames written to a temporary sequence folder: the
+    fixture keeps the JPEG bytes, the frames as cv2 decoded them here, and the reference's outputs for downsampling 4 / 3 / 2.5
+    in both colour orders."""
+    import tempfile
+    import cv2
+    fn = reference_function("get_pair_color_imgs")
+    rs = np.random.RandomState(123)
+    h, w = 216, 384
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for k, idx in enumerate((17, 23)):
+            base = np.stack([128 + 100 * np.sin(xx / (23.0 + 5 * k) + c) * np.cos(yy / (31.0 - 3 * k) + 2 * c) for c in range(3)], -1)
+            img = np.clip(base + rs.randn(h, w, 3) * 6.0, 0, 255).astype(np.uint8)
+            cv2.imwrite(os.path.join(tmp, "{:08d}.jpg".format(idx)), img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+            out[f"jpeg_{k}"] = np.frombuffer(open(os.path.join(tmp, "{:08d}.jpg".format(idx)), "rb").read(), dtype=np.uint8)
+            out[f"decoded_{k}"] = cv2.imread(os.path.join(tmp, "{:08d}.jpg".format(idx)))
+        cases = []
+        for ds, crop in ((4.0, (3, 51, 4, 92)), (3.0, (0, 72, 0, 128)), (2.5, (5, 85, 2, 150))):
+            for mode in ("rgb", "bgr"):
+                tag = f"ds{ds}_{mode}"
+                out["out_" + tag] = fn(tmp, [17, 23], crop[0], crop[1], crop[2], crop[3], ds, False, mode)
+                cases.append((ds, *crop, 1 if mode == "rgb" else 0))
+        out["cases"] = np.array(cases, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "pipeline_a.npz"), **out)
+    print("pipeline_a", {k: v.shape for k, v in out.items()})
+
+
 def main(only=None):
-    for tag, rec in (("export_a", record_export), ("raster_a", record_raster), ("sampler_a", record_sampler)):
+    for tag, rec in (("export_a", record_export), ("raster_a", record_raster), ("sampler_a", record_sampler),
+                     ("pipeline_a", record_pipeline)):
         if only and tag in only:
             rec()
             only = [t for t in only if t != tag]
