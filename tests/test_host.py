@@ -63,6 +63,15 @@ def test_shape_validation_and_sizes():
     assert lib.endo_net_backward_scratch_bytes(_cfg(model), 2, 64, 96) > 0
     per_img = lib.endo_net_activation_bytes(_cfg(model), 1, 256, 320)
     assert 80e6 < per_img < 200e6         # write-once activations: ~0.9e8 B/image vs 7.2e8 layer-by-layer
+    # backward scratch of the benchmark shape (16 images of 256x320): gradient buffers of the six levels (channel totals 192 /
+    # 240 / 288 / 336 / 384 / 336: [up 48 | in | down-new 48 | up-new 48], the bottleneck has no up part) + the bf16 operand planes of the weight-gradient GEMMs: two sets of
+    # activation planes for the widest full-resolution layer (Cin 180 -> 184) and of 48-channel gradient planes, plus one routed-
+    # gradient and one activation plane set per TransitionDown (96 / 144 / 192 / 240 / 288 channels); small tables on top
+    px = [16 * (256 >> l) * (320 >> l) for l in range(6)]
+    grads = 4 * sum(p * c for p, c in zip(px, (192, 240, 288, 336, 384, 336)))
+    planes = 2 * (2 * px[0] * 184 + 2 * px[0] * 48) + sum(2 * 2 * p * c for p, c in zip(px, (96, 144, 192, 240, 288)))
+    total = lib.endo_net_backward_scratch_bytes(_cfg(model), 16, 256, 320)
+    assert grads + planes < total < grads + planes + 64e6, (total, grads, planes)
 
 
 def test_no_cpu_fallback():
